@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — EDM per-timestep bias engine on B200: CV bias+force evaluations/s and hills/s.
+
+Workload (BASELINE.json configs[1], "c2_pair_rdf"): 1-D pair-distance EDM, bias box 1.68-5.0,
+spacing 0.00025 (13 281 grid points), sigma 0.025, hill_density 250, threshold tempering;
+10^6 synthetic atoms per GPU, uniform in a periodic cube at number density 0.1, every pair with
+minimum-image distance < 5.0 evaluated once (about 2.6e7 pairs per GPU per step).
+
+One step = one MD step of fix edm_pair with hill addition: cell binning, pair search, bias
+energy + force per pair with force scatter, two hill proposals per pair, selection, (N > 1:
+all-gather of the accepted hills), height scaling, bias_per_step limiter, deposit.
+
+  value  evaluations/s over all ranks with positions and forces already resident in HBM
+  e2e    the same step through the host-buffer C ABI call (edm_pair_step_cells): positions and
+         forces copied host->device from pinned memory and forces + result copied back, every step
+  --impl reference   the reference's own CPU code (oracle/_ref, unmodified lib/ compiled here) on the
+         host cores: P independent single-rank instances, one per core, each on a shard of the
+         pairs with a full grid replica (the reference's scaling model for a replicated grid)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "electronic-dance-music_b200", "python"))
+
+EDM_TEXT = ("tempering 1\nglobal_tempering 2.0\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.1\n"
+            "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025\n")
+N_ATOMS = 1_000_000
+DENSITY = 0.1
+CUTOFF = 5.0
+TEMPERATURE, BOLTZ = 300.0, 0.0019872
+PREWARM_HILLS = 20000        # hills deposited before timing so the evaluated bias is not flat
+DEPOSIT_BATCH = 1 << 20      # hills in the batched-deposit throughput measurement
+HILL_CAP = 4096              # records per rank in the exchange block
+ALG_BYTES_PER_ATOM = 76      # 24 B x + 48 B f read-modify-write + 4 B type, per atom per step
+
+
+def write_edm(tmpdir):
+    f = os.path.join(tmpdir, "c2.edm")
+    with open(f, "w") as fh:
+        fh.write(EDM_TEXT + "hills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmpdir, tmpdir))
+    return f
+
+
+def prewarm_hills(rng):
+    c = rng.uniform(1.68, 5.0, PREWARM_HILLS)
+    h = np.full(PREWARM_HILLS, 0.02 / 250)
+    return c, h
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            p = [t.strip() for t in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+
+def _cpu_worker(args):
+    """One single-rank reference instance on one core: evaluates its shard of pair distances."""
+    kind, edm_file, r, warm_c, warm_h, repeats, core = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    b = pyoracle.Bias(kind, edm_file)
+    b.log_enable(False)
+    b.setup(TEMPERATURE, BOLTZ)
+    b.subdivide([1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    b.gauss.add_values(warm_c[:2000], warm_h[:2000])
+    return b.time_pair_eval(r, repeats)
+
+
+def cpu_pair_rate(kind, edm_file, r, warm, cores, repeats):
+    """evaluations/s of the reference's update_force over `r`, sharded over `cores` processes."""
+    import multiprocessing as mp
+    shards = np.array_split(r, cores)
+    avail = sorted(os.sched_getaffinity(0))
+    jobs = [(kind, edm_file, np.ascontiguousarray(s), warm[0], warm[1], repeats, avail[i % len(avail)])
+            for i, s in enumerate(shards)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        times = pool.map(_cpu_worker, jobs)
+        wall = time.perf_counter() - t0
+    # every instance runs concurrently; the job is done when the slowest shard is
+    return r.size * repeats / max(times), max(times), wall
+
+
+def cpu_hill_rate(kind, n_hills, warm_rng):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    g = pyoracle.GaussGrid(kind, 1, [1.68], [5.0], [0.00025], [0], 1, [0.025])
+    c = warm_rng.uniform(1.68, 5.0, n_hills)
+    h = np.full(n_hills, 1e-6)
+    t = g.time_add_values(c, h)
+    return n_hills / t
+
+
+def oracle_kind():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    if pyoracle.available("ref"):
+        return "ref", "reference"
+    if not pyoracle.available("port"):
+        pyoracle.build(("port",))
+    return "port", "port"
+
+
+def sample_pair_distances(rng, n):
+    """r of uniformly distributed pairs inside the cutoff sphere: p(r) ~ r^2 on [0, CUTOFF)."""
+    return CUTOFF * rng.uniform(0, 1, n) ** (1.0 / 3.0)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    kind, kind_name = oracle_kind()
+    tmp = tempfile.mkdtemp()
+    edm_file = write_edm(tmp)
+    rng = np.random.default_rng(1234 + 1)
+    warm = prewarm_hills(rng)
+    cores = len(os.sched_getaffinity(0))
+    sample = 2_600_000 * cores                # bounded sample: 2.6e6 pair distances per instance per step
+    r = sample_pair_distances(rng, sample)
+    for _ in range(args.warmup):
+        cpu_pair_rate(kind, edm_file, r[: sample // 10], warm, cores, 1)
+    rates, tms = [], []
+    for _ in range(args.steps):
+        rate, t, _ = cpu_pair_rate(kind, edm_file, r, warm, cores, 1)
+        rates.append(rate)
+        tms.append(t)
+    value = sample * args.steps / sum(tms)
+    hills = cpu_hill_rate(kind, 20000, rng)
+    out = {
+        "impl": "reference", "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(tms) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "c2_pair_rdf", "atoms_per_gpu": N_ATOMS, "cutoff": CUTOFF,
+                   "step": "bounded sample: %d pair evaluations per step" % sample},
+        "hills_per_s": hills,
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind_name,
+                         "sample": "%d pair distances (p(r)~r^2, r<5) per step through EDMBias::update_force, "
+                                   "%d single-rank instances pinned one per core; hills/s: 20000 add_value calls on "
+                                   "one core" % (sample, cores),
+                         "hills_per_s_1core": hills},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------ GPU arm
+
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import ctypes as C
+    import edm_b200 as edm
+
+    if edm.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = edm.lib()
+    tmp = tempfile.mkdtemp()
+    edm_file = write_edm(tmp)
+    bias = edm.bias_from_edm(edm_file, TEMPERATURE, BOLTZ, [1.68], [5.0], [1.68], [5.0], [0], [0.0], device=local_rank)
+    warm_rng = np.random.default_rng(1234 + 1)
+    warm = prewarm_hills(warm_rng)          # same hills on every rank: replicas start identical
+    bias.bias_grid.add_values(*warm)
+    edm.check(L.edm_bias_set_profiling(bias.h, 1))
+
+    box_len = (N_ATOMS / DENSITY) ** (1.0 / 3.0)
+    box = np.array([box_len] * 3)
+    rng = np.random.default_rng(1234 + 1 + 1000 * rank)
+    n_sets = 3                               # rotate position sets; L2 is flushed between steps anyway
+    xs_host = [torch.from_numpy(rng.uniform(0, box_len, size=(N_ATOMS, 3))).pin_memory() for _ in range(n_sets)]
+    xs_dev = [x.cuda(non_blocking=True) for x in xs_host]
+    f_dev = torch.zeros((N_ATOMS, 3), dtype=torch.float64, device="cuda")
+    f_host = torch.zeros((N_ATOMS, 3), dtype=torch.float64).pin_memory()
+    energy_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    blk_doubles = L.edm_hill_block_doubles(1, HILL_CAP)
+    block = torch.zeros(blk_doubles, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(blk_doubles * world, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    boxp = box.ctypes.data_as(C.POINTER(C.c_double))
+    expected_pairs = N_ATOMS * (4.0 / 3.0) * np.pi * CUTOFF ** 3 * DENSITY / 2
+    est_local = int(2 * expected_pairs)
+    seed = 20261018
+
+    def step_resident(step):
+        x = xs_dev[step % n_sets]
+        est_total = est_local * world
+        edm.check(L.edm_pair_select_cells_dev(bias.h, N_ATOMS, x.data_ptr(), f_dev.data_ptr(), None, 0, 0, boxp,
+                                              CUTOFF, est_total, seed + rank, step, energy_dev.data_ptr(), stream))
+        edm.check(L.edm_bias_hills_pack_dev(bias.h, block.data_ptr(), HILL_CAP, stream))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, block)
+            src = gathered
+        else:
+            src = block
+        edm.check(L.edm_bias_hills_commit_dev(bias.h, src.data_ptr(), world, HILL_CAP, est_total, stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_no = 0
+    for _ in range(max(args.warmup, 3)):
+        step_resident(step_no)
+        step_no += 1
+    barrier()
+    st0 = bias.state()
+    launches0 = edm.launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pair_ms = []
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                         # evict L2 between timed iterations (outside the event pair)
+        ev[k][0].record()
+        step_resident(step_no)
+        ev[k][1].record()
+        step_no += 1
+        ms = C.c_double(0)
+        edm.check(L.edm_bias_profile_ms(bias.h, C.byref(ms)))   # waits for this step's pair kernel
+        pair_ms.append(ms.value)
+    barrier()
+    clk = clocks.stop()
+    launches = edm.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    st1 = bias.state()
+    hills_timed = len(bias.log())             # events logged since creation (prewarm deposits are not logged)
+
+    # ---- e2e through the host-buffer C ABI
+    def step_e2e(step):
+        xh = xs_host[step % n_sets]
+        r = edm.PairResult()
+        edm.check(L.edm_pair_step_cells(bias.h, N_ATOMS, xh.data_ptr(), f_host.data_ptr(), None, 0, 0, boxp, CUTOFF,
+                                        1, est_local * world, seed + rank, step, C.byref(r)))
+        return r
+
+    r0 = step_e2e(step_no)
+    step_no += 1
+    pairs_per_step = [0] * n_sets
+    for s in range(n_sets):
+        rr = step_e2e(step_no)
+        pairs_per_step[step_no % n_sets] = rr.n_pairs
+        step_no += 1
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    e2e_pairs = 0
+    for k in range(e2e_steps):
+        rr = step_e2e(step_no)
+        e2e_pairs += rr.n_pairs
+        step_no += 1
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    pairs_timed = sum(pairs_per_step[(st0["steps"] + k) % n_sets] for k in range(args.steps))
+
+    # ---- batched deposit throughput (hills/s) on a scratch replica of the bias grid
+    dep_grid = edm.GaussGrid(1, [1.68], [5.0], [0.00025], [0], 1, [0.025], device=local_rank)
+    drng = np.random.default_rng(99 + rank)
+    dc = torch.from_numpy(drng.uniform(1.68, 5.0, DEPOSIT_BATCH)).cuda()
+    dh = torch.full((DEPOSIT_BATCH,), 1e-6, dtype=torch.float64, device="cuda")
+    dba = torch.zeros(DEPOSIT_BATCH, dtype=torch.float64, device="cuda")
+    dep_launch0 = edm.launch_count()
+    for _ in range(2):
+        edm.check(L.edm_gauss_deposit_dev(dep_grid.h, DEPOSIT_BATCH, dc.data_ptr(), dh.data_ptr(), dba.data_ptr(), stream))
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dep_reps = 3
+    d0.record()
+    for _ in range(dep_reps):
+        edm.check(L.edm_gauss_deposit_dev(dep_grid.h, DEPOSIT_BATCH, dc.data_ptr(), dh.data_ptr(), dba.data_ptr(), stream))
+    d1.record()
+    torch.cuda.synchronize()
+    dep_ms = d0.elapsed_time(d1) / dep_reps
+    hills_per_s = DEPOSIT_BATCH / (dep_ms * 1e-3)
+
+    # ---- reduce over ranks: max time, summed work
+    stats = torch.tensor([total_ms, e2e_s, float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)],
+                         dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s = float(mx[0]), float(mx[1])
+        pairs_all, e2e_pairs_all, hills_all, launches_all = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[5])
+    else:
+        pairs_all, e2e_pairs_all, hills_all, launches_all = float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = pairs_all / (total_ms * 1e-3)
+        kernel_ms = float(np.mean(pair_ms))
+        alg_bytes = ALG_BYTES_PER_ATOM * N_ATOMS
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        st_hills = st1["steps"] - st0["steps"]
+        out = {
+            "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "c2_pair_rdf", "atoms_per_gpu": N_ATOMS, "number_density": DENSITY,
+                       "cutoff": CUTOFF, "pairs_per_gpu_per_step": pairs_per_step[0], "grid_points": 13281,
+                       "hill_density": 250, "hill_rounds_timed": st_hills,
+                       "l2": "flushed between timed steps (512 MiB memset outside the per-step CUDA-event pair)",
+                       "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
+            "hills_per_s": hills_all,
+            "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
+                      "in_situ_hill_events": int(hills_timed)},
+            "roofline": {"bound": "hbm", "kernel": "pair_cells_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "fp64-pipe bound, not HBM bound (SURVEY 8d): 2.9 B/pair of compulsory traffic"},
+            "e2e": {"value": e2e_pairs_all / e2e_s, "unit": "evals/s",
+                    "h2d_bytes_per_step": 2 * N_ATOMS * 24, "d2h_bytes_per_step": N_ATOMS * 24 + 24,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            kind, kind_name = oracle_kind()
+            cores = len(os.sched_getaffinity(0))
+            crng = np.random.default_rng(4321)
+            sample = 2_600_000 * cores
+            r = sample_pair_distances(crng, sample)
+            rate, t, _ = cpu_pair_rate(kind, edm_file, r, warm, cores, 2)
+            hills = cpu_hill_rate(kind, 20000, crng)
+            out["cpu_baseline"] = {
+                "value": rate, "unit": "evals/s", "cores": cores, "kind": kind_name,
+                "sample": "%d pair distances x2 through EDMBias::update_force on %d single-rank instances (one per "
+                          "core, full grid replica each); hills/s: 20000 GaussGrid::add_value calls on one core"
+                          % (sample, cores),
+                "hills_per_s_1core": hills}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

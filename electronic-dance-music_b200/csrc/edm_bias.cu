@@ -1,0 +1,825 @@
+// EDMBias step logic in HBM: batched force update (update_forces), candidate selection,
+// height scaling, bias_per_step limiter, overflow backlog and hill log (add_hills).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "edm_host.h"
+
+namespace edm {
+
+// ------------------------------------------------------------------ K1: update_forces
+
+// EDMBias::update_forces, lib/edm_bias.cpp:276-295: thread per atom, coalesced row loads,
+// f -= dV/dx, energy reduced per CTA in a fixed order (partials summed in CTA order afterwards).
+template <int DIM>
+__global__ void __launch_bounds__(256) forces_kernel(GridDesc g, long n, const double* __restrict__ x, long xs,
+                                                     double* __restrict__ f, long fs, const int* __restrict__ mask,
+                                                     int apply_mask, double* __restrict__ partial) {
+  __shared__ double red[33];
+  double e = 0.0;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (apply_mask >= 0 && !(mask[i] & apply_mask)) continue;
+    double xi[DIM], der[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) xi[d] = x[i * xs + d];
+    e += d_eval_point<DIM>(g, xi, der, g.b_interp != 0);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) f[i * fs + d] -= der[d];
+  }
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void sum_partials_kernel(int n, const double* __restrict__ partial, double* out) {
+  __shared__ double red[33];
+  double e = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) e += partial[i];
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+// ------------------------------------------------------------------ K4: selection
+
+// add_hill's acceptance test, lib/edm_bias.cpp:543 (T17): runiform < hill_density / est.
+// Accepted candidates are appended through one atomic counter and ordered by key afterwards, so
+// the limiter sees them in candidate order whatever the launch geometry.
+template <int DIM>
+__global__ void __launch_bounds__(256) select_kernel(long n, const double* __restrict__ x, long xs,
+                                                     const double* __restrict__ runiform, const int* __restrict__ mask,
+                                                     int apply_mask, double thresh, int accept_all, uint64_t key,
+                                                     uint64_t first_counter, BiasDev* st, HillAccepted* acc,
+                                                     long cap) {
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (apply_mask >= 0 && !(apply_mask & mask[i])) continue;
+    bool take = accept_all;
+    if (!take) {
+      double u = runiform ? runiform[i] : uniform_from_key(key, first_counter + (uint64_t)i);
+      take = u < thresh;
+    }
+    if (take) {
+      int slot = atomicAdd(&st->n_accepted, 1);
+      if (slot < cap) {
+        acc[slot].key = first_counter + (uint64_t)i;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) acc[slot].x[d] = x[i * xs + d];
+      } else {
+        st->accepted_overflow = 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K4: the hill round
+
+struct RoundParams {
+  int b_tempering, b_targeting;
+  double global_tempering, bias_factor, boltzmann_factor;
+  double hill_prefactor, bias_per_step, hill_density, expected_target, total_volume;
+  long long est_hill_count;
+  long accepted_cap, log_cap;
+};
+
+// One hill, deposited by the whole CTA with plain read-modify-writes (one hill at a time, so no
+// two threads touch the same point unless a periodic window revisits it; then fp64 atomics, whose
+// operands are equal, keep the result order-independent).  Returns add_value's integral to all.
+template <int DIM>
+__device__ double cta_deposit(const GridDesc& g, const double* x0, double h, double* red, int* sflag) {
+  constexpr int W = RecW<DIM>::value;
+  HillGeom<DIM> hg;
+  if (!d_hill_prepare<DIM>(g, x0, hg)) return 0.0;
+  long long total = 1;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) total *= (2 * g.minisize[d] + 1);
+  double ba = 0.0;
+  bool dirty = false;
+  for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+    int idx[DIM];
+    long long lin;
+    if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
+    double etot, force[DIM];
+    bool cnz;
+    if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
+    double add = h * etot;
+    double* r = g.rec + lin * W;
+    if (g.dup_possible) {
+      atomicAdd(r, add);
+#pragma unroll
+      for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
+    } else {
+      r[0] += add;
+#pragma unroll
+      for (int d = 0; d < DIM; d++) r[1 + d] += h * force[d];
+    }
+    ba += add * g.vol_element;
+    dirty |= cnz;
+  }
+  if (threadIdx.x == 0) *sflag = 0;
+  double tot = block_sum(ba, red);  // contains __syncthreads: record writes are visible CTA-wide after it
+  if (dirty) *sflag = 1;
+  __syncthreads();
+  if (*sflag) {  // duplicate_boundary, lib/gaussian_grid.h:365-368
+    for (int k = threadIdx.x; k < g.n_dup; k += blockDim.x)
+      g.rec[g.dup_pairs[2 * k] * W] = g.rec[g.dup_pairs[2 * k + 1] * W];
+  }
+  __syncthreads();
+  return tot;
+}
+
+// output_hill, lib/edm_bias.cpp:586-612 (thread 0 only)
+template <int DIM>
+__device__ void log_event(BiasDev* st, const GridDesc& hist, edm_hill_event_t* log, long log_cap, const double* pos,
+                          double height, double bias_added, int type, double total_volume) {
+  if (st->log_n < log_cap) {
+    edm_hill_event_t& e = log[st->log_n++];
+    e.steps = st->steps;
+    e.type = type;
+    e.hills_added = st->hills_added;
+    for (int d = 0; d < 3; d++) e.pos[d] = d < DIM ? pos[d] : 0.0;
+    e.height = height;
+    e.bias_added = bias_added;
+    e.cum_over_vol = st->cum_bias / total_volume;
+  } else {
+    st->log_dropped++;
+  }
+  // histogram bump, lib/grid.h:370-385 on cv_hist_ (T21)
+  double v = (type == 'b' || type == 'h' || type == 'n') ? 1.0 : ((type == 'u' || type == 'v') ? -1.0 : 0.0);
+  if (v != 0.0 && hist.rec) {
+    bool inside = true;
+    long long lin = 0, pstride = 1;
+    for (int d = 0; d < DIM; d++) {
+      double xd = pos[d];
+      if (!hist.periodic[d] && (xd < hist.min[d] || xd >= hist.upper[d])) inside = false;
+      if (hist.periodic[d]) xd = d_wrap(xd, hist.min[d], hist.len[d]);
+      long long idx = (long long)floor(__ddiv_rn(__dsub_rn(xd, hist.min[d]), hist.dx[d]));
+      idx = idx < 0 ? 0 : (idx > hist.n[d] - 1 ? hist.n[d] - 1 : idx);
+      lin += idx * pstride;
+      pstride *= hist.n[d];
+    }
+    if (inside) hist.rec[lin * hist.rec_w] += v;
+  }
+}
+
+// Orders the accepted candidates by key (= candidate order).  Keys are unique.  Rank sort for
+// the usual few hundred entries, bitonic network in global memory beyond that.
+__device__ void cta_sort_accepted(HillAccepted* a, HillAccepted* tmp, int n) {
+  if (n <= 1) return;
+  if (n <= 4096) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      unsigned long long k = a[i].key;
+      int rank = 0;
+      for (int j = 0; j < n; j++) rank += (a[j].key < k);
+      tmp[rank] = a[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
+    return;
+  }
+  // bitonic network over np2 real slots: the buffer capacity is a power of two (ensure_accepted),
+  // the tail is padded with maximal keys that sort to the end
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = n + threadIdx.x; i < np2; i += blockDim.x) a[i].key = ~0ULL;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          bool up = ((i & k) == 0);
+          unsigned long long ki = a[i].key, kl = a[l].key;
+          if ((ki > kl) == up && ki != kl) {
+            HillAccepted t = a[i];
+            a[i] = a[l];
+            a[l] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// pre_add_hill -> add_hill... -> post_add_hill for one round, in the reference's order
+// (lib/edm_bias.cpp:413-442, 528-563, 444-526, 313-380, 565-583).  A single CTA walks the
+// sequence; the work inside each step (a hill's window, the sort) is spread over its threads.
+// Sequential on purpose: with local well-tempering hill k's height reads the bias left by hills
+// < k, and the limiter is a running sum with an undo ("Hard parts").
+template <int DIM>
+__global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc hist, GridDesc target,
+                                                          RoundParams prm, BiasDev* st, HillAccepted* acc,
+                                                          HillAccepted* acc_tmp, edm_hill_event_t* log) {
+  __shared__ double red[33];
+  __shared__ int sflag;
+  __shared__ double s_pos[3];
+  __shared__ double s_h;
+  __shared__ int s_go;
+  __shared__ double s_prefactor;
+  const int W1 = DIM + 1;
+  const bool t0 = threadIdx.x == 0;
+  const double bps = prm.bias_per_step;
+
+  // ---- pre_add_hill
+  if (t0) {
+    double pf = prm.hill_prefactor;
+    if (prm.global_tempering > 0) {  // T15: threshold tempering
+      double avg = st->cum_bias / prm.total_volume;
+      if (avg >= prm.global_tempering)
+        pf *= exp(-(avg - prm.global_tempering) /
+                  (prm.global_tempering * (prm.bias_factor - 1) * prm.boltzmann_factor));
+    }
+    s_prefactor = pf;
+    st->temp_hill_cum = 0.0;
+    st->hills_added = 0;
+  }
+  __syncthreads();
+
+  // ---- flush_bias_buffer(bias_per_step)
+  double drained = 0.0;  // meaningful on thread 0
+  while (true) {
+    if (t0) {
+      s_go = (st->left < st->right) ? 1 : 0;
+      if (s_go) {
+        const double* slot = &st->overflow[st->left * W1];
+        for (int d = 0; d < DIM; d++) s_pos[d] = slot[d];
+        s_h = slot[DIM];
+      }
+    }
+    __syncthreads();
+    if (!s_go) break;
+    double pos[DIM];
+    for (int d = 0; d < DIM; d++) pos[d] = s_pos[d];
+    double h = s_h;
+    double temp = cta_deposit<DIM>(bias, pos, h, red, &sflag);
+    if (t0) {
+      st->hills_added++;
+      drained += temp;
+      log_event<DIM>(st, hist, log, prm.log_cap, pos, h, temp, 'b', prm.total_volume);
+      s_go = 0;
+      if (drained > bps) {
+        double hh = fmax(bps - drained, -h);  // T20
+        st->overflow[st->left * W1 + DIM] = -hh;
+        s_h = hh;
+        s_go = 1;
+      }
+    }
+    __syncthreads();
+    if (s_go) {
+      double hh = s_h;
+      double t2 = cta_deposit<DIM>(bias, pos, hh, red, &sflag);
+      if (t0) {
+        log_event<DIM>(st, hist, log, prm.log_cap, pos, hh, t2, 'v', prm.total_volume);
+        st->hills_added++;
+        drained += t2;
+      }
+      break;  // uniform: s_go is shared
+    }
+    if (t0) st->left++;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (t0) {
+    if (st->left == st->right) st->left = st->right = 0;
+    st->temp_hill_cum += drained;
+    st->skip = (st->left == 0 && st->right == 0) ? 0 : 1;  // T18
+  }
+  __syncthreads();
+
+  // ---- add_hill for every accepted candidate, in candidate order
+  int nacc = st->n_accepted;
+  if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
+  if (!st->skip && nacc > 0) {
+    cta_sort_accepted(acc, acc_tmp, nacc);
+    for (int k = 0; k < nacc; k++) {
+      double pos[DIM];
+      for (int d = 0; d < DIM; d++) pos[d] = acc[k].x[d];
+      if (t0) {
+        double this_h = s_prefactor;
+        if (prm.b_targeting) this_h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
+        if (prm.b_tempering && prm.global_tempering < 0)  // T15: local well-tempering
+          this_h *= exp(-d_get_value<DIM>(bias, pos) / ((prm.bias_factor - 1) * prm.boltzmann_factor));
+        if (prm.hill_density < 0)
+          this_h /= (double)(int)prm.est_hill_count;
+        else
+          this_h /= prm.hill_density;
+        this_h = fmin(this_h, 1.0 * bps);  // BIAS_CLAMP, lib/edm_bias.h:14
+        s_h = this_h;
+        s_go = (st->temp_hill_cum < bps) ? 1 : 0;
+      }
+      __syncthreads();
+      double this_h = s_h;
+      int buffer_flag = 0;  // thread 0
+      if (s_go) {
+        double ba = cta_deposit<DIM>(bias, pos, this_h, red, &sflag);
+        if (t0) {
+          st->temp_hill_cum += ba;
+          st->hills_added++;
+          log_event<DIM>(st, hist, log, prm.log_cap, pos, this_h, ba, 'h', prm.total_volume);
+          s_go = 0;
+          if (st->temp_hill_cum > bps) {
+            s_h = fmax(bps - st->temp_hill_cum, -this_h);  // T20
+            s_go = 1;
+          }
+        }
+        __syncthreads();
+        if (s_go) {
+          double temp_h = s_h;
+          double ba2 = cta_deposit<DIM>(bias, pos, temp_h, red, &sflag);
+          if (t0) {
+            st->hills_added++;
+            log_event<DIM>(st, hist, log, prm.log_cap, pos, temp_h, ba2, 'u', prm.total_volume);
+            st->temp_hill_cum += ba2;
+            buffer_flag = 1;
+            this_h = -temp_h;
+          }
+        }
+      } else if (t0) {
+        log_event<DIM>(st, hist, log, prm.log_cap, pos, 0.0, 0.0, 'h', prm.total_volume);
+        buffer_flag = 1;
+      }
+      if (t0 && buffer_flag) {  // lib/edm_bias.cpp:498-523 incl. the off-by-one push (T19)
+        if (st->right == EDM_BUFFER_SLOTS) {
+          if (st->left == 0) {
+            st->backlog_full = 1;  // the reference aborts here
+          } else {
+            st->left--;
+            for (int d = 0; d < DIM; d++) st->overflow[st->left * W1 + d] = pos[d];
+            st->overflow[st->left * W1 + DIM] = this_h;
+          }
+        } else {
+          st->right++;
+          for (int d = 0; d < DIM; d++) st->overflow[st->right * W1 + d] = pos[d];
+          st->overflow[st->right * W1 + DIM] = this_h;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // ---- post_add_hill (serial build: no exchange), update_height (T22)
+  if (t0) {
+    st->cum_bias += st->temp_hill_cum;
+    st->steps++;
+  }
+}
+
+__global__ void reset_accepted_kernel(BiasDev* st) {
+  st->n_accepted = 0;
+  st->accepted_overflow = 0;
+}
+
+// hill exchange blocks: double[0] = count, then `count` centres of DIM doubles (key order)
+template <int DIM>
+__global__ void pack_block_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* tmp, double* block, long cap) {
+  int n = st->n_accepted;
+  if (n > cap) n = (int)cap;
+  cta_sort_accepted(acc, tmp, n);
+  if (threadIdx.x == 0) block[0] = (double)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int d = 0; d < DIM; d++) block[1 + (long)i * DIM + d] = acc[i].x[d];
+}
+
+template <int DIM>
+__global__ void unpack_blocks_kernel(BiasDev* st, HillAccepted* acc, long acc_cap, const double* blocks, int nblocks,
+                                     long cap) {
+  if (blockIdx.x != 0) return;
+  __shared__ int s_off;
+  size_t bw = 1 + (size_t)cap * DIM;
+  int off = 0;
+  for (int b = 0; b < nblocks; b++) {
+    const double* blk = blocks + (size_t)b * bw;
+    int cnt = (int)blk[0];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      if (off + i < acc_cap) {
+        acc[off + i].key = (unsigned long long)(off + i);  // rank-major order is the canonical order
+        for (int d = 0; d < DIM; d++) acc[off + i].x[d] = blk[1 + (size_t)i * DIM + d];
+      }
+    }
+    off += cnt;
+  }
+  if (threadIdx.x == 0) {
+    s_off = off;
+    st->n_accepted = s_off;
+    if (off > acc_cap) st->accepted_overflow = 1;
+  }
+}
+
+}  // namespace edm
+
+using namespace edm;
+
+static RoundParams round_params(const edm_bias* b, long long est) {
+  RoundParams r;
+  const edm_bias_params_t& p = b->prm;
+  r.b_tempering = p.b_tempering;
+  r.b_targeting = p.b_targeting && b->target;
+  r.global_tempering = p.global_tempering;
+  r.bias_factor = p.bias_factor;
+  r.boltzmann_factor = p.boltzmann_factor;
+  r.hill_prefactor = p.hill_prefactor;
+  r.bias_per_step = p.bias_per_step;
+  r.hill_density = p.hill_density;
+  r.expected_target = p.expected_target;
+  r.total_volume = p.total_volume;
+  r.est_hill_count = est;
+  r.accepted_cap = b->accepted_cap;
+  r.log_cap = b->log_cap;
+  return r;
+}
+
+static int ensure_accepted(edm_bias* b, long need) {
+  if (need <= b->accepted_cap) return EDM_OK;
+  long cap = 4096;
+  while (cap < need) cap <<= 1;  // power of two: cta_sort_accepted pads in place
+  HillAccepted* p = nullptr;
+  EDM_CUDA(cudaMalloc(&p, 2 * (size_t)cap * sizeof(HillAccepted)));
+  if (b->d_accepted) cudaFree(b->d_accepted);
+  b->d_accepted = p;
+  b->accepted_cap = cap;
+  return EDM_OK;
+}
+
+int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st) {
+  count_launches(1);
+  reset_accepted_kernel<<<1, 1, 0, st>>>(b->d_state);
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+// launches the hill round over whatever sits in the accepted buffer
+int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
+  RoundParams rp = round_params(b, est);
+  GridDesc none;
+  memset(&none, 0, sizeof(none));
+  const GridDesc& hist = b->hist ? b->hist->d : none;
+  const GridDesc& target = b->target ? b->target->d : none;
+  HillAccepted* tmp = b->d_accepted + b->accepted_cap;
+  count_launches(1);
+  switch (b->prm.dim) {
+    case 1: hill_round_kernel<1><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
+    case 2: hill_round_kernel<2><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
+    default: hill_round_kernel<3><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+int edm_bias_check_round(edm_bias* b) {
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  if (hdr.backlog_full) {
+    set_error("The bias overflow buffer is full. Too many hills (lib/edm_bias.cpp:503-507)");
+    return EDM_ERR_BACKLOG_FULL;
+  }
+  if (hdr.accepted_overflow) {
+    set_error("accepted-hill buffer exhausted");
+    return EDM_ERR_CAPACITY;
+  }
+  return EDM_OK;
+}
+
+static int select_launch(edm_bias* b, long n, const double* x, long xs, const double* runiform, const int* mask,
+                         int apply_mask, long long est, uint64_t seed, uint64_t step, uint64_t first_counter,
+                         cudaStream_t st) {
+  if (n <= 0) return EDM_OK;
+  const edm_bias_params_t& p = b->prm;
+  int accept_all = p.hill_density < 0;
+  double thresh = accept_all ? 2.0 : p.hill_density / (double)(int)est;  // lib/edm_bias.cpp:543 (est is an int there)
+  uint64_t key = uniform_key(seed, step);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  count_launches(1);
+  switch (p.dim) {
+    case 1: select_kernel<1><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
+    case 2: select_kernel<2><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
+    default: select_kernel<3><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+extern "C" {
+
+int edm_bias_create(edm_bias_t** out, edm_grid_t* bias, edm_grid_t* cv_hist, edm_grid_t* target,
+                    const edm_bias_params_t* params) {
+  EDM_REQUIRE(out && bias && params, "NULL argument");
+  EDM_REQUIRE(bias->d.is_gauss && bias->d.dim == params->dim, "bias must be a GaussGrid of params->dim dimensions");
+  EDM_TRY(ensure_device(bias->device));
+  edm_bias* b = new edm_bias();
+  b->device = bias->device;
+  b->prm = *params;
+  b->bias = bias;
+  b->hist = cv_hist;
+  b->target = target;
+  *out = b;
+  EDM_CUDA(cudaMalloc(&b->d_state, sizeof(BiasDev)));
+  EDM_CUDA(cudaMemset(b->d_state, 0, sizeof(BiasDev)));  // T19: the backlog storage starts zero-filled
+  b->log_cap = 1 << 16;
+  EDM_CUDA(cudaMalloc(&b->d_log, (size_t)b->log_cap * sizeof(edm_hill_event_t)));
+  b->n_partial = 148 * 8;
+  EDM_CUDA(cudaMalloc(&b->d_energy_partial, (size_t)b->n_partial * sizeof(double)));
+  EDM_CUDA(cudaMalloc(&b->d_scalar, 8 * sizeof(double)));
+  EDM_TRY(ensure_accepted(b, 4096));
+  return EDM_OK;
+}
+
+int edm_bias_destroy(edm_bias_t* b) {
+  if (!b) return EDM_OK;
+  cudaSetDevice(b->device);
+  if (b->d_state) cudaFree(b->d_state);
+  if (b->d_accepted) cudaFree(b->d_accepted);
+  if (b->d_log) cudaFree(b->d_log);
+  if (b->d_energy_partial) cudaFree(b->d_energy_partial);
+  if (b->d_scalar) cudaFree(b->d_scalar);
+  for (int i = 0; i < 2; i++)
+    if (b->ev_pair[i]) cudaEventDestroy(b->ev_pair[i]);
+  b->io.release();
+  b->io2.release();
+  b->io3.release();
+  b->io4.release();
+  b->cells.release();
+  delete b;
+  return EDM_OK;
+}
+
+int edm_bias_state(edm_bias_t* b, edm_bias_state_t* out) {
+  EDM_REQUIRE(b && out, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  out->cum_bias = hdr.cum_bias;
+  out->temp_hill_cum = hdr.temp_hill_cum;
+  out->steps = hdr.steps;
+  out->hills_added = hdr.hills_added;
+  out->skipped = hdr.skip;
+  out->backlog_left = (long)hdr.left;
+  out->backlog_right = (long)hdr.right;
+  out->n_accepted = hdr.n_accepted;
+  out->log_dropped = hdr.log_dropped;
+  return EDM_OK;
+}
+
+int edm_bias_set_cum_bias(edm_bias_t* b, double cum_bias) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  EDM_CUDA(cudaMemcpy(&b->d_state->cum_bias, &cum_bias, sizeof(double), cudaMemcpyHostToDevice));
+  return EDM_OK;
+}
+
+int edm_bias_backlog_get(edm_bias_t* b, long* left, long* right, double* buffer) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  if (left) *left = (long)hdr.left;
+  if (right) *right = (long)hdr.right;
+  if (buffer)
+    EDM_CUDA(cudaMemcpy(buffer, b->d_state->overflow, EDM_BUFFER_DBLS * sizeof(double), cudaMemcpyDeviceToHost));
+  return EDM_OK;
+}
+
+int edm_bias_backlog_set(edm_bias_t* b, long left, long right, const double* buffer) {
+  EDM_REQUIRE(b && buffer, "NULL argument");
+  EDM_REQUIRE(left >= 0 && left <= right && right <= EDM_BUFFER_SLOTS, "bad backlog indices");
+  EDM_TRY(ensure_device(b->device));
+  long long lr[2] = {left, right};
+  EDM_CUDA(cudaMemcpy(&b->d_state->left, lr, sizeof(lr), cudaMemcpyHostToDevice));
+  EDM_CUDA(cudaMemcpy(b->d_state->overflow, buffer, EDM_BUFFER_DBLS * sizeof(double), cudaMemcpyHostToDevice));
+  return EDM_OK;
+}
+
+int edm_bias_log_read(edm_bias_t* b, edm_hill_event_t* out, long cap, long* n) {
+  EDM_REQUIRE(b && n, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  long cnt = hdr.log_n;
+  if (out) {
+    long take = cnt < cap ? cnt : cap;
+    if (take > 0) EDM_CUDA(cudaMemcpy(out, b->d_log, (size_t)take * sizeof(edm_hill_event_t), cudaMemcpyDeviceToHost));
+    int zero = 0;
+    EDM_CUDA(cudaMemcpy(&b->d_state->log_n, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    *n = take;
+  } else {
+    *n = cnt;
+  }
+  return EDM_OK;
+}
+
+// ------------------------------------------------------------------ update_forces
+
+int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                               const int* mask, int apply_mask, double* energy, void* stream) {
+  EDM_REQUIRE(b && (n == 0 || (x && f)), "NULL argument");
+  EDM_REQUIRE(apply_mask < 0 || mask, "apply_mask >= 0 needs a mask");
+  EDM_REQUIRE(xstride >= b->prm.dim && fstride >= b->prm.dim, "stride < dim");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blocks = (n + 255) / 256;
+  if (blocks > b->n_partial) blocks = b->n_partial;
+  if (blocks < 1) blocks = 1;
+  const GridDesc& g = b->bias->d;
+  count_launches(energy ? 2 : 1);
+  switch (b->prm.dim) {
+    case 1: forces_kernel<1><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
+    case 2: forces_kernel<2><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
+    default: forces_kernel<3><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  if (energy) {
+    sum_partials_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy);
+    EDM_CUDA(cudaGetLastError());
+  }
+  return EDM_OK;
+}
+
+int edm_bias_update_forces(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                           const int* mask, int apply_mask, double* energy) {
+  EDM_REQUIRE(b && (n == 0 || (x && f)), "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  if (energy) *energy = 0.0;
+  if (n <= 0) return EDM_OK;
+  size_t bx = (size_t)n * xstride * sizeof(double), bf = (size_t)n * fstride * sizeof(double);
+  EDM_TRY(b->io.reserve(bx));
+  EDM_TRY(b->io2.reserve(bf));
+  const int* dmask = nullptr;
+  if (apply_mask >= 0) {
+    EDM_REQUIRE(mask != nullptr, "apply_mask >= 0 needs a mask");
+    EDM_TRY(b->io3.reserve((size_t)n * sizeof(int)));
+    EDM_CUDA(cudaMemcpyAsync(b->io3.p, mask, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, 0));
+    dmask = b->io3.as<int>();
+  }
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bf, cudaMemcpyHostToDevice, 0));
+  EDM_TRY(edm_bias_update_forces_dev(b, n, b->io.as<double>(), xstride, b->io2.as<double>(), fstride, dmask, apply_mask,
+                                     b->d_scalar, nullptr));
+  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bf, cudaMemcpyDeviceToHost, 0));
+  double e = 0;
+  EDM_CUDA(cudaMemcpy(&e, b->d_scalar, sizeof(double), cudaMemcpyDeviceToHost));
+  if (energy) *energy = e;
+  return EDM_OK;
+}
+
+// ------------------------------------------------------------------ add_hills
+
+int edm_bias_select_dev(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform, const int* mask,
+                        int apply_mask, long long est_hill_count, uint64_t seed, uint64_t step, uint64_t first_counter,
+                        void* stream) {
+  EDM_REQUIRE(b && (n == 0 || x), "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, (long)first_counter + n));
+  return select_launch(b, n, x, xstride, runiform, mask, apply_mask, est_hill_count, seed, step, first_counter,
+                       (cudaStream_t)stream);
+}
+
+int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,
+                           const int* mask, int apply_mask, uint64_t seed, uint64_t step, void* stream) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+  EDM_TRY(edm_bias_reset_accepted(b, st));
+  // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
+  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, st));
+  return edm_bias_launch_round(b, n, st);
+}
+
+int edm_bias_add_hills(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform, const int* mask,
+                       int apply_mask, uint64_t seed, uint64_t step) {
+  EDM_REQUIRE(b && (n == 0 || x), "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  const double* dx = nullptr;
+  const double* du = nullptr;
+  const int* dm = nullptr;
+  if (n > 0) {
+    size_t bx = (size_t)n * xstride * sizeof(double);
+    EDM_TRY(b->io.reserve(bx));
+    EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
+    dx = b->io.as<double>();
+    if (runiform) {
+      EDM_TRY(b->io2.reserve((size_t)n * sizeof(double)));
+      EDM_CUDA(cudaMemcpyAsync(b->io2.p, runiform, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, 0));
+      du = b->io2.as<double>();
+    }
+    if (apply_mask >= 0) {
+      EDM_REQUIRE(mask != nullptr, "apply_mask >= 0 needs a mask");
+      EDM_TRY(b->io3.reserve((size_t)n * sizeof(int)));
+      EDM_CUDA(cudaMemcpyAsync(b->io3.p, mask, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, 0));
+      dm = b->io3.as<int>();
+    }
+  }
+  EDM_TRY(edm_bias_add_hills_dev(b, n, dx, xstride, du, dm, apply_mask, seed, step, nullptr));
+  EDM_CUDA(cudaDeviceSynchronize());
+  return edm_bias_check_round(b);
+}
+
+int edm_bias_pre_add_hill(edm_bias_t* b, int est_hill_count) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  EDM_TRY(edm_bias_reset_accepted(b, 0));
+  b->in_round = 1;
+  b->round_est = est_hill_count;
+  b->round_count = 0;
+  return EDM_OK;
+}
+
+int edm_bias_add_hill_batch(edm_bias_t* b, long n, const double* x, const double* runiform) {
+  EDM_REQUIRE(b && (n == 0 || x), "NULL argument");
+  if (!b->in_round) {  // lib/edm_bias.cpp:530-531 aborts
+    set_error("Must call pre_add_hill before add_hill");
+    return EDM_ERR_STATE;
+  }
+  EDM_REQUIRE(runiform || b->prm.hill_density < 0, "add_hill needs runiform when hill_density > 0");
+  EDM_TRY(ensure_device(b->device));
+  if (n <= 0) return EDM_OK;
+  int D = b->prm.dim;
+  size_t bx = (size_t)n * D * sizeof(double);
+  EDM_TRY(b->io.reserve(bx));
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
+  const double* du = nullptr;
+  if (runiform) {
+    EDM_TRY(b->io2.reserve((size_t)n * sizeof(double)));
+    EDM_CUDA(cudaMemcpyAsync(b->io2.p, runiform, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, 0));
+    du = b->io2.as<double>();
+  }
+  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, (long)b->round_count + n));
+  EDM_TRY(select_launch(b, n, b->io.as<double>(), D, du, nullptr, -1, b->round_est, 0, 0, b->round_count, 0));
+  b->round_count += (unsigned long long)n;
+  EDM_CUDA(cudaDeviceSynchronize());
+  return EDM_OK;
+}
+
+int edm_bias_post_add_hill(edm_bias_t* b) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  if (!b->in_round) {
+    set_error("Must call pre_add_hill before post_add_hill");
+    return EDM_ERR_STATE;
+  }
+  EDM_TRY(ensure_device(b->device));
+  b->in_round = 0;
+  EDM_TRY(edm_bias_launch_round(b, b->round_est, 0));
+  EDM_CUDA(cudaDeviceSynchronize());
+  return edm_bias_check_round(b);
+}
+
+int edm_bias_set_profiling(edm_bias_t* b, int on) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  if (on && !b->ev_pair[0]) {
+    EDM_CUDA(cudaEventCreate(&b->ev_pair[0]));
+    EDM_CUDA(cudaEventCreate(&b->ev_pair[1]));
+  }
+  b->profiling = on;
+  return EDM_OK;
+}
+
+int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms) {
+  EDM_REQUIRE(b && pair_kernel_ms && b->ev_pair[0], "profiling was never enabled");
+  EDM_TRY(ensure_device(b->device));
+  EDM_CUDA(cudaEventSynchronize(b->ev_pair[1]));
+  float ms = 0;
+  EDM_CUDA(cudaEventElapsedTime(&ms, b->ev_pair[0], b->ev_pair[1]));
+  *pair_kernel_ms = ms;
+  return EDM_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange
+
+size_t edm_hill_block_doubles(int dim, long cap) { return 1 + (size_t)cap * dim; }
+
+int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream) {
+  EDM_REQUIRE(b && block && cap > 0, "bad argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  HillAccepted* tmp = b->d_accepted + b->accepted_cap;
+  count_launches(1);
+  switch (b->prm.dim) {
+    case 1: pack_block_kernel<1><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
+    case 2: pack_block_kernel<2><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
+    default: pack_block_kernel<3><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, long cap, long long est_hill_count,
+                              void* stream) {
+  EDM_REQUIRE(b && blocks && nblocks > 0 && cap > 0, "bad argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  EDM_TRY(ensure_accepted(b, (long)nblocks * cap));
+  count_launches(1);
+  switch (b->prm.dim) {
+    case 1: unpack_blocks_kernel<1><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
+    case 2: unpack_blocks_kernel<2><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
+    default: unpack_blocks_kernel<3><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  return edm_bias_launch_round(b, est_hill_count, st);
+}
+
+}  // extern "C"

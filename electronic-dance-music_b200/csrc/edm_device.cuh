@@ -1,0 +1,379 @@
+// Device-side building blocks shared by every EDM kernel (sm_100a, fp64 throughout).
+//
+// Layout in HBM (DESIGN.md "Data layout"):
+//   * one RECORD per grid point, dim 0 fastest: {V, dV/dx0[, dV/dx1, dV/dx2]} padded to 2 doubles
+//     in 1-D and 4 doubles in 2-D/3-D, so a corner of the interpolation stencil is one aligned
+//     16 B / 32 B access and the two dim-0 neighbours share a sector pair;
+//   * per-dimension POINT TABLES ptab[d][index][8] = {xx, inside_boundary, uL, uU, t6, t7, Z, Z'}:
+//     everything in the McGovern-De Pablo deposit that depends on the grid point only
+//     (lib/gaussian_grid.h:270,308-323), built once on the host with the reference's exact
+//     expressions so grid-point coordinates and table look-ups are bit-identical.
+//
+// Where a rounding decides something discontinuous (cell index, wrap count, support test
+// dp^2 < 8, boundary membership) the reference's operation order is kept with explicit _rn
+// intrinsics, which nvcc never contracts into FMAs.  Elsewhere FMAs and
+// reciprocals are used freely; those change results by a few ulp, far inside the 1e-10 bar.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edm {
+
+constexpr double kGaussSupport = 8.0;      // GAUSS_SUPPORT, lib/gaussian_grid.h:10
+constexpr int kBcTableSize = 65536;        // BC_TABLE_SIZE, lib/gaussian_grid.h:11
+constexpr double kBcMar = 2.0;             // BC_MAR, lib/gaussian_grid.h:12
+constexpr double kInterpZero = 0.0000001;  // lib/grid.h:113 (T6)
+constexpr int kPtabW = 8;
+
+template <int DIM> struct RecW { static constexpr int value = (DIM == 1) ? 2 : 4; };
+
+struct GridDesc {
+  int dim;
+  int rec_w;
+  int n[3];
+  int periodic[3];  // grid periodicity (b_periodic_)
+  int b_interp, b_deriv, is_gauss;
+  int dup_possible;  // a periodic window wider than the grid revisits points (lib/gaussian_grid.h:251-262)
+  double min[3], max[3], dx[3];
+  double len[3];     // max - min as the reference evaluates it
+  double upper[3];   // max - dx: exclusive non-periodic bound (T4), evaluated on the host
+  double inv_dx[3];
+  double* rec;
+  long long size;
+  // GaussGrid part
+  double sigma[3];        // sigma * sqrt(2) (T8)
+  double sqrtpi_sigma[3]; // sqrt(M_PI) * sigma_  (lib/gaussian_grid.h:340)
+  double bmin[3], bmax[3], blen[3];
+  int bper[3];
+  int minisize[3];
+  const double* ptab[3];
+  const long long* dup_pairs;  // (outer, bound) linear indices of duplicate_boundary, lib/gaussian_grid.h:571-630
+  int n_dup;
+  double vol_element;
+};
+
+// lib/grid.h:17-20 (T1): floor for every finite in-range argument
+__device__ __forceinline__ int d_int_floor(double v) { return (int)floor(v); }
+// lib/grid.h:22-26 (T2): round half away from zero
+__device__ __forceinline__ double d_round(double v) { return v < 0.0 ? ceil(v - 0.5) : floor(v + 0.5); }
+
+// x -= L * int_floor((x - min) / L), lib/grid.h:270.  The quotient floors to 0 exactly when
+// 0 <= x - min < L, so the division is skipped for points already inside.
+__device__ __forceinline__ double d_wrap(double x, double mn, double len) {
+  double t = __dsub_rn(x, mn);
+  if (t >= 0.0 && t < len) return x;
+  double k = (double)d_int_floor(__ddiv_rn(t, len));
+  return __dsub_rn(x, __dmul_rn(len, k));
+}
+
+// lib/gaussian_grid.h:490-499 (inclusive)
+template <int DIM> __device__ __forceinline__ bool d_in_bounds(const GridDesc& g, const double* x) {
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (x[d] < g.bmin[d] || x[d] > g.bmax[d]) return false;
+  return true;
+}
+
+// lib/gaussian_grid.h:504-541: nearest-image remap
+template <int DIM> __device__ __forceinline__ void d_remap(const GridDesc& g, double* x) {
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    if (x[d] < g.min[d] || x[d] > g.max[d]) {
+      if (g.periodic[d]) {
+        double k = (double)d_int_floor(__ddiv_rn(__dsub_rn(x[d], g.min[d]), g.len[d]));
+        x[d] = __dsub_rn(x[d], __dmul_rn(g.len[d], k));
+      } else if (g.bper[d]) {
+        double bl = g.blen[d];
+        double dp0 = __dmul_rn(d_round(__ddiv_rn(__dsub_rn(g.min[d], x[d]), bl)), bl);
+        double dp1 = __dmul_rn(d_round(__ddiv_rn(__dsub_rn(g.max[d], x[d]), bl)), bl);
+        double a = fabs(__dsub_rn(__dsub_rn(g.min[d], x[d]), dp0));
+        double b = fabs(__dsub_rn(__dsub_rn(g.max[d], x[d]), dp1));
+        x[d] = __dadd_rn(x[d], (a < b) ? dp0 : dp1);
+      }
+    }
+  }
+}
+
+template <int W> struct RecLoad;
+template <> struct RecLoad<2> {
+  __device__ __forceinline__ static void ld(const double* p, double* out) {
+    double2 v = *reinterpret_cast<const double2*>(p);
+    out[0] = v.x;
+    out[1] = v.y;
+  }
+};
+template <> struct RecLoad<4> {
+  __device__ __forceinline__ static void ld(const double* p, double* out) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *reinterpret_cast<const double2*>(p + 2);
+    out[0] = a.x;
+    out[1] = a.y;
+    out[2] = b.x;
+    out[3] = b.y;
+  }
+};
+
+// Grid::get_value_deriv (lib/grid.h:390-446) behind GaussGrid::get_value_deriv
+// (lib/gaussian_grid.h:118-138), with interp<DIM> (lib/grid.h:52-139) restructured:
+//   tabf*C_d = tabf*a(X) + s*tabder_d*b(X)*dx   and   tabf*D_d = tabf*a'(X)*s/dx + tabder_d*c(X)
+// in 1-D (no division), one reciprocal of tabf per corner in 2-D/3-D.
+template <int DIM>
+__device__ __forceinline__ double d_eval_point(const GridDesc& g, const double* xin, double* der, bool interp) {
+  constexpr int W = RecW<DIM>::value;
+  double x[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    x[d] = xin[d];
+    der[d] = 0.0;
+  }
+  if (g.is_gauss) {
+    if (!d_in_bounds<DIM>(g, x)) {
+      d_remap<DIM>(g, x);
+      if (!d_in_bounds<DIM>(g, x)) return 0.0;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (!g.periodic[d] && (x[d] < g.min[d] || x[d] >= g.upper[d])) return 0.0;  // in_grid (T4)
+
+  long long base = 0, pstride = 1;
+  long long stride[DIM];
+  double X0[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    double xi = x[d];
+    if (g.periodic[d]) xi = d_wrap(xi, g.min[d], g.len[d]);
+    double t = __dsub_rn(xi, g.min[d]);
+    long long idx = (long long)floor(__ddiv_rn(t, g.dx[d]));  // T5: a true division
+    int nd = g.n[d];
+    long long hi = g.periodic[d] ? nd - 1 : nd - 2;
+    idx = idx < 0 ? 0 : (idx > hi ? hi : idx);  // rounding can land one past the last cell; clamp
+    double where = __dsub_rn(t, __dmul_rn((double)idx, g.dx[d]));
+    X0[d] = where * g.inv_dx[d];
+    stride[d] = (g.periodic[d] && idx == nd - 1) ? pstride * (1 - nd) : pstride;  // lib/grid.h:432-433
+    base += idx * pstride;
+    pstride *= nd;
+  }
+  if (!interp) {  // lib/grid.h:438-443
+    double r[W];
+    RecLoad<W>::ld(g.rec + base * W, r);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) der[d] = r[1 + d];
+    return r[0];
+  }
+  double f = 0.0;
+#pragma unroll
+  for (int c = 0; c < (1 << DIM); c++) {
+    long long shift = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+      if ((c >> d) & 1) shift += stride[d];
+    double r[W];
+    RecLoad<W>::ld(g.rec + (base + shift) * W, r);
+    double tabf = r[0];
+    bool nz = !(fabs(tabf) < kInterpZero);  // T6
+    if (DIM == 1) {
+      int b = c & 1;
+      double X = fabs(X0[0] - (double)b);
+      double s = b ? -1.0 : 1.0;
+      double X2 = X * X, X3 = X2 * X;
+      double a = 1.0 - 3.0 * X2 + 2.0 * X3;
+      double bp = X - 2.0 * X2 + X3;
+      double ap = -6.0 * X + 6.0 * X2;
+      double cc = 1.0 - 4.0 * X + 3.0 * X2;
+      double td = nz ? r[1] : 0.0;
+      f += tabf * a + s * td * bp * g.dx[0];
+      der[0] += tabf * ap * s * g.inv_dx[0] + td * cc;
+    } else {
+      double rinv = nz ? 1.0 / tabf : 0.0;
+      double C[DIM], D[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        int b = (c >> d) & 1;
+        double X = fabs(X0[d] - (double)b);
+        double s = b ? -1.0 : 1.0;
+        double X2 = X * X, X3 = X2 * X;
+        double qq = -r[1 + d] * rinv;
+        C[d] = (1.0 - 3.0 * X2 + 2.0 * X3) - s * qq * (X - 2.0 * X2 + X3) * g.dx[d];
+        D[d] = ((-6.0 * X + 6.0 * X2) - s * qq * (1.0 - 4.0 * X + 3.0 * X2) * g.dx[d]) * s * g.inv_dx[d];
+      }
+      double ff = 1.0;
+#pragma unroll
+      for (int d = 0; d < DIM; d++) ff *= C[d];
+      f += tabf * ff;
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        double fd = D[d];
+#pragma unroll
+        for (int e = 0; e < DIM; e++)
+          if (e != d) fd *= C[e];
+        der[d] += tabf * fd;
+      }
+    }
+  }
+  return f;
+}
+
+// Grid::get_value (lib/grid.h:343-365) behind GaussGrid::get_value (lib/gaussian_grid.h:99-116)
+template <int DIM> __device__ __forceinline__ double d_get_value(const GridDesc& g, const double* xin) {
+  double der[DIM];
+  return d_eval_point<DIM>(g, xin, der, g.b_interp && g.b_deriv);
+}
+
+// ---------------------------------------------------------------- hill deposit pieces
+
+template <int DIM> struct HillGeom {
+  double x[DIM];   // centre after remap
+  int xi[DIM];     // centre cell, may be negative (lib/gaussian_grid.h:222-224)
+  double t1[DIM];  // exp(-(x-L)^2/sigma^2), lib/gaussian_grid.h:310
+  double t3[DIM];  // exp(-(x-U)^2/sigma^2), lib/gaussian_grid.h:312
+};
+
+// lib/gaussian_grid.h:205-224 (T10): false when the centre lies outside a non-periodic boundary
+template <int DIM>
+__device__ __forceinline__ bool d_hill_prepare(const GridDesc& g, const double* x0, HillGeom<DIM>& hg) {
+#pragma unroll
+  for (int d = 0; d < DIM; d++) hg.x[d] = x0[d];
+  d_remap<DIM>(g, hg.x);
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (!g.bper[d] && (hg.x[d] < g.bmin[d] || hg.x[d] > g.bmax[d])) return false;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    hg.xi[d] = d_int_floor(__ddiv_rn(__dsub_rn(hg.x[d], g.min[d]), g.dx[d]));
+    hg.t1[d] = 0.0;
+    hg.t3[d] = 0.0;
+    if (!g.bper[d]) {
+      double s2 = __dmul_rn(g.sigma[d], g.sigma[d]);
+      double a = __dsub_rn(hg.x[d], g.bmin[d]);
+      double b = __dsub_rn(hg.x[d], g.bmax[d]);
+      hg.t1[d] = exp(__ddiv_rn(-__dmul_rn(a, a), s2));
+      hg.t3[d] = exp(__ddiv_rn(-__dmul_rn(b, b), s2));
+    }
+  }
+  return true;
+}
+
+// One (hill, grid point) term of lib/gaussian_grid.h:283-355 incl. the multi-D McGDP quirks
+// (T11).  idx[] must already be a valid wrapped grid index.  On success: etot = expo + corr (per
+// unit height), force[d] = per-unit-height addend of grid_deriv_[.][d].
+template <int DIM>
+__device__ __forceinline__ bool d_hill_term(const GridDesc& g, const HillGeom<DIM>& hg, const int* idx,
+                                            double& etot, double* force, bool& corr_nonzero) {
+  double dp[DIM];
+  const double* row[DIM];
+  double dp2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    row[d] = g.ptab[d] + (long long)idx[d] * kPtabW;
+    if (row[d][1] == 0.0) return false;  // outside a non-periodic boundary (T10)
+    double v = __dsub_rn(row[d][0], hg.x[d]);
+    if (g.periodic[d]) v = __dsub_rn(v, __dmul_rn(d_round(__ddiv_rn(v, g.len[d])), g.len[d]));
+    v = __ddiv_rn(v, g.sigma[d]);
+    dp[d] = v;
+    dp2 = __dadd_rn(dp2, __dmul_rn(v, v));
+  }
+  if (!(dp2 < kGaussSupport)) return false;
+  double expo = exp(-dp2);
+  double bc_denom = 1.0, corr = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    if (!g.bper[d]) {
+      const double uL = row[d][2], uU = row[d][3], t6 = row[d][4], t7 = row[d][5];
+      corr = (hg.t1[d] - expo) * uL + (hg.t3[d] - expo) * uU;
+      bc_denom *= row[d][6];
+      double t5 = -2.0 * dp[d] / g.sigma[d];
+      double F = t5 * expo;
+      F += (hg.t1[d] - expo) * t6 - t5 * expo * uL + (hg.t3[d] - expo) * t7 - t5 * expo * uU;
+      F = F * bc_denom - row[d][7] * (expo + corr);
+      F /= bc_denom * bc_denom;
+      corr /= bc_denom;
+      force[d] = F;
+    } else {
+      bc_denom *= g.sqrtpi_sigma[d];
+    }
+  }
+  expo /= bc_denom;
+  etot = expo + corr;
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (g.bper[d]) force[d] = -(2.0 * dp[d] / g.sigma[d] * expo);
+  corr_nonzero = (corr * corr > 0.0);
+  return true;
+}
+
+// Maps window offset w (dim 0 fastest over 2*minisize+1 per dim) to a wrapped grid index,
+// lib/gaussian_grid.h:229-268.  False when the point falls off a non-periodic grid.
+template <int DIM>
+__device__ __forceinline__ bool d_window_index(const GridDesc& g, const HillGeom<DIM>& hg, long long w, int* idx,
+                                               long long& linear) {
+  linear = 0;
+  long long pstride = 1;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    int span = 2 * g.minisize[d] + 1;
+    int off;
+    if (d < DIM - 1) {
+      off = (int)(w % span);
+      w = (w - off) / span;
+    } else {
+      off = (int)w;
+    }
+    int i = off - g.minisize[d] + hg.xi[d];
+    if (i >= g.n[d]) {
+      if (!g.periodic[d]) return false;
+      i %= g.n[d];
+    }
+    if (i < 0) {
+      if (!g.periodic[d]) return false;
+      i += g.n[d];
+      if (i < 0) return false;  // window wider than two periods: outside anything the reference can index
+    }
+    idx[d] = i;
+    linear += (long long)i * pstride;
+    pstride *= g.n[d];
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- reductions / RNG
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the CTA in a fixed order (lane tree, then warps in order): run-to-run deterministic.
+// red must hold 33 doubles of shared memory.  Every thread receives the total.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; i++) t += red[i];
+    red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+// stream key for (seed, step); computed once per launch on the host
+__host__ __device__ __forceinline__ uint64_t uniform_key(uint64_t seed, uint64_t step) {
+  return mix64(seed ^ mix64(step + 0x9E3779B97F4A7C15ULL));
+}
+__host__ __device__ __forceinline__ double uniform_from_key(uint64_t key, uint64_t counter) {
+  uint64_t bits = mix64(key + counter * 0x9E3779B97F4A7C15ULL);
+  return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace edm

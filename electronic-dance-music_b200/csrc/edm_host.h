@@ -1,0 +1,107 @@
+// Host-side object layouts behind the opaque C handles of include/edm_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/edm_b200.h"
+#include "edm_device.cuh"
+
+namespace edm {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define EDM_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return ::edm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define EDM_REQUIRE(cond, msg)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ::edm::set_error(msg);          \
+      return EDM_ERR_ARG;             \
+    }                                 \
+  } while (0)
+
+#define EDM_TRY(call)            \
+  do {                           \
+    int rc__ = (call);           \
+    if (rc__ != EDM_OK) return rc__; \
+  } while (0)
+
+int ensure_device(int device);
+void count_launches(int n);
+
+// Device scratch that grows on demand and is reused across calls (no allocation on the steady
+// per-step path once sizes settle).
+struct Scratch {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t need);
+  void release();
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace edm
+
+struct edm_grid {
+  int device = 0;
+  edm::GridDesc d;          // what kernels receive by value
+  double sigma_user[3];     // sigma as given (bias_sigma), before the sqrt(2)
+  std::vector<double> bc_denom[3], bc_deriv[3];  // McGDP tables, lib/gaussian_grid.h:551-552
+  double* d_ptab[3] = {nullptr, nullptr, nullptr};
+  long long* d_dup = nullptr;
+  edm::Scratch io;          // staging for upload/download/eval of host buffers
+  edm::Scratch work;        // deposit scratch (prepared hills, partials, slots)
+  int* d_flags = nullptr;   // [0] dirty-bounds flag
+};
+
+struct HillAccepted {  // one selected candidate
+  unsigned long long key;
+  double x[3];
+};
+
+struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/edm_bias.h:130,161-178
+  double cum_bias;
+  double temp_hill_cum;
+  long long steps;
+  int hills_added;
+  int skip;
+  long long left, right;
+  int n_accepted;
+  int accepted_overflow;
+  int log_n;
+  int log_dropped;
+  int backlog_full;
+  int pad;
+  unsigned long long n_pairs;
+  double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
+};
+
+struct edm_bias {
+  int device = 0;
+  edm_bias_params_t prm;
+  edm_grid* bias = nullptr;
+  edm_grid* hist = nullptr;
+  edm_grid* target = nullptr;
+  BiasDev* d_state = nullptr;
+  HillAccepted* d_accepted = nullptr;
+  long accepted_cap = 0;
+  edm_hill_event_t* d_log = nullptr;
+  long log_cap = 0;
+  double* d_energy_partial = nullptr;  // per-CTA energy partials
+  int n_partial = 0;
+  double* d_scalar = nullptr;          // [0] energy
+  edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
+  edm::Scratch cells;                  // cell-list scratch of the pair kernels
+  // streaming triple
+  int in_round = 0;
+  long long round_est = 0;
+  unsigned long long round_count = 0;
+  int profiling = 0;
+  cudaEvent_t ev_pair[2] = {nullptr, nullptr};
+};

@@ -1,0 +1,509 @@
+// Pair-distance collective variable of fix edm_pair (lammps/fix_edm_pair.cpp:139-256) on the
+// device: cell binning, half-shell pair search, 1-D bias evaluation at r, force scatter and the
+// two-per-pair hill proposals.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "edm_host.h"
+
+int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st);
+int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st);
+int edm_bias_check_round(edm_bias* b);
+
+namespace edm {
+
+struct CellGrid {
+  int nc[3];
+  double cs[3];
+  double box[3];
+  int ncell;
+};
+
+struct PairParams {
+  int itype, jtype, use_types;
+  int do_hills, accept_all;
+  double thresh;
+  uint64_t key;
+  double rc2;
+  long natoms;
+  long acc_cap;
+};
+
+__device__ __forceinline__ int cell_coord(double x, double cs, int nc) {
+  int c = (int)floor(x / cs);
+  return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+__global__ void cell_count_kernel(long n, const double* __restrict__ x, CellGrid cg, int* __restrict__ cell_of,
+                                  int* __restrict__ count) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx = cell_coord(x[3 * i + 0], cg.cs[0], cg.nc[0]);
+  int cy = cell_coord(x[3 * i + 1], cg.cs[1], cg.nc[1]);
+  int cz = cell_coord(x[3 * i + 2], cg.cs[2], cg.nc[2]);
+  int c = (cz * cg.nc[1] + cy) * cg.nc[0] + cx;
+  cell_of[i] = c;
+  atomicAdd(&count[c], 1);
+}
+
+// exclusive scan of count[0..n) into start[0..n]; one CTA, each thread scans a contiguous slice
+__global__ void __launch_bounds__(1024) cell_scan_kernel(int n, const int* __restrict__ count, int* __restrict__ start) {
+  __shared__ int part[1024];
+  int per = (n + blockDim.x - 1) / blockDim.x;
+  int lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+  int s = 0;
+  for (int i = lo; i < hi; i++) s += count[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < blockDim.x; t++) {
+      int v = part[t];
+      part[t] = run;
+      run += v;
+    }
+    start[n] = run;
+  }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = lo; i < hi; i++) {
+    start[i] = run;
+    run += count[i];
+  }
+}
+
+__global__ void cell_fill_kernel(long n, const int* __restrict__ cell_of, const int* __restrict__ start,
+                                 int* __restrict__ fill, int* __restrict__ order) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cell_of[i];
+  int slot = start[c] + atomicAdd(&fill[c], 1);
+  order[slot] = (int)i;
+}
+
+// canonical order inside a cell (ascending atom index) + gather of positions/types into slot order,
+// so the result does not depend on the order the atomics above happened to resolve in
+__global__ void cell_sort_gather_kernel(int ncell, const int* __restrict__ start, int* __restrict__ order,
+                                        const double* __restrict__ x, const int* __restrict__ type,
+                                        double* __restrict__ xs, int* __restrict__ ts) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int lo = start[c], hi = start[c + 1];
+  for (int a = lo + 1; a < hi; a++) {
+    int v = order[a];
+    int b = a - 1;
+    while (b >= lo && order[b] > v) {
+      order[b + 1] = order[b];
+      b--;
+    }
+    order[b + 1] = v;
+  }
+  for (int a = lo; a < hi; a++) {
+    int i = order[a];
+    xs[3 * (long)a + 0] = x[3 * (long)i + 0];
+    xs[3 * (long)a + 1] = x[3 * (long)i + 1];
+    xs[3 * (long)a + 2] = x[3 * (long)i + 2];
+    if (ts) ts[a] = type ? type[i] : 0;
+  }
+}
+
+// 1-D bias evaluation at r with update_force's sign (lib/edm_bias.cpp:297-311): returns V(r),
+// force = -dV/dr.
+__device__ __forceinline__ double pair_eval(const GridDesc& g, double r, double& force) {
+  double der[1];
+  double rr[1] = {r};
+  double v = d_eval_point<1>(g, rr, der, g.b_interp != 0);
+  force = -der[0];
+  return v;
+}
+
+__device__ __forceinline__ void propose_hills(const PairParams& pp, unsigned long long pairkey, double r, BiasDev* st,
+                                              HillAccepted* acc) {
+#pragma unroll
+  for (int which = 0; which < 2; which++) {
+    unsigned long long k = 2ULL * pairkey + which;
+    bool take = pp.accept_all || (uniform_from_key(pp.key, k) < pp.thresh);
+    if (take) {
+      int slot = atomicAdd(&st->n_accepted, 1);
+      if (slot < pp.acc_cap) {
+        acc[slot].key = k;
+        acc[slot].x[0] = r;
+        acc[slot].x[1] = 0.0;
+        acc[slot].x[2] = 0.0;
+      } else {
+        st->accepted_overflow = 1;
+      }
+    }
+  }
+}
+
+// v1: one thread per atom (slot order), half shell of 13 forward cells + own cell.
+__global__ void __launch_bounds__(128) pair_cells_kernel(GridDesc g, CellGrid cg, PairParams pp,
+                                                         const int* __restrict__ start, const int* __restrict__ order,
+                                                         const double* __restrict__ xs, const int* __restrict__ ts,
+                                                         double* __restrict__ f, double* __restrict__ partial,
+                                                         BiasDev* st, HillAccepted* acc) {
+  __shared__ double red[33];
+  double e = 0.0;
+  unsigned long long npairs = 0;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long a = (long)blockIdx.x * blockDim.x + threadIdx.x; a < pp.natoms; a += stride) {
+    const double xi = xs[3 * a + 0], yi = xs[3 * a + 1], zi = xs[3 * a + 2];
+    const int ti = pp.use_types ? ts[a] : 0;
+    if (pp.use_types && ti != pp.itype && ti != pp.jtype) continue;
+    const int oi = order[a];
+    int cx = cell_coord(xi, cg.cs[0], cg.nc[0]);
+    int cy = cell_coord(yi, cg.cs[1], cg.nc[1]);
+    int cz = cell_coord(zi, cg.cs[2], cg.nc[2]);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int nb = 0; nb < 14; nb++) {
+      // nb 0 = own cell; 1..13 = offsets with (dz,dy,dx) lexicographically positive
+      int t = nb + 13;  // 13..26 in the 3x3x3 enumeration, 13 = centre
+      int ox = t % 3 - 1, oy = (t / 3) % 3 - 1, oz = t / 9 - 1;
+      int qx = cx + ox, qy = cy + oy, qz = cz + oz;
+      double sx = 0.0, sy = 0.0, sz = 0.0;
+      if (qx >= cg.nc[0]) { qx -= cg.nc[0]; sx = cg.box[0]; } else if (qx < 0) { qx += cg.nc[0]; sx = -cg.box[0]; }
+      if (qy >= cg.nc[1]) { qy -= cg.nc[1]; sy = cg.box[1]; } else if (qy < 0) { qy += cg.nc[1]; sy = -cg.box[1]; }
+      if (qz >= cg.nc[2]) { qz -= cg.nc[2]; sz = cg.box[2]; } else if (qz < 0) { qz += cg.nc[2]; sz = -cg.box[2]; }
+      int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
+      long jlo = start[q], jhi = start[q + 1];
+      if (nb == 0) jlo = a + 1;
+      for (long j = jlo; j < jhi; j++) {
+        // separation exactly as the oracle forms it: (x_i - x_j) - image shift, squares summed in x,y,z order
+        double dx = __dsub_rn(__dsub_rn(xi, xs[3 * j + 0]), sx);
+        double dy = __dsub_rn(__dsub_rn(yi, xs[3 * j + 1]), sy);
+        double dz = __dsub_rn(__dsub_rn(zi, xs[3 * j + 2]), sz);
+        double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (!(d2 < pp.rc2)) continue;
+        if (pp.use_types) {
+          int tj = ts[j];
+          bool match = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
+          if (!match) continue;
+        }
+        const int oj = order[j];
+        // the pair is oriented (i = lower atom index) as in a half list sorted by (i, j)
+        double sgn = (oi < oj) ? 1.0 : -1.0;
+        double r = sqrt(d2);
+        double rinv = 1.0 / r;
+        double force;
+        e += pair_eval(g, r, force);
+        npairs++;
+        double px = dx * rinv * force, py = dy * rinv * force, pz = dz * rinv * force;
+        fx += px;
+        fy += py;
+        fz += pz;
+        atomicAdd(&f[3 * (long)oj + 0], -px);
+        atomicAdd(&f[3 * (long)oj + 1], -py);
+        atomicAdd(&f[3 * (long)oj + 2], -pz);
+        (void)sgn;
+        if (pp.do_hills) {
+          unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
+          propose_hills(pp, lo * (unsigned long long)pp.natoms + hi, r, st, acc);
+        }
+      }
+    }
+    atomicAdd(&f[3 * (long)oi + 0], fx);
+    atomicAdd(&f[3 * (long)oi + 1], fy);
+    atomicAdd(&f[3 * (long)oi + 2], fz);
+  }
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  // pair count: integer, so the atomic order is irrelevant
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+  if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&st->n_pairs, npairs);
+}
+
+// Neighbour-list form: one thread per listed i-row (lammps/fix_edm_pair.cpp:177-240).
+__global__ void __launch_bounds__(128) pair_list_kernel(GridDesc g, PairParams pp, long nlocal, long inum,
+                                                        const int* __restrict__ ilist, const long* __restrict__ first,
+                                                        const int* __restrict__ jlist, const double* __restrict__ x,
+                                                        const int* __restrict__ type, const double* __restrict__ runiform,
+                                                        double* __restrict__ f, double* __restrict__ partial,
+                                                        BiasDev* st, HillAccepted* acc, unsigned long long* ncalls) {
+  __shared__ double red[33];
+  double e = 0.0;
+  unsigned long long npairs = 0, calls = 0;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (long ii = (long)blockIdx.x * blockDim.x + threadIdx.x; ii < inum; ii += stride) {
+    const int i = ilist[ii];
+    int type_ind = 0;
+    if (pp.use_types) {
+      int it = type[i];
+      if (it == pp.itype) type_ind = 1;
+      else if (it == pp.jtype) type_ind = 0;
+      else continue;
+    }
+    const double xi = x[3 * (long)i + 0], yi = x[3 * (long)i + 1], zi = x[3 * (long)i + 2];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (long k = first[ii]; k < first[ii + 1]; k++) {
+      const int j = jlist[k];
+      if (pp.use_types) {
+        int jt = type[j];
+        if (type_ind && jt != pp.jtype) continue;
+        if (!type_ind && jt != pp.itype) continue;
+      }
+      double dx = __dsub_rn(xi, x[3 * (long)j + 0]);
+      double dy = __dsub_rn(yi, x[3 * (long)j + 1]);
+      double dz = __dsub_rn(zi, x[3 * (long)j + 2]);
+      double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      double r = sqrt(d2);
+      double rinv = 1.0 / r;
+      double force;
+      e += pair_eval(g, r, force);
+      npairs++;
+      double px = dx * rinv * force, py = dy * rinv * force, pz = dz * rinv * force;
+      fx += px;
+      fy += py;
+      fz += pz;
+      const bool jlocal = j < nlocal;
+      if (jlocal) {
+        atomicAdd(&f[3 * (long)j + 0], -px);
+        atomicAdd(&f[3 * (long)j + 1], -py);
+        atomicAdd(&f[3 * (long)j + 2], -pz);
+      }
+      if (pp.do_hills) {
+        int nprop = jlocal ? 2 : 1;
+        calls += nprop;
+        for (int which = 0; which < nprop; which++) {
+          unsigned long long kk = 2ULL * (unsigned long long)k + which;
+          double u = runiform ? runiform[kk] : uniform_from_key(pp.key, kk);
+          if (pp.accept_all || u < pp.thresh) {
+            int slot = atomicAdd(&st->n_accepted, 1);
+            if (slot < pp.acc_cap) {
+              acc[slot].key = kk;
+              acc[slot].x[0] = r;
+              acc[slot].x[1] = 0.0;
+              acc[slot].x[2] = 0.0;
+            } else {
+              st->accepted_overflow = 1;
+            }
+          }
+        }
+      }
+    }
+    atomicAdd(&f[3 * (long)i + 0], fx);
+    atomicAdd(&f[3 * (long)i + 1], fy);
+    atomicAdd(&f[3 * (long)i + 2], fz);
+  }
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  for (int o = 16; o > 0; o >>= 1) {
+    npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+    calls += __shfl_down_sync(0xffffffffu, calls, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (npairs) atomicAdd(&st->n_pairs, npairs);
+    if (calls) atomicAdd(ncalls, calls);
+  }
+}
+
+__global__ void reset_pairs_kernel(BiasDev* st, unsigned long long* ncalls) {
+  st->n_pairs = 0;
+  if (ncalls) *ncalls = 0;
+}
+
+__global__ void sum_partials2_kernel(int n, const double* __restrict__ partial, double* out) {
+  __shared__ double red[33];
+  double e = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) e += partial[i];
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) out[0] = tot;
+}
+
+}  // namespace edm
+
+using namespace edm;
+
+static PairParams pair_params(const edm_bias* b, const int* type, int itype, int jtype, int do_hills, long long est,
+                              uint64_t seed, uint64_t step, double cutoff, long natoms) {
+  PairParams pp;
+  pp.itype = itype;
+  pp.jtype = jtype;
+  pp.use_types = type != nullptr;
+  pp.do_hills = do_hills;
+  pp.accept_all = b->prm.hill_density < 0;
+  pp.thresh = pp.accept_all ? 2.0 : b->prm.hill_density / (double)(int)est;
+  pp.key = uniform_key(seed, step);
+  pp.rc2 = cutoff * cutoff;
+  pp.natoms = natoms;
+  pp.acc_cap = b->accepted_cap;
+  return pp;
+}
+
+// binning + pair kernel on device pointers; leaves the energy in b->d_scalar[0]
+static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* f, const int* type, int itype,
+                             int jtype, const double* box, double cutoff, int do_hills, long long est, uint64_t seed,
+                             uint64_t step, double* energy_dev, cudaStream_t st) {
+  EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");  // fix_edm_pair.cpp:52-53
+  EDM_REQUIRE(natoms > 0 && natoms < 2000000000L, "bad atom count");
+  CellGrid cg;
+  long long ncell = 1;
+  for (int d = 0; d < 3; d++) {
+    cg.box[d] = box[d];
+    cg.nc[d] = (int)floor(box[d] / cutoff);
+    EDM_REQUIRE(cg.nc[d] >= 3, "box must hold at least 3 cutoffs per side for the half-shell cell search");
+    cg.cs[d] = box[d] / cg.nc[d];
+    ncell *= cg.nc[d];
+  }
+  EDM_REQUIRE(ncell < 2000000000LL, "too many cells");
+  cg.ncell = (int)ncell;
+  // scratch: cell_of[n], order[n], ts[n], count[ncell+1], start[ncell+1], xs[3n]
+  size_t n = (size_t)natoms, nc1 = (size_t)ncell + 1;
+  size_t off_cell = 0, off_order = off_cell + n * 4, off_ts = off_order + n * 4, off_count = off_ts + n * 4;
+  size_t off_start = off_count + nc1 * 4;
+  size_t off_xs = (off_start + nc1 * 4 + 255) / 256 * 256;
+  size_t total = off_xs + 3 * n * sizeof(double);
+  EDM_TRY(b->cells.reserve(total));
+  char* base = b->cells.as<char>();
+  int* cell_of = reinterpret_cast<int*>(base + off_cell);
+  int* order = reinterpret_cast<int*>(base + off_order);
+  int* ts = reinterpret_cast<int*>(base + off_ts);
+  int* count = reinterpret_cast<int*>(base + off_count);
+  int* start = reinterpret_cast<int*>(base + off_start);
+  double* xs = reinterpret_cast<double*>(base + off_xs);
+
+  EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
+  unsigned nb = (unsigned)((natoms + 255) / 256);
+  cell_count_kernel<<<nb, 256, 0, st>>>(natoms, x, cg, cell_of, count);
+  cell_scan_kernel<<<1, 1024, 0, st>>>(cg.ncell, count, start);
+  EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
+  cell_fill_kernel<<<nb, 256, 0, st>>>(natoms, cell_of, start, count, order);
+  cell_sort_gather_kernel<<<(cg.ncell + 127) / 128, 128, 0, st>>>(cg.ncell, start, order, x, type, xs, type ? ts : nullptr);
+  EDM_CUDA(cudaGetLastError());
+
+  PairParams pp = pair_params(b, type, itype, jtype, do_hills, est, seed, step, cutoff, natoms);
+  reset_pairs_kernel<<<1, 1, 0, st>>>(b->d_state, nullptr);
+  long long blocks = (natoms + 127) / 128;
+  if (blocks > b->n_partial) blocks = b->n_partial;
+  if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[0], st));
+  pair_cells_kernel<<<(int)blocks, 128, 0, st>>>(b->bias->d, cg, pp, start, order, xs, ts, f, b->d_energy_partial,
+                                                 b->d_state, b->d_accepted);
+  if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[1], st));
+  count_launches(7);
+  sum_partials2_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy_dev);
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+static int read_pair_result(edm_bias* b, edm_pair_result_t* result, const unsigned long long* ncalls_dev) {
+  if (!result) return EDM_OK;
+  double e;
+  unsigned long long np;
+  EDM_CUDA(cudaMemcpy(&e, b->d_scalar, sizeof(double), cudaMemcpyDeviceToHost));
+  EDM_CUDA(cudaMemcpy(&np, &b->d_state->n_pairs, sizeof(np), cudaMemcpyDeviceToHost));
+  result->energy = e;
+  result->n_pairs = (long long)np;
+  result->n_calls = 2 * (long long)np;
+  if (ncalls_dev) {
+    unsigned long long nc;
+    EDM_CUDA(cudaMemcpy(&nc, ncalls_dev, sizeof(nc), cudaMemcpyDeviceToHost));
+    result->n_calls = (long long)nc;
+  }
+  return EDM_OK;
+}
+
+extern "C" {
+
+int edm_pair_select_cells_dev(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype,
+                              int jtype, const double* box, double cutoff, long long est_hill_count, uint64_t seed,
+                              uint64_t step, double* energy_dev, void* stream) {
+  EDM_REQUIRE(b && x && f && box, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  EDM_TRY(edm_bias_reset_accepted(b, st));
+  return pair_cells_launch(b, natoms, x, f, type, itype, jtype, box, cutoff, 1, est_hill_count, seed, step,
+                           energy_dev ? energy_dev : b->d_scalar, st);
+}
+
+int edm_pair_step_cells_dev(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype,
+                            int jtype, const double* box, double cutoff, int do_hills, long long est_hill_count,
+                            uint64_t seed, uint64_t step, edm_pair_result_t* result, void* stream) {
+  EDM_REQUIRE(b && x && f && box, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, st));
+  EDM_TRY(pair_cells_launch(b, natoms, x, f, type, itype, jtype, box, cutoff, do_hills, est_hill_count, seed, step,
+                            b->d_scalar, st));
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, st));
+  if (result) {
+    EDM_CUDA(cudaStreamSynchronize(st));
+    EDM_TRY(read_pair_result(b, result, nullptr));
+    if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  }
+  return EDM_OK;
+}
+
+int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype, int jtype,
+                        const double* box, double cutoff, int do_hills, long long est_hill_count, uint64_t seed,
+                        uint64_t step, edm_pair_result_t* result) {
+  EDM_REQUIRE(b && x && f && box && natoms > 0, "bad argument");
+  EDM_TRY(ensure_device(b->device));
+  size_t bx = (size_t)natoms * 3 * sizeof(double);
+  EDM_TRY(b->io.reserve(bx));
+  EDM_TRY(b->io2.reserve(bx));
+  const int* dt = nullptr;
+  if (type) {
+    EDM_TRY(b->io3.reserve((size_t)natoms * sizeof(int)));
+    EDM_CUDA(cudaMemcpyAsync(b->io3.p, type, (size_t)natoms * sizeof(int), cudaMemcpyHostToDevice, 0));
+    dt = b->io3.as<int>();
+  }
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, 0));
+  edm_pair_result_t local;
+  EDM_TRY(edm_pair_step_cells_dev(b, natoms, b->io.as<double>(), b->io2.as<double>(), dt, itype, jtype, box, cutoff,
+                                  do_hills, est_hill_count, seed, step, &local, nullptr));
+  EDM_CUDA(cudaMemcpy(f, b->io2.p, bx, cudaMemcpyDeviceToHost));
+  if (result) *result = local;
+  return EDM_OK;
+}
+
+int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
+                       int jtype, long inum, const int* ilist, const long* first, const int* jlist, int do_hills,
+                       long long est_hill_count, const double* runiform, uint64_t seed, uint64_t step,
+                       edm_pair_result_t* result) {
+  EDM_REQUIRE(b && x && f && ilist && first && (jlist || first[inum] == 0), "NULL argument");
+  EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");
+  EDM_TRY(ensure_device(b->device));
+  long nlisted = first[inum];
+  size_t bx = (size_t)nall * 3 * sizeof(double);
+  EDM_TRY(b->io.reserve(bx));
+  EDM_TRY(b->io2.reserve(bx));
+  // list scratch: ilist[inum] | first[inum+1] | jlist[nlisted] | type[nall] | ncalls | uniforms
+  size_t o_il = 0, o_first = (o_il + (size_t)inum * 4 + 7) / 8 * 8, o_jl = o_first + (size_t)(inum + 1) * 8;
+  size_t o_ty = (o_jl + (size_t)nlisted * 4 + 7) / 8 * 8, o_nc = (o_ty + (size_t)nall * 4 + 7) / 8 * 8;
+  size_t o_u = o_nc + 8;
+  size_t total = o_u + (runiform ? (size_t)nlisted * 2 * sizeof(double) : 0);
+  EDM_TRY(b->io4.reserve(total));
+  char* base = b->io4.as<char>();
+  EDM_CUDA(cudaMemcpyAsync(base + o_il, ilist, (size_t)inum * 4, cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(base + o_first, first, (size_t)(inum + 1) * 8, cudaMemcpyHostToDevice, 0));
+  if (nlisted) EDM_CUDA(cudaMemcpyAsync(base + o_jl, jlist, (size_t)nlisted * 4, cudaMemcpyHostToDevice, 0));
+  if (type) EDM_CUDA(cudaMemcpyAsync(base + o_ty, type, (size_t)nall * 4, cudaMemcpyHostToDevice, 0));
+  if (runiform)
+    EDM_CUDA(cudaMemcpyAsync(base + o_u, runiform, (size_t)nlisted * 2 * sizeof(double), cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, 0));
+  unsigned long long* ncalls = reinterpret_cast<unsigned long long*>(base + o_nc);
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, 0));
+  PairParams pp = pair_params(b, type, itype, jtype, do_hills, est_hill_count, seed, step, 0.0, nall);
+  reset_pairs_kernel<<<1, 1>>>(b->d_state, ncalls);
+  long long blocks = (inum + 127) / 128;
+  if (blocks > b->n_partial) blocks = b->n_partial;
+  if (blocks < 1) blocks = 1;
+  pair_list_kernel<<<(int)blocks, 128>>>(b->bias->d, pp, nlocal, inum, reinterpret_cast<int*>(base + o_il),
+                                         reinterpret_cast<long*>(base + o_first), reinterpret_cast<int*>(base + o_jl),
+                                         b->io.as<double>(), type ? reinterpret_cast<int*>(base + o_ty) : nullptr,
+                                         runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, b->io2.as<double>(),
+                                         b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
+  sum_partials2_kernel<<<1, 256>>>((int)blocks, b->d_energy_partial, b->d_scalar);
+  count_launches(3);
+  EDM_CUDA(cudaGetLastError());
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, 0));
+  EDM_CUDA(cudaMemcpy(f, b->io2.p, bx, cudaMemcpyDeviceToHost));
+  EDM_TRY(read_pair_result(b, result, ncalls));
+  if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  return EDM_OK;
+}
+
+}  // extern "C"

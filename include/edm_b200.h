@@ -1,0 +1,234 @@
+/* edm_b200.h — C ABI of the B200-native EDM per-timestep bias engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.
+ * The reference has no plugin ABI — consumers include <edm/edm_bias.h> and link libedm.so — so
+ * each entry point below names the reference member function it stands in for (file:line into
+ * whitead/electronic-dance-music).  The C++ classes EDM::Grid / EDM::GaussGrid / EDM::EDMBias in
+ * electronic-dance-music_b200/edm/ are thin host code over exactly these calls, and
+ * INTEGRATION.md shows how fix_edm.cpp / fix_edm_pair.cpp bind to them.
+ *
+ * Conventions
+ *   - every function returns EDM_OK (0) or a negative edm_status_t; edm_last_error() gives text.
+ *     (The reference aborts through edm_error(), lib/edm.cpp:4-7; the C++ mirror keeps that.)
+ *   - "_dev" entry points take DEVICE pointers and a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream) and never synchronise; the others take HOST pointers, copy
+ *     host->device->host inside the call and return when the result is in host memory.
+ *   - all arithmetic is fp64; arrays are row-major; positions/forces are rows of `stride` doubles
+ *     of which the first `dim` are used (LAMMPS passes stride 3, the reference tests stride 1).
+ *   - there is no CPU fallback: without a CUDA device every call fails with EDM_ERR_NO_DEVICE.
+ */
+#ifndef EDM_B200_H
+#define EDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum edm_status {
+  EDM_OK = 0,
+  EDM_ERR_ARG = -1,         /* bad argument */
+  EDM_ERR_NO_DEVICE = -2,   /* no CUDA device / driver */
+  EDM_ERR_CUDA = -3,        /* a CUDA call failed */
+  EDM_ERR_STATE = -4,       /* call order violated (add_hill before pre_add_hill, ...) */
+  EDM_ERR_CAPACITY = -5,    /* accepted-hill or hill-log buffer exhausted */
+  EDM_ERR_BACKLOG_FULL = -6 /* overflow deque full: the reference aborts, lib/edm_bias.cpp:503-507 */
+} edm_status_t;
+
+typedef struct edm_grid edm_grid_t; /* Grid / GaussGrid resident in HBM */
+typedef struct edm_bias edm_bias_t; /* EDMBias step state resident in HBM */
+
+#define EDM_BUFFER_SLOTS 2048 /* BIAS_BUFFER_SIZE, lib/edm_bias.h:15 */
+#define EDM_BUFFER_DBLS 8192  /* BIAS_BUFFER_DBLS, lib/edm_bias.h:16 */
+
+const char* edm_last_error(void);
+int edm_device_count(int* count);
+/* Device-side counter-based uniform in [0,1) used when the caller passes no runiform array
+ * (stand-in for LAMMPS RanMars, lammps/fix_edm.cpp:149-151); exposed so hosts can reproduce it. */
+double edm_uniform(uint64_t seed, uint64_t step, uint64_t counter);
+
+/* ------------------------------------------------------------------ Grid / GaussGrid */
+
+/* make_grid, lib/grid.h:911 -> DimmedGrid ctor lib/grid.h:190-213 */
+int edm_grid_create(edm_grid_t** out, int device, int dim, const double* min, const double* max,
+                    const double* spacing, const int* periodic, int b_derivatives, int b_interpolate);
+/* geometry as DimmedGrid::read computes it from a PLUMED-1 header, lib/grid.h:759-806:
+ * bins[] is the "#! BIN" line, max[] the "#! MAX" line (un-extended). */
+int edm_grid_create_from_header(edm_grid_t** out, int device, int dim, const int* bins, const double* min,
+                                const double* max, const int* periodic, int b_derivatives, int b_interpolate);
+/* make_gauss_grid, lib/gaussian_grid.h:636 -> DimmedGaussGrid ctor lib/gaussian_grid.h:65-80 */
+int edm_gauss_create(edm_grid_t** out, int device, int dim, const double* min, const double* max,
+                     const double* spacing, const int* periodic, int b_interpolate, const double* sigma);
+int edm_grid_destroy(edm_grid_t* g);
+/* GaussGrid::set_boundary, lib/gaussian_grid.h:378-435 (rebuilds the McGDP tables) */
+int edm_grid_set_boundary(edm_grid_t* g, const double* min, const double* max, const int* periodic);
+/* public members of DimmedGrid / DimmedGaussGrid, lib/grid.h:876-885, lib/gaussian_grid.h:544-549.
+ * Any output pointer may be NULL.  minisize is 0 for a plain grid. */
+int edm_grid_geometry(const edm_grid_t* g, int* dim, int* n, double* dx, double* min, double* max,
+                      int* periodic, int* minisize, size_t* size);
+int edm_grid_flags(const edm_grid_t* g, int* b_derivatives, int* b_interpolate, int* is_gauss);
+int edm_grid_boundary(const edm_grid_t* g, double* bmin, double* bmax, int* bperiodic, double* sigma_sqrt2);
+/* Grid::set_interpolation, lib/grid.h:837 */
+int edm_grid_set_interpolation(edm_grid_t* g, int b_interpolate);
+/* values[size], derivs[size*dim] in the reference's layout (grid_[p], grid_deriv_[p*dim+d],
+ * dim 0 fastest, +dV/dx); derivs may be NULL.  Stand-ins for direct grid_ access and for
+ * Grid::read / Grid::write (lib/grid.h:448-503, 712-835), whose text I/O stays on the host. */
+int edm_grid_upload(edm_grid_t* g, const double* values, const double* derivs);
+int edm_grid_download(const edm_grid_t* g, double* values, double* derivs);
+/* Grid::clear, lib/grid.h:679 */
+int edm_grid_clear(edm_grid_t* g);
+/* Grid::get_value_deriv batched, lib/grid.h:390-446 / lib/gaussian_grid.h:118-138 */
+int edm_grid_eval(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der);
+int edm_grid_eval_dev(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der,
+                      void* stream);
+/* Grid::get_value batched, lib/grid.h:343-365 / lib/gaussian_grid.h:99-116 */
+int edm_grid_get_value(const edm_grid_t* g, long n, const double* x, long xstride, double* value);
+/* DimmedGrid::add_value (histogram bump), lib/grid.h:370-385; fails on interpolated grids */
+int edm_grid_hist_add(edm_grid_t* g, long n, const double* x, long xstride, const double* v);
+/* Grid::add, lib/grid.h:275-290: this += scale * other(x_p) + offset at every grid point */
+int edm_grid_add(edm_grid_t* g, const edm_grid_t* other, double scale, double offset);
+/* Grid::max_value / min_value, lib/grid.h:292-309 */
+int edm_grid_minmax(const edm_grid_t* g, double* min_value, double* max_value);
+/* GaussGrid::remap, lib/gaussian_grid.h:504-541, on one point (in place) */
+int edm_grid_remap(const edm_grid_t* g, double* x);
+/* GaussGrid::add_value batched, lib/gaussian_grid.h:176-372: deposits n hills in list order and
+ * returns each hill's integrated bias.  Equivalent to n sequential add_value calls. */
+int edm_gauss_deposit(edm_grid_t* g, long n, const double* centres, const double* heights, double* bias_added);
+int edm_gauss_deposit_dev(edm_grid_t* g, long n, const double* centres, const double* heights,
+                          double* bias_added, void* stream);
+
+/* ------------------------------------------------------------------ EDMBias */
+
+typedef struct edm_bias_params { /* the numbers read_input parses, lib/edm_bias.cpp:1009-1064 */
+  int dim;
+  int b_tempering;
+  int b_targeting;
+  double global_tempering;
+  double bias_factor;
+  double boltzmann_factor; /* kB*T, lib/edm_bias.cpp:267 */
+  double hill_prefactor;
+  double bias_per_step;
+  double hill_density;    /* < 0: every candidate deposits, lib/edm_bias.cpp:543 */
+  double expected_target; /* lib/edm_bias.cpp:1062 */
+  double total_volume;    /* lib/edm_bias.cpp:211-220 */
+} edm_bias_params_t;
+
+typedef struct edm_bias_state { /* lib/edm_bias.h:130,161-178 */
+  double cum_bias;
+  double temp_hill_cum; /* last completed round's added bias */
+  long long steps;
+  int hills_added;
+  int skipped;          /* b_skip_hill_add_ of the last round */
+  long backlog_left, backlog_right;
+  long n_accepted;      /* candidates that passed selection in the last round */
+  long log_dropped;     /* hill-log records lost to a full log buffer */
+} edm_bias_state_t;
+
+typedef struct edm_hill_event { /* one HILLS line, lib/edm_bias.cpp:586-599 */
+  long long steps;
+  int type; /* 'h','u','b','v' (lib/edm_bias.h:20-25) */
+  int hills_added;
+  double pos[3];
+  double height;
+  double bias_added;
+  double cum_over_vol;
+} edm_hill_event_t;
+
+/* bias and cv_hist are borrowed (the C++ EDMBias owns them); target may be NULL. */
+int edm_bias_create(edm_bias_t** out, edm_grid_t* bias, edm_grid_t* cv_hist, edm_grid_t* target,
+                    const edm_bias_params_t* params);
+int edm_bias_destroy(edm_bias_t* b);
+int edm_bias_state(edm_bias_t* b, edm_bias_state_t* out);
+int edm_bias_set_cum_bias(edm_bias_t* b, double cum_bias);
+/* overflow deque, lib/edm_bias.h:175-177: buffer holds EDM_BUFFER_DBLS doubles */
+int edm_bias_backlog_get(edm_bias_t* b, long* left, long* right, double* buffer);
+int edm_bias_backlog_set(edm_bias_t* b, long left, long right, const double* buffer);
+/* drains the device hill log (HILLS records in deposit order) */
+int edm_bias_log_read(edm_bias_t* b, edm_hill_event_t* out, long cap, long* n);
+
+/* EDMBias::update_forces, lib/edm_bias.cpp:276-295: f[i][0..dim) -= dV/dx(x[i]), returns sum V.
+ * mask may be NULL when apply_mask < 0. */
+int edm_bias_update_forces(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                           const int* mask, int apply_mask, double* energy);
+/* energy is a DEVICE pointer to one double */
+int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                               const int* mask, int apply_mask, double* energy, void* stream);
+
+/* EDMBias::add_hills, lib/edm_bias.cpp:401-411 (= pre_add_hill(n); add_hill per masked atom;
+ * post_add_hill()).  runiform may be NULL: uniforms then come from edm_uniform(seed, step, i). */
+int edm_bias_add_hills(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,
+                       const int* mask, int apply_mask, uint64_t seed, uint64_t step);
+int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,
+                           const int* mask, int apply_mask, uint64_t seed, uint64_t step, void* stream);
+
+/* The streaming triple, lib/edm_bias.cpp:413-442, 528-563, 565-583.  add_hill_batch may be called
+ * any number of times between pre and post; candidates keep their call order. */
+int edm_bias_pre_add_hill(edm_bias_t* b, int est_hill_count);
+int edm_bias_add_hill_batch(edm_bias_t* b, long n, const double* x, const double* runiform);
+int edm_bias_post_add_hill(edm_bias_t* b);
+
+/* ------------------------------------------------------------------ pair-distance CV (fix edm_pair) */
+
+typedef struct edm_pair_result {
+  double energy;        /* sum of V(r) over evaluated pairs, fix_edm_pair.cpp:217 */
+  long long n_pairs;    /* pairs evaluated (update_force-equivalents) */
+  long long n_calls;    /* hill proposals made: the caller's next est_hill_count, fix_edm_pair.cpp:245 */
+} edm_pair_result_t;
+
+/* FixEDMPair::post_force, lammps/fix_edm_pair.cpp:139-256, for a periodic orthorhombic box
+ * [0,box)^3 with the neighbour search done on the device: every pair i<j with minimum-image
+ * distance < cutoff whose types match (itype,jtype) is evaluated once (half list, both atoms
+ * local), forces are accumulated into f, and if do_hills each pair proposes two hills
+ * (fix_edm_pair.cpp:230-236) with uniforms edm_uniform(seed, step, 2*(i*natoms+j)+{0,1}),
+ * accepted hills ordered by (i, j).  Lib-level order: all evaluations see the start-of-step bias
+ * (SURVEY 3.2).  type may be NULL (all atoms match). */
+int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype,
+                        int jtype, const double* box, double cutoff, int do_hills, long long est_hill_count,
+                        uint64_t seed, uint64_t step, edm_pair_result_t* result);
+/* result is a HOST pointer filled after an internal stream synchronise only if non-NULL */
+int edm_pair_step_cells_dev(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype,
+                            int jtype, const double* box, double cutoff, int do_hills,
+                            long long est_hill_count, uint64_t seed, uint64_t step, edm_pair_result_t* result,
+                            void* stream);
+/* Same loop over a caller-supplied half neighbour list in LAMMPS NeighList form flattened to CSR
+ * (ilist[inum], first[inum+1] offsets into jlist[]; j already masked with NEIGHMASK; j >= nlocal
+ * are ghosts whose force is not updated, fix_edm_pair.cpp:223).  runiform (2 per listed pair, in
+ * list order) may be NULL: uniforms then come from edm_uniform(seed, step, 2*k+{0,1}). */
+int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type,
+                       int itype, int jtype, long inum, const int* ilist, const long* first, const int* jlist,
+                       int do_hills, long long est_hill_count, const double* runiform, uint64_t seed,
+                       uint64_t step, edm_pair_result_t* result);
+
+/* ------------------------------------------------------------------ multi-GPU hill exchange */
+
+/* Replaces flush_buffers / check_for_flush, lib/edm_bias.cpp:614-706 (broadcast mode): each rank
+ * selects candidates locally (edm_*_select), packs its accepted hills into a fixed-capacity device
+ * block, the caller all-gathers the blocks (NCCL), and every rank commits the rank-major
+ * concatenation so all replicas deposit identical hills in one canonical order.
+ * Block layout: double[0] = count, then count records of (dim) doubles, capacity cap records. */
+size_t edm_hill_block_doubles(int dim, long cap);
+int edm_bias_select_dev(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,
+                        const int* mask, int apply_mask, long long est_hill_count, uint64_t seed, uint64_t step,
+                        uint64_t first_counter, void* stream);
+int edm_pair_select_cells_dev(edm_bias_t* b, long natoms, const double* x, double* f, const int* type,
+                              int itype, int jtype, const double* box, double cutoff, long long est_hill_count,
+                              uint64_t seed, uint64_t step, double* energy_dev, void* stream);
+int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream);
+int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, long cap,
+                              long long est_hill_count, void* stream);
+
+/* ------------------------------------------------------------------ measurement hooks (bench.py) */
+
+/* Kernels launched by this library since load (all devices, this process). */
+int edm_launch_count(long long* count);
+/* When on, the pair kernels are bracketed by CUDA events on their launch stream. */
+int edm_bias_set_profiling(edm_bias_t* b, int on);
+/* Duration of the last profiled pair kernel in ms (synchronises on its end event). */
+int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDM_B200_H */

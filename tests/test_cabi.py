@@ -1,0 +1,88 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every symbol
+include/edm_b200.h declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "edm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(edm_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def edm():
+    import edm_b200
+    if not os.path.exists(edm_b200.LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "electronic-dance-music_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_lib()
+    return edm_b200
+
+
+def test_library_exports_every_declared_symbol(edm):
+    lib = edm.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 45
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_binding_covers_every_declared_symbol(edm):
+    assert set(declared_symbols()) <= set(edm.EXPORTS), set(declared_symbols()) - set(edm.EXPORTS)
+
+
+def test_header_cites_the_reference_interface():
+    text = open(os.path.join(ROOT, "include", "edm_b200.h")).read()
+    for ref in ("lib/grid.h", "lib/gaussian_grid.h", "lib/edm_bias.cpp", "lammps/fix_edm_pair.cpp"):
+        assert ref in text
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "edm_b200.h"\nint main(void){ edm_bias_params_t p; (void)p; return 0; }\n')
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_uniform_matches_oracle_rng(edm, port):
+    L = port.load("port")
+    for seed, step, ctr in [(0, 0, 0), (1, 2, 3), (20261018, 77, 2 ** 40 + 5), (2 ** 63, 2 ** 31, 2 ** 62)]:
+        assert edm.uniform(seed, step, ctr) == L.uniform(seed, step, ctr)
+    u = port.uniform_fill(9, 4, 100, 1000)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.05
+
+
+def test_no_cpu_fallback_without_a_gpu(edm):
+    if edm.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(edm.EdmError) as e:
+        edm.GaussGrid(1, [0], [1], [0.1], [0], 1, [0.1])
+    assert "no CUDA device" in str(e.value)
+    h = C.c_void_p()
+    rc = edm.lib().edm_grid_create(C.byref(h), 0, 1, (C.c_double * 1)(0), (C.c_double * 1)(1), (C.c_double * 1)(0.1),
+                                   (C.c_int * 1)(0), 0, 0)
+    assert rc == -2 and not h.value
+
+
+def test_product_never_touches_the_oracle():
+    """The product tree may not include, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "electronic-dance-music_b200")
+    bad = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".h", ".cpp", ".py", ".hpp")):
+                text = open(os.path.join(d, f), errors="ignore").read()
+                if re.search(r"oracle/|pyoracle|libedm_oracle|libedm_ref|edm_oracle\.h", text):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad

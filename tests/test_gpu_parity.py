@@ -1,0 +1,424 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs.  Bars (BASELINE.json north_star): hill selection and buffering decisions bit-exact;
+energies, forces and grid values within 1e-10 relative in fp64.
+
+"Relative" is taken per element against max(|ref|, FLOOR * max|ref|) with FLOOR = 1e-2: interpolated
+derivatives and summed pair forces are differences of O(V/dx) terms and pass through zero, where the
+reference's own rounding noise (a few ulp(V)/dx, about 1e-13 of the array's scale for dx = 0.00025)
+exceeds 1e-10 of the element.  So every element larger than 1 % of the array's largest magnitude is
+held to 1e-10 of its own size, and nothing is ever looser than 1e-12 of the array's scale.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+FLOOR = 1e-2
+
+
+def assert_close(dev, refv, what, rtol=RTOL):
+    dev, refv = np.asarray(dev, float), np.asarray(refv, float)
+    assert dev.shape == refv.shape, what
+    scale = np.abs(refv).max() if refv.size else 0.0
+    denom = np.maximum(np.abs(refv), FLOOR * scale)
+    denom[denom == 0] = 1.0
+    err = np.abs(dev - refv) / denom
+    worst = err.max() if err.size else 0.0
+    assert worst <= rtol, "%s: worst relative error %.3e (tolerance %.1e)" % (what, worst, rtol)
+
+
+@pytest.fixture(scope="module")
+def edm():
+    import edm_b200
+    if edm_b200.device_count() == 0:
+        pytest.fail("no CUDA device visible: the GPU tests cannot fall back to the CPU")
+    return edm_b200
+
+
+def write_edm(tmp_path, name, text):
+    p = tmp_path / name
+    p.write_text(text + "\nhills_filename %s/HILLS_%s\nhistogram_filename %s/HIST_%s\n" % (tmp_path, name, tmp_path, name))
+    return str(p)
+
+
+GRID_CASES = {
+    # name: (dim, min, max, spacing, grid periodic, sigma, boundary (min, max, periodic) or None)
+    "1d_rdf_mcgdp": (1, [1.68], [5.0], [0.00025], [0], [0.025], None),
+    "1d_periodic": (1, [0.0], [10.0], [10.0 / 1024], [1], [0.025], None),
+    "1d_sub_periodic_boundary": (1, [-2.0], [7.0], [0.1], [0], [0.1], ([0.0], [10.0], [1])),
+    "1d_inner_mcgdp": (1, [-100.0], [100.0], [1.0], [1], [10.0], ([-50.0], [50.0], [0])),
+    "1d_window_wider_than_grid": (1, [2.0], [10.0], [1.0], [1], [1.0], None),
+    "2d_periodic": (2, [0.0, 0.0], [8.0, 8.0], [0.0625, 0.0625], [1, 1], [0.25, 0.25], None),
+    "2d_mixed": (2, [0.0, 0.0], [10.0, 5.0], [0.1, 0.13], [1, 0], [0.3, 0.25], ([0.0, 0.0], [10.0, 10.0], [1, 0])),
+    "2d_mcgdp": (2, [0.0, 1.0], [4.0, 3.0], [0.05, 0.04], [0, 0], [0.2, 0.15], None),
+    "3d_periodic": (3, [0.0, 0.0, 0.0], [8.0, 8.0, 8.0], [0.25, 0.25, 0.25], [1, 1, 1], [0.5, 0.5, 0.5], None),
+    "3d_inner_mcgdp": (3, [-10.0] * 3, [10.0] * 3, [0.9, 1.1, 1.4], [1, 1, 1], [3.0, 3.0, 3.0],
+                       ([-5.0] * 3, [5.0] * 3, [0, 0, 0])),
+}
+
+
+def make_pair(edm, port, case):
+    dim, mn, mx, sp, per, sg, bnd = GRID_CASES[case]
+    gd = edm.GaussGrid(dim, mn, mx, sp, per, 1, sg)
+    go = port.GaussGrid("port", dim, mn, mx, sp, per, 1, sg)
+    if bnd is not None:
+        gd.set_boundary(*bnd)
+        go.set_boundary(*bnd)
+    return gd, go
+
+
+def sample_points(rng, case, n, pad=0.3):
+    dim, mn, mx, _, _, _, bnd = GRID_CASES[case]
+    lo = np.array(bnd[0] if bnd else mn, float)
+    hi = np.array(bnd[1] if bnd else mx, float)
+    span = hi - lo
+    return rng.uniform(lo - pad * span, hi + pad * span, size=(n, dim))
+
+
+@pytest.mark.parametrize("case", sorted(GRID_CASES))
+def test_geometry_matches_oracle(edm, port, case):
+    gd, go = make_pair(edm, port, case)
+    a, b = gd.info(), go.info()
+    for k in ("n", "dx", "min", "max", "minisize"):
+        assert np.array_equal(a[k], b[k]), k
+    assert gd.size == go.size
+
+
+@pytest.mark.parametrize("case", sorted(GRID_CASES))
+def test_deposit_and_eval_parity(edm, port, case):
+    """K3 + K1: batched add_value then batched get_value_deriv, vs the oracle's sequential calls."""
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    gd, go = make_pair(edm, port, case)
+    dim = GRID_CASES[case][0]
+    nh = 300 if dim < 3 else 60
+    centres = sample_points(rng, case, nh, pad=0.15)
+    # hills exactly on the walls / corners are part of the reference's own tests (edm_test.cpp:593-601)
+    bnd = GRID_CASES[case][6] or (GRID_CASES[case][1], GRID_CASES[case][2], None)
+    centres[0] = bnd[0]
+    centres[1] = bnd[1]
+    heights = rng.uniform(0.5, 1.5, nh)
+    heights[5] = -0.3  # undo hills are negative (lib/edm_bias.cpp:479)
+    ba_d = gd.add_values(centres, heights)
+    ba_o = go.add_values(centres, heights)
+    assert np.array_equal(ba_d == 0.0, ba_o == 0.0), "rejected-hill decisions differ"
+    assert_close(ba_d, ba_o, "bias_added")
+    vd, dd = gd.get_arrays()
+    vo, do = go.get_arrays()
+    assert np.array_equal(vd == 0.0, vo == 0.0), "support / boundary membership differs"
+    assert_close(vd, vo, "grid values")
+    assert_close(dd, do, "grid derivatives")
+    # evaluation on the oracle's grid (bit-identical tables), incl. points outside grid and boundary
+    gd.set_arrays(vo, do)
+    x = sample_points(rng, case, 20000)
+    val_d, der_d = gd.eval(x)
+    val_o, der_o = go.eval(x)
+    assert np.array_equal(val_d == 0.0, val_o == 0.0), "in-bounds decisions differ"
+    assert_close(val_d, val_o, "interpolated value")
+    assert_close(der_d, der_o, "interpolated derivative")
+    gv_d = gd.get_value(x[:2000])
+    gv_o = go.get_value(x[:2000])
+    assert_close(gv_d, gv_o, "get_value")
+
+
+def test_deposit_matches_compiled_reference(edm, ref):
+    """Same check against the UNMODIFIED reference (oracle/_ref), 1-D pair-RDF geometry."""
+    rng = np.random.default_rng(7)
+    gd = edm.GaussGrid(1, [1.68], [5.0], [0.00025], [0], 1, [0.025])
+    gr = ref.GaussGrid("ref", 1, [1.68], [5.0], [0.00025], [0], 1, [0.025])
+    c = rng.uniform(1.5, 5.2, 400)
+    h = rng.uniform(1e-5, 1e-4, 400)
+    ba_d, ba_r = gd.add_values(c, h), gr.add_values(c, h)
+    assert_close(ba_d, ba_r, "bias_added vs reference")
+    vd, dd = gd.get_arrays()
+    vr, dr = gr.get_arrays()
+    assert_close(vd, vr, "grid vs reference")
+    assert_close(dd, dr, "grid derivative vs reference")
+    x = rng.uniform(1.0, 5.5, 50000)
+    a, b = gd.eval(x), gr.eval(x)
+    assert_close(a[0], b[0], "value vs reference")
+    assert_close(a[1], b[1], "derivative vs reference")
+
+
+def test_large_batch_deposit_chunks(edm, port):
+    """The multi-chunk owner-computes path (batch >> one chunk) against the oracle, and the size-
+    independent property the reference tests (edm_test.cpp:570-573): sum(bias_added) = grid integral."""
+    rng = np.random.default_rng(11)
+    gd = edm.GaussGrid(1, [1.68], [5.0], [0.00025], [0], 1, [0.025])
+    go = port.GaussGrid("port", 1, [1.68], [5.0], [0.00025], [0], 1, [0.025])
+    n = 6000
+    c = rng.uniform(1.68, 5.0, n)
+    h = np.full(n, 1e-6)
+    ba_d, ba_o = gd.add_values(c, h), go.add_values(c, h)
+    assert_close(ba_d, ba_o, "bias_added")
+    vd, dd = gd.get_arrays()
+    vo, do = go.get_arrays()
+    assert_close(vd, vo, "grid values")
+    assert_close(dd, do, "grid derivatives")
+    dx = gd.info()["dx"][0]
+    assert abs(vd.sum() * dx - ba_d.sum()) <= 1e-9 * abs(ba_d.sum())
+
+
+def test_remap_cases(edm, port):
+    """The remap table of edm_test.cpp:252-333."""
+    gd = edm.GaussGrid(2, [0, 0], [10, 5], [1, 1], [1, 0], 1, [0.1, 0.1])
+    go = port.GaussGrid("port", 2, [0, 0], [10, 5], [1, 1], [1, 0], 1, [0.1, 0.1])
+    for g in (gd, go):
+        g.set_boundary([0, 0], [10, 10], [1, 1])
+    for p, want in [([0, 1], [0, 1]), ([-1, 1], [9, 1]), ([9, 6], [9, 6]), ([9, 11], [9, 1]), ([9, 9], [9, -1]),
+                    ([9, -1], [9, -1])]:
+        a, b = gd.remap(p), go.remap(p)
+        assert np.array_equal(a, b)
+        assert np.allclose(a, want, atol=0.3)
+
+
+BIAS_CASES = {
+    "c1_sanity_density": dict(
+        text="tempering 0\nhill_prefactor 0.25\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.009765625\n"
+             "bias_sigma 0.025\nhill_density 250",
+        T=1.0, kB=1.0, sub=([0.0], [10.0]), periodic=[1], skin=[0.0], n=20000, lo=-1.0, hi=11.0, steps=6),
+    "c2_rdf_threshold_tempering": dict(
+        text="tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.1\n"
+             "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025",
+        T=300.0, kB=0.0019872, sub=([1.68], [5.0]), periodic=[0], skin=[0.0], n=30000, lo=0.5, hi=5.5, steps=6),
+    "c5_rdf_tight_limiter_backlog": dict(
+        text="tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.0002\n"
+             "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025",
+        T=300.0, kB=0.0019872, sub=([1.68], [5.0]), periodic=[0], skin=[0.0], n=30000, lo=0.5, hi=5.5, steps=14),
+    "1d_local_well_tempering": dict(
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.5\nbias_per_step 1000\n"
+             "hill_density 120\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.01\nbias_sigma 0.1",
+        T=300.0, kB=0.0019872, sub=([0.0], [10.0]), periodic=[1], skin=[0.0], n=5000, lo=0.0, hi=10.0, steps=5),
+    "2d_local_well_tempering": dict(
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 100\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\n"
+             "bias_sigma 0.25 0.25",
+        T=300.0, kB=0.0019872, sub=([0.0, 0.0], [8.0, 8.0]), periodic=[1, 1], skin=[0.0, 0.0], n=4000, lo=0.0, hi=8.0,
+        steps=4),
+    "3d_all_candidates_deposit": dict(
+        text="tempering 0\nhill_prefactor 1.0\nbias_per_step 0.4\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
+             "bias_spacing 0.25 0.25 0.25\nbias_sigma 0.5 0.5 0.5",
+        T=1.0, kB=1.0, sub=([0.0] * 3, [8.0] * 3), periodic=[1, 1, 1], skin=[0.0] * 3, n=40, lo=0.0, hi=8.0, steps=4),
+}
+
+
+def run_bias_case(edm, port, tmp_path, name, masked=False):
+    cfg = BIAS_CASES[name]
+    f = write_edm(tmp_path, name + ".edm", cfg["text"])
+    sublo, subhi = cfg["sub"]
+    bo = port.Bias("port", f)
+    bo.setup(cfg["T"], cfg["kB"])
+    bo.subdivide(sublo, subhi, sublo, subhi, cfg["periodic"], cfg["skin"])
+    bd = edm.bias_from_edm(f, cfg["T"], cfg["kB"], sublo, subhi, sublo, subhi, cfg["periodic"], cfg["skin"])
+    D = bo.dim
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    n = cfg["n"]
+    mask = None
+    if masked:
+        mask = rng.integers(0, 4, n).astype(np.int32)
+        bo.set_mask(mask)
+    for step in range(cfg["steps"]):
+        x = np.ascontiguousarray(rng.uniform(cfg["lo"], cfg["hi"], size=(n, 3)))  # LAMMPS rows: stride 3
+        u = rng.uniform(0, 1, n)
+        fo = np.zeros((n, 3))
+        fd = np.zeros((n, 3))
+        am = 2 if masked else -1
+        eo = bo.update_forces(x, fo, am)
+        ed = bd.update_forces(x, fd, mask, am)
+        if step > 0:
+            assert abs(ed - eo) <= RTOL * abs(eo), "energy step %d: %r vs %r" % (step, ed, eo)
+            assert_close(fd, fo, "forces step %d" % step)
+        bo.add_hills(x, u, am)
+        bd.add_hills(x, u, mask, am)
+    return bd, bo
+
+
+def compare_bias(bd, bo):
+    ld, lo = bd.log(), bo.log()
+    assert len(ld) == len(lo), "number of hill events differs: %d vs %d" % (len(ld), len(lo))
+    # decisions: bit-exact
+    for k in ("steps", "type", "hills_added"):
+        assert np.array_equal(ld[k], lo[k]), "hill log field %s differs" % k
+    assert np.array_equal(ld["pos"], lo["pos"]), "hill centres differ"
+    assert_close(ld["height"], lo["height"], "hill heights")
+    assert_close(ld["bias_added"], lo["bias_added"], "bias_added")
+    assert_close(ld["cum_over_vol"], lo["cum_over_vol"], "cum_bias/volume")
+    sd, po = bd.state(), bo.params()
+    assert sd["steps"] == int(po["steps"])
+    assert abs(sd["cum_bias"] - po["cum_bias"]) <= RTOL * abs(po["cum_bias"])
+    l_d, r_d, buf_d = bd.backlog()
+    l_o, r_o, buf_o = bo.backlog()
+    assert (l_d, r_d) == (l_o, r_o), "backlog indices differ"
+    assert_close(buf_d, buf_o, "backlog contents")
+    vd, dd = bd.bias_grid.get_arrays()
+    vo, do = bo.gauss.get_arrays()
+    assert_close(vd, vo, "bias grid")
+    assert_close(dd, do, "bias grid derivative")
+    hd = bd.hist_grid.get_arrays()[0]
+    ho = bo.hist.get_arrays()[0]
+    assert np.array_equal(hd, ho), "CV histogram differs"
+    return ld
+
+
+@pytest.mark.parametrize("name", sorted(BIAS_CASES))
+def test_bias_round_parity(edm, port, tmp_path, name):
+    """K4 + K3 + K1 through update_forces/add_hills over several steps."""
+    bd, bo = run_bias_case(edm, port, tmp_path, name)
+    log = compare_bias(bd, bo)
+    assert len(log) > 0
+
+
+def test_bias_backlog_exercised(edm, port, tmp_path):
+    """The tight-limiter case really drains a backlog: b/v/u events and skipped rounds appear."""
+    bd, bo = run_bias_case(edm, port, tmp_path, "c5_rdf_tight_limiter_backlog")
+    log = compare_bias(bd, bo)
+    types = set(chr(t) for t in log["type"])
+    assert {"h", "u", "b", "v"} <= types, types
+    assert bd.backlog()[1] > 0
+
+
+def test_bias_masked_atoms(edm, port, tmp_path):
+    bd, bo = run_bias_case(edm, port, tmp_path, "c2_rdf_threshold_tempering", masked=True)
+    compare_bias(bd, bo)
+
+
+def test_streaming_triple_matches_add_hills(edm, port, tmp_path):
+    """pre_add_hill / add_hill xN / post_add_hill (two batches) against the oracle's triple."""
+    cfg = BIAS_CASES["c5_rdf_tight_limiter_backlog"]
+    f = write_edm(tmp_path, "triple.edm", cfg["text"])
+    bo = port.Bias("port", f)
+    bo.setup(cfg["T"], cfg["kB"])
+    bo.subdivide([1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    bd = edm.bias_from_edm(f, cfg["T"], cfg["kB"], [1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    rng = np.random.default_rng(5)
+    for step in range(8):
+        r = rng.uniform(0.5, 5.5, 20000)
+        u = rng.uniform(0, 1, 20000)
+        bo.pre_add_hill(20000)
+        bo.add_hill_many(r, u)
+        bo.post_add_hill()
+        bd.pre_add_hill(20000)
+        bd.add_hill_many(r[:7000], u[:7000])
+        bd.add_hill_many(r[7000:], u[7000:])
+        bd.post_add_hill()
+    compare_bias(bd, bo)
+
+
+def test_notebook_golden_vector(edm, tmp_path):
+    """python-example/EDM.ipynb:103 — the reference's only full-precision known answer."""
+    f = write_edm(tmp_path, "nb.edm", "tempering 0\nhill_prefactor 1.0\ndimension 1\nbox_low 0.0\nbox_high 1.0\n"
+                                      "bias_spacing 0.01\nbias_sigma 0.5")
+    bd = edm.bias_from_edm(f, 1.0, 1.0, [0.0], [10.0], [0.0], [10.0], [0], [0.0])
+    bd.pre_add_hill(1)
+    bd.add_hill_many([0.25], [0.0])
+    bd.post_add_hill()
+    x = np.array([[0.24]])
+    force = np.zeros((1, 1))
+    e = bd.update_forces(x, force)
+    assert abs(e - 1.1002417338159258) <= 1e-10 * 1.1002417338159258
+    assert abs(-force[0, 0] - (-0.6144025830861709)) <= 1e-10 * 0.6144025830861709
+
+
+def make_atoms(rng, n, L):
+    return np.ascontiguousarray(rng.uniform(0, L, size=(n, 3)))
+
+
+PAIR_EDM = ("tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.1\n"
+            "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025")
+
+
+def make_pair_biases(edm, port, tmp_path, text=PAIR_EDM):
+    f = write_edm(tmp_path, "pair.edm", text)
+    bo = port.Bias("port", f)
+    bo.setup(300.0, 0.0019872)
+    bo.subdivide([1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    bd = edm.bias_from_edm(f, 300.0, 0.0019872, [1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    return bd, bo
+
+
+def test_pair_cells_parity(edm, port, tmp_path):
+    """K2: cell-list pair step (evaluate all pairs, force scatter, two hill proposals per pair)
+    against the oracle's restated fix_edm_pair loop over a half list of the same pairs."""
+    rng = np.random.default_rng(21)
+    n, L, rc = 6000, 36.0, 5.0
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+    est = 2 * 150000
+    for step in range(4):
+        x = make_atoms(rng, n, L)
+        pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
+        # the same counter-based uniforms the device draws: key 2*(i*n+j)+{0,1}
+        keys = (pi.astype(np.uint64) * np.uint64(n) + pj.astype(np.uint64)) * np.uint64(2)
+        u = np.empty(2 * pi.size)
+        seed = 99
+        u[0::2] = [edm.uniform(seed, step, int(k)) for k in keys]
+        u[1::2] = [edm.uniform(seed, step, int(k) + 1) for k in keys]
+        fo = np.zeros((n, 3))
+        fd = np.zeros((n, 3))
+        eo, r_o = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=est, uniforms=u)
+        res = bd.pair_step_cells(x, fd, [L, L, L], rc, do_hills=True, est=est, seed=seed, step=step)
+        assert res["n_pairs"] == pi.size, "pair sets differ: %d vs %d" % (res["n_pairs"], pi.size)
+        assert res["n_calls"] == 2 * pi.size
+        if step > 0:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "pair forces step %d" % step)
+        est = res["n_calls"]
+    compare_bias(bd, bo)
+
+
+def test_pair_list_parity(edm, port, tmp_path):
+    """The neighbour-list form with caller-supplied uniforms and ghost atoms (j >= nlocal)."""
+    rng = np.random.default_rng(22)
+    n, L, rc = 3000, 30.0, 5.0
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+    for step in range(3):
+        x = make_atoms(rng, n, L)
+        pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
+        keep = np.all(sh == 0.0, axis=1)  # plain (non-image) pairs: a list over real coordinates
+        pi, pj = pi[keep], pj[keep]
+        u = rng.uniform(0, 1, 2 * pi.size)
+        fo = np.zeros((n, 3))
+        fd = np.zeros((n, 3))
+        eo, _ = bo.pair_step(pi, pj, x, fo, do_hills=True, est=2 * pi.size, uniforms=u)
+        ilist = np.arange(n, dtype=np.int32)
+        first = np.zeros(n + 1, np.int64)
+        np.add.at(first, pi + 1, 1)
+        first = np.cumsum(first)
+        res = bd.pair_step_list(x, fd, n, ilist, first, pj, do_hills=True, est=2 * pi.size, runiform=u)
+        assert res["n_pairs"] == pi.size
+        if step > 0:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "list forces step %d" % step)
+    compare_bias(bd, bo)
+
+
+def test_full_size_properties_pair_rdf(edm):
+    """BASELINE configs[1] at full size (10^6 atoms): size-independent properties only —
+    Newton's third law (total bias force = 0), pair count against the ideal-gas expectation,
+    energy = sum over a recomputation with forces off, determinism of the decisions."""
+    rng = np.random.default_rng(1234 + 1)
+    n, rc = 1_000_000, 5.0
+    L = (n / 0.1) ** (1.0 / 3.0)
+    import tempfile
+    d = tempfile.mkdtemp()
+    f = os.path.join(d, "c2.edm")
+    open(f, "w").write(PAIR_EDM + "\nhills_filename %s/H\nhistogram_filename %s/G\n" % (d, d))
+    bd = edm.bias_from_edm(f, 300.0, 0.0019872, [1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    x = make_atoms(rng, n, L)
+    est = 2 * 26_000_000
+    logs = []
+    for step in range(3):
+        fd = np.zeros((n, 3))
+        res = bd.pair_step_cells(x, fd, [L, L, L], rc, do_hills=True, est=est, seed=5, step=step)
+        expect = n * (4.0 / 3.0) * np.pi * rc ** 3 * 0.1 / 2
+        assert abs(res["n_pairs"] - expect) < 0.01 * expect
+        if step > 0:
+            assert np.abs(fd).max() > 0
+            assert np.abs(fd.sum(axis=0)).max() <= 1e-9 * np.abs(fd).sum()
+        est = res["n_calls"]
+    log = bd.log()
+    assert len(log) > 300 and bd.state()["steps"] == 3
+    # hills land where pairs are: inside [0, rc)
+    assert log["pos"][:, 0].min() >= 0 and log["pos"][:, 0].max() < rc
