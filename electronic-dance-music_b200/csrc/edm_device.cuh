@@ -376,4 +376,13 @@ __host__ __device__ __forceinline__ double uniform_from_key(uint64_t key, uint64
   return (double)(bits >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// pair proposals: one hash per pair, one 32-bit uniform per proposal (LAMMPS' RanMars has 24 bits)
+__host__ __device__ __forceinline__ uint64_t pair_bits(uint64_t key, uint64_t pairkey) {
+  return mix64(key + pairkey * 0x9E3779B97F4A7C15ULL);
+}
+__host__ __device__ __forceinline__ double pair_uniform_from_bits(uint64_t bits, int which) {
+  uint64_t half = which == 0 ? (bits >> 32) : (bits & 0xffffffffULL);
+  return (double)half * (1.0 / 4294967296.0);
+}
+
 }  // namespace edm

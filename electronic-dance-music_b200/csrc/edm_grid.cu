@@ -605,6 +605,10 @@ int edm_device_count(int* count) {
   return EDM_OK;
 }
 
+double edm_uniform_pair(uint64_t seed, uint64_t step, uint64_t pairkey, int which) {
+  return pair_uniform_from_bits(pair_bits(uniform_key(seed, step), pairkey), which);
+}
+
 int edm_launch_count(long long* count) {
   if (count) *count = g_launches.load();
   return EDM_OK;

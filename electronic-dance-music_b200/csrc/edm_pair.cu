@@ -3,6 +3,7 @@
 // two-per-pair hill proposals.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "edm_host.h"
@@ -24,6 +25,8 @@ struct PairParams {
   int itype, jtype, use_types;
   int do_hills, accept_all;
   double thresh;
+  uint64_t thresh_bits;  // ceil(thresh * 2^32), saturated
+  int dbg;
   uint64_t key;
   double rc2;
   long natoms;
@@ -84,11 +87,11 @@ __global__ void cell_fill_kernel(long n, const int* __restrict__ cell_of, const 
 
 // canonical order inside a cell (ascending atom index) + gather of positions/types into slot order,
 // so the result does not depend on the order the atomics above happened to resolve in
-__global__ void cell_sort_gather_kernel(int ncell, const int* __restrict__ start, int* __restrict__ order,
+__global__ void cell_sort_gather_kernel(CellGrid cg, const int* __restrict__ start, int* __restrict__ order,
                                         const double* __restrict__ x, const int* __restrict__ type,
-                                        double* __restrict__ xs, int* __restrict__ ts) {
+                                        double* __restrict__ xs, float* __restrict__ xs32, int* __restrict__ ts) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncell) return;
+  if (c >= cg.ncell) return;
   int lo = start[c], hi = start[c + 1];
   for (int a = lo + 1; a < hi; a++) {
     int v = order[a];
@@ -99,11 +102,18 @@ __global__ void cell_sort_gather_kernel(int ncell, const int* __restrict__ start
     }
     order[b + 1] = v;
   }
+  // cell-relative fp32 copy for the pair kernel's prefilter (error ~cs * 6e-8, box-size independent)
+  const double cx = (c % cg.nc[0]) * cg.cs[0], cy = ((c / cg.nc[0]) % cg.nc[1]) * cg.cs[1];
+  const double cz = (c / (cg.nc[0] * cg.nc[1])) * cg.cs[2];
   for (int a = lo; a < hi; a++) {
     int i = order[a];
-    xs[3 * (long)a + 0] = x[3 * (long)i + 0];
-    xs[3 * (long)a + 1] = x[3 * (long)i + 1];
-    xs[3 * (long)a + 2] = x[3 * (long)i + 2];
+    const double px = x[3 * (long)i + 0], py = x[3 * (long)i + 1], pz = x[3 * (long)i + 2];
+    xs[3 * (long)a + 0] = px;
+    xs[3 * (long)a + 1] = py;
+    xs[3 * (long)a + 2] = pz;
+    xs32[3 * (long)a + 0] = (float)(px - cx);
+    xs32[3 * (long)a + 1] = (float)(py - cy);
+    xs32[3 * (long)a + 2] = (float)(pz - cz);
     if (ts) ts[a] = type ? type[i] : 0;
   }
 }
@@ -118,16 +128,19 @@ __device__ __forceinline__ double pair_eval(const GridDesc& g, double r, double&
   return v;
 }
 
+// The two hill proposals of a pair (lammps/fix_edm_pair.cpp:230-236) draw their uniforms from one
+// hash: u_which = 32-bit half of pair_bits() * 2^-32 (edm_uniform_pair).  u < thresh is decided on
+// the integers: bits32 < ceil(thresh * 2^32).
 __device__ __forceinline__ void propose_hills(const PairParams& pp, unsigned long long pairkey, double r, BiasDev* st,
                                               HillAccepted* acc) {
+  const uint64_t bits = pair_bits(pp.key, pairkey);
 #pragma unroll
   for (int which = 0; which < 2; which++) {
-    unsigned long long k = 2ULL * pairkey + which;
-    bool take = pp.accept_all || (uniform_from_key(pp.key, k) < pp.thresh);
-    if (take) {
+    const uint64_t half = which == 0 ? (bits >> 32) : (bits & 0xffffffffULL);
+    if (pp.accept_all || half < pp.thresh_bits) {
       int slot = atomicAdd(&st->n_accepted, 1);
       if (slot < pp.acc_cap) {
-        acc[slot].key = k;
+        acc[slot].key = 2ULL * pairkey + which;
         acc[slot].x[0] = r;
         acc[slot].x[1] = 0.0;
         acc[slot].x[2] = 0.0;
@@ -212,6 +225,343 @@ __global__ void __launch_bounds__(128) pair_cells_kernel(GridDesc g, CellGrid cg
   // pair count: integer, so the atomic order is irrelevant
   for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
   if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&st->n_pairs, npairs);
+}
+
+// ---- v4: warp per home cell, fp32 prefilter, warp-level compaction ---------------------------
+//
+// Only 1 in 6.5 tested pairs lies inside the cutoff, so a thread-per-atom loop (v1 above) runs the
+// heavy per-pair path (square root, interpolation, hashing, force scatter) with ~15 % of its lanes
+// active.  Here a warp owns one home cell:
+//   * STAGE: the atoms of the own cell and of the 13 forward neighbour cells are copied, x-row by
+//     x-row (cells adjacent in x are contiguous in slot order), into shared memory as fp32
+//     coordinates relative to the corner of the 3x3x3 neighbourhood (built from the cell-relative
+//     fp32 copy the binning kernel leaves, so no image shift and no dependence on the box size);
+//   * TEST: for each home atom (warp-uniform) the lanes sweep the staged atoms 32 at a time and
+//     compare an fp32 distance against a 1e-4 enlarged cutoff (full-rate fp32); accepted (i, j)
+//     index pairs are compacted into a per-warp queue with a ballot;
+//   * HEAVY: whenever 32 pairs are queued each lane takes one: it reloads both atoms in fp64, forms
+//     the separation exactly in the oracle's operation order, applies the exact cutoff test,
+//     evaluates the bias at r, hashes the two hill proposals and scatters the forces.
+// The prefilter only decides what reaches the exact test, so results do not depend on it.
+// Home-atom forces: segmented shuffle scan over the batch (entries of one atom are contiguous),
+// the last lane of each run adds the run total to a shared-memory accumulator; neighbour-atom
+// forces leave as fp64 REDs.
+#ifndef EDM_PAIR_MINBLOCKS
+#define EDM_PAIR_MINBLOCKS 5
+#endif
+constexpr int kPairWarps = 4;
+constexpr int kJCap = 192;
+constexpr int kICap = 64;
+constexpr int kQCap = 64;
+
+struct PairWarpSmem {
+  double fi[kICap][3];
+  float jx[kJCap], jy[kJCap], jz[kJCap];
+  float ix[kICap], iy[kICap], iz[kICap];
+  int jslot[kJCap];
+  int queue[kQCap];            // (ii << 16) | jj
+  unsigned char jcode[kJCap];  // image shift code, 2 bits per dim
+};
+
+struct PairCtx {
+  GridDesc g;
+  CellGrid cg;
+  PairParams pp;
+  const int* start;
+  const int* order;
+  const double* xs;
+  const float* xs32;  // cell-relative fp32 copy of xs
+  const int* ts;
+  double* f;
+  double* partial;
+  BiasDev* st;
+  HillAccepted* acc;
+};
+
+__device__ __noinline__ double pair_eval_slow(const GridDesc& g, double r, double& force) {
+  return pair_eval(g, r, force);
+}
+
+// lean 1-D evaluation for the pair path: the arithmetic of d_eval_point<1> for an interpolated
+// non-periodic grid; everything else (remap, periodic wrap) goes through the generic routine
+__device__ __forceinline__ double pair_eval_fast(const GridDesc& g, double r, double& force) {
+  force = 0.0;
+  if (r < g.bmin[0] || r > g.bmax[0] || g.periodic[0] || !g.b_interp) return pair_eval_slow(g, r, force);
+  if (r < g.min[0] || r >= g.upper[0]) return 0.0;
+  const double t = __dsub_rn(r, g.min[0]);
+  int idx = (int)(t * g.inv_dx[0]);  // a one-off at a cell edge is harmless: the interpolant is C1 there
+  const int hi = g.n[0] - 2;
+  idx = idx < 0 ? 0 : (idx > hi ? hi : idx);
+  const double where = __dsub_rn(t, __dmul_rn((double)idx, g.dx[0]));
+  const double X = where * g.inv_dx[0];
+  const double2 r0 = *reinterpret_cast<const double2*>(g.rec + (long)idx * 2);
+  const double2 r1 = *reinterpret_cast<const double2*>(g.rec + (long)idx * 2 + 2);
+  const double Y = fabs(X - 1.0);
+  const double X2 = X * X, X3 = X2 * X, Y2 = Y * Y, Y3 = Y2 * Y;
+  const double td0 = !(fabs(r0.x) < kInterpZero) ? r0.y : 0.0;
+  const double td1 = !(fabs(r1.x) < kInterpZero) ? r1.y : 0.0;
+  double f = r0.x * (1.0 - 3.0 * X2 + 2.0 * X3) + td0 * (X - 2.0 * X2 + X3) * g.dx[0];
+  double der = r0.x * (-6.0 * X + 6.0 * X2) * g.inv_dx[0] + td0 * (1.0 - 4.0 * X + 3.0 * X2);
+  f += r1.x * (1.0 - 3.0 * Y2 + 2.0 * Y3) - td1 * (Y - 2.0 * Y2 + Y3) * g.dx[0];
+  der += -r1.x * (-6.0 * Y + 6.0 * Y2) * g.inv_dx[0] + td1 * (1.0 - 4.0 * Y + 3.0 * Y2);
+  force = -der;
+  return f;
+}
+
+// hill proposals of one pair; the exactly rounded sqrt is taken only for an accepted proposal
+__device__ __forceinline__ void propose_hills_d2(const PairParams& pp, unsigned long long pairkey, double d2,
+                                                 BiasDev* st, HillAccepted* acc) {
+  const uint64_t bits = pair_bits(pp.key, pairkey);
+  const bool t0 = pp.accept_all || (bits >> 32) < pp.thresh_bits;
+  const bool t1 = pp.accept_all || (bits & 0xffffffffULL) < pp.thresh_bits;
+  if (t0 || t1) {
+    const double r = sqrt(d2);
+#pragma unroll
+    for (int which = 0; which < 2; which++) {
+      if (which == 0 ? t0 : t1) {
+        int slot = atomicAdd(&st->n_accepted, 1);
+        if (slot < pp.acc_cap) {
+          acc[slot].key = 2ULL * pairkey + which;
+          acc[slot].x[0] = r;
+          acc[slot].x[1] = 0.0;
+          acc[slot].x[2] = 0.0;
+        } else {
+          st->accepted_overflow = 1;
+        }
+      }
+    }
+  }
+}
+
+__device__ __noinline__ void pair_heavy_batch(const PairCtx& c, PairWarpSmem& w, int first, int count, int ilo,
+                                              double& e, unsigned long long& npairs) {
+  const int lane = threadIdx.x & 31;
+  bool on = lane < count;
+  int ii = -1;
+  double px = 0.0, py = 0.0, pz = 0.0;
+  if (on) {
+    const int q = w.queue[first + lane];
+    ii = q >> 16;
+    const int jj = q & 0xffff;
+    const long si = ilo + ii, sj = w.jslot[jj];
+    const int code = w.jcode[jj];
+    const double sx = (code & 1) ? c.cg.box[0] : ((code & 2) ? -c.cg.box[0] : 0.0);
+    const double sy = (code & 4) ? c.cg.box[1] : ((code & 8) ? -c.cg.box[1] : 0.0);
+    const double sz = (code & 16) ? c.cg.box[2] : ((code & 32) ? -c.cg.box[2] : 0.0);
+    // exactly the oracle's separation: (x_i - x_j) - image shift, squares summed in x, y, z order
+    const double dx = __dsub_rn(__dsub_rn(c.xs[3 * si + 0], c.xs[3 * sj + 0]), sx);
+    const double dy = __dsub_rn(__dsub_rn(c.xs[3 * si + 1], c.xs[3 * sj + 1]), sy);
+    const double dz = __dsub_rn(__dsub_rn(c.xs[3 * si + 2], c.xs[3 * sj + 2]), sz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    on = d2 < c.pp.rc2;
+    if (on) {
+      const int oi = c.order[si], oj = c.order[sj];
+      const double rinv = rsqrt(d2);
+      const double r = d2 * rinv;  // within 2 ulp of sqrt(d2): enough for V(r); hills take the exact root
+      double force = 1.0;
+      if (!(c.pp.dbg & 2)) e += pair_eval_fast(c.g, r, force);
+      npairs++;
+      const double s = rinv * force;
+      px = dx * s;
+      py = dy * s;
+      pz = dz * s;
+      if (c.pp.do_hills && !(c.pp.dbg & 4)) {
+        const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
+        propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
+      }
+      if (!(c.pp.dbg & 1)) {
+      atomicAdd(&c.f[3 * (long)oj + 0], -px);
+      atomicAdd(&c.f[3 * (long)oj + 1], -py);
+      atomicAdd(&c.f[3 * (long)oj + 2], -pz);
+      }
+    }
+  }
+  if (c.pp.dbg & 16) {
+    if (on) {
+      const long o = 3 * (long)c.order[ilo + ii];
+      atomicAdd(&c.f[o + 0], px);
+      atomicAdd(&c.f[o + 1], py);
+      atomicAdd(&c.f[o + 2], pz);
+    }
+    return;
+  }
+  // home-atom side: inclusive segmented scan over runs of equal ii (contiguous in the queue)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int iu = __shfl_up_sync(0xffffffffu, ii, o);
+    const double ux = __shfl_up_sync(0xffffffffu, px, o);
+    const double uy = __shfl_up_sync(0xffffffffu, py, o);
+    const double uz = __shfl_up_sync(0xffffffffu, pz, o);
+    if (lane >= o && iu == ii) {
+      px += ux;
+      py += uy;
+      pz += uz;
+    }
+  }
+  const int inext = __shfl_down_sync(0xffffffffu, ii, 1);
+  if (ii >= 0 && (lane == 31 || inext != ii)) {
+    w.fi[ii][0] += px;
+    w.fi[ii][1] += py;
+    w.fi[ii][2] += pz;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kPairWarps * 32, EDM_PAIR_MINBLOCKS) pair_cells_v4_kernel(const __grid_constant__ PairCtx c) {
+  __shared__ PairWarpSmem wsm[kPairWarps];
+  __shared__ double red[33];
+  PairWarpSmem& w = wsm[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * kPairWarps;
+  const CellGrid& cg = c.cg;
+  const PairParams& pp = c.pp;
+  double e = 0.0;
+  unsigned long long npairs = 0;
+  const float rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;  // prefilter radius; the fp32 error is ~1e-6 relative
+  const float csx = (float)cg.cs[0], csy = (float)cg.cs[1], csz = (float)cg.cs[2];
+
+  for (int cell = gw; cell < cg.ncell; cell += nwarps) {
+    const int clo = c.start[cell], chi = c.start[cell + 1];
+    if (clo == chi) continue;
+    const int cx = cell % cg.nc[0], cy = (cell / cg.nc[0]) % cg.nc[1], cz = cell / (cg.nc[0] * cg.nc[1]);
+    for (int ilo = clo; ilo < chi; ilo += kICap) {
+      const int ni = min(kICap, chi - ilo);
+      for (int a = lane; a < ni; a += 32) {
+        w.ix[a] = c.xs32[3 * (long)(ilo + a) + 0] + csx;
+        w.iy[a] = c.xs32[3 * (long)(ilo + a) + 1] + csy;
+        w.iz[a] = c.xs32[3 * (long)(ilo + a) + 2] + csz;
+        w.fi[a][0] = 0.0;
+        w.fi[a][1] = 0.0;
+        w.fi[a][2] = 0.0;
+      }
+      int nj = 0, nq = 0;
+      // own-cell atoms are always staged at the head of the list: entries [0, self_hi) hold slots
+      // self_slot0, self_slot0 + 1, ...; of those only partners with a larger slot than i count
+      int self_hi = 0, self_slot0 = 0;
+      __syncwarp();
+
+      // TEST (+ HEAVY on full batches) over the staged list; drains the queue at the end because
+      // queue entries index the staged list
+      auto run_tests = [&]() {
+        __syncwarp();
+        for (int ii = 0; ii < ni; ii++) {
+          const int si = ilo + ii;
+          int ti = 0;
+          if (pp.use_types) {
+            ti = c.ts[si];
+            if (ti != pp.itype && ti != pp.jtype) continue;
+          }
+          const float xi = w.ix[ii], yi = w.iy[ii], zi = w.iz[ii];
+          const int selfcut = si - self_slot0;
+          // four staged atoms per lane and trip: independent fp32 chains hide the LDS latency and
+          // the loop/queue bookkeeping is paid once per 128 tests
+          for (int jb = 0; jb < nj; jb += 128) {
+            bool take[4];
+            int jjs[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int jj = jb + 32 * u + lane;
+              jjs[u] = jj;
+              take[u] = false;
+              if (jj < nj) {
+                const float dx = xi - w.jx[jj], dy = yi - w.jy[jj], dz = zi - w.jz[jj];
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                take[u] = (d2 < rc2m) && (jj >= self_hi || jj > selfcut);
+                if (take[u] && pp.use_types) {
+                  const int tj = c.ts[w.jslot[jj]];
+                  take[u] = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const unsigned m = __ballot_sync(0xffffffffu, take[u]);
+              if (m == 0u) continue;
+              if (take[u]) w.queue[nq + __popc(m & ((1u << lane) - 1u))] = (ii << 16) | jjs[u];
+              nq += __popc(m);
+              if (nq >= 32) {
+                __syncwarp();
+                nq -= 32;
+                if (!(pp.dbg & 8)) pair_heavy_batch(c, w, nq, 32, ilo, e, npairs);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (nq && !(pp.dbg & 8)) pair_heavy_batch(c, w, 0, nq, ilo, e, npairs);
+        nq = 0;
+      };
+
+      // half shell as 5 x-rows: (oy,oz) = (0,0) with ox = 0..1 (own cell first), then
+      // (1,0), (-1,1), (0,1), (1,1) with ox = -1..1
+      for (int row = 0; row < 5; row++) {
+        const int oy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3);
+        const int oz = (row < 2) ? 0 : 1;
+        const int ox0 = (row == 0) ? 0 : -1;
+        int qy = cy + oy, qz = cz + oz, ycode = 0;
+        if (qy >= cg.nc[1]) { qy -= cg.nc[1]; ycode |= 4; } else if (qy < 0) { qy += cg.nc[1]; ycode |= 8; }
+        if (qz >= cg.nc[2]) { qz -= cg.nc[2]; ycode |= 16; } else if (qz < 0) { qz += cg.nc[2]; ycode |= 32; }
+        const float offy = (float)(oy + 1) * csy, offz = (float)(oz + 1) * csz;
+        const int rowbase = (qz * cg.nc[1] + qy) * cg.nc[0];
+        for (int ox = ox0; ox <= 1; ox++) {
+          int qx = cx + ox, code = ycode;
+          if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
+          // merge the following cells of the row while they stay contiguous (no wrap in between)
+          int ncell = 1;
+          while (ox + ncell <= 1 && qx + ncell < cg.nc[0] && !(code & 2)) ncell++;
+          if ((code & 2)) ncell = 1;  // the wrapped-low cell stands alone; the rest restarts at qx = 0
+          const int q0 = rowbase + qx;
+          const int b0 = c.start[q0];
+          const int b1 = c.start[q0 + 1];
+          const int b2 = (ncell > 1) ? c.start[q0 + 2] : b1;
+          const int b3 = (ncell > 2) ? c.start[q0 + 3] : b2;
+          const float offx0 = (float)(ox + 1) * csx;
+          const bool own = (row == 0 && ox == 0);
+          int lo = b0;
+          const int hi = b3;
+          while (lo < hi) {
+            if (nj == kJCap) {
+              run_tests();
+              nj = 0;
+              self_hi = 0;
+              __syncwarp();
+            }
+            const int takeN = min(kJCap - nj, hi - lo);
+            if (own && lo < b1) {  // nj == 0 here: the own cell opens the list, also after a refill
+              self_slot0 = lo;
+              self_hi = min(takeN, b1 - lo);
+            }
+            for (int a = lane; a < takeN; a += 32) {
+              const int sl = lo + a;
+              const float offx = offx0 + (float)((sl >= b1) + (sl >= b2)) * csx;
+              w.jx[nj + a] = c.xs32[3 * (long)sl + 0] + offx;
+              w.jy[nj + a] = c.xs32[3 * (long)sl + 1] + offy;
+              w.jz[nj + a] = c.xs32[3 * (long)sl + 2] + offz;
+              w.jslot[nj + a] = sl;
+              w.jcode[nj + a] = (unsigned char)code;
+            }
+            nj += takeN;
+            lo += takeN;
+          }
+          ox += ncell - 1;
+        }
+      }
+      if (nj) run_tests();
+      __syncwarp();
+      for (int a = lane; a < ni; a += 32) {
+        const long o = 3 * (long)c.order[ilo + a];
+        atomicAdd(&c.f[o + 0], w.fi[a][0]);
+        atomicAdd(&c.f[o + 1], w.fi[a][1]);
+        atomicAdd(&c.f[o + 2], w.fi[a][2]);
+      }
+      __syncwarp();
+    }
+  }
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) c.partial[blockIdx.x] = tot;
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+  if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
 }
 
 // Neighbour-list form: one thread per listed i-row (lammps/fix_edm_pair.cpp:177-240).
@@ -324,7 +674,12 @@ static PairParams pair_params(const edm_bias* b, const int* type, int itype, int
   pp.do_hills = do_hills;
   pp.accept_all = b->prm.hill_density < 0;
   pp.thresh = pp.accept_all ? 2.0 : b->prm.hill_density / (double)(int)est;
+  {
+    double tb = ceil(pp.thresh * 4294967296.0);
+    pp.thresh_bits = tb >= 4294967296.0 ? 4294967296ULL : (tb <= 0.0 ? 0ULL : (uint64_t)tb);
+  }
   pp.key = uniform_key(seed, step);
+  pp.dbg = getenv("EDM_DBG") ? atoi(getenv("EDM_DBG")) : 0;
   pp.rc2 = cutoff * cutoff;
   pp.natoms = natoms;
   pp.acc_cap = b->accepted_cap;
@@ -353,7 +708,8 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   size_t off_cell = 0, off_order = off_cell + n * 4, off_ts = off_order + n * 4, off_count = off_ts + n * 4;
   size_t off_start = off_count + nc1 * 4;
   size_t off_xs = (off_start + nc1 * 4 + 255) / 256 * 256;
-  size_t total = off_xs + 3 * n * sizeof(double);
+  size_t off_xs32 = off_xs + 3 * n * sizeof(double);
+  size_t total = off_xs32 + 3 * n * sizeof(float);
   EDM_TRY(b->cells.reserve(total));
   char* base = b->cells.as<char>();
   int* cell_of = reinterpret_cast<int*>(base + off_cell);
@@ -362,6 +718,7 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   int* count = reinterpret_cast<int*>(base + off_count);
   int* start = reinterpret_cast<int*>(base + off_start);
   double* xs = reinterpret_cast<double*>(base + off_xs);
+  float* xs32 = reinterpret_cast<float*>(base + off_xs32);
 
   EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
   unsigned nb = (unsigned)((natoms + 255) / 256);
@@ -369,16 +726,43 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   cell_scan_kernel<<<1, 1024, 0, st>>>(cg.ncell, count, start);
   EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
   cell_fill_kernel<<<nb, 256, 0, st>>>(natoms, cell_of, start, count, order);
-  cell_sort_gather_kernel<<<(cg.ncell + 127) / 128, 128, 0, st>>>(cg.ncell, start, order, x, type, xs, type ? ts : nullptr);
+  cell_sort_gather_kernel<<<(cg.ncell + 127) / 128, 128, 0, st>>>(cg, start, order, x, type, xs, xs32, type ? ts : nullptr);
   EDM_CUDA(cudaGetLastError());
 
   PairParams pp = pair_params(b, type, itype, jtype, do_hills, est, seed, step, cutoff, natoms);
   reset_pairs_kernel<<<1, 1, 0, st>>>(b->d_state, nullptr);
-  long long blocks = (natoms + 127) / 128;
-  if (blocks > b->n_partial) blocks = b->n_partial;
+  // EDM_PAIR_MODE=0 selects the v1 thread-per-atom kernel (kept for A/B measurements)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* ev = getenv("EDM_PAIR_MODE");
+    mode = ev ? atoi(ev) : 1;
+  }
+  long long blocks;
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[0], st));
-  pair_cells_kernel<<<(int)blocks, 128, 0, st>>>(b->bias->d, cg, pp, start, order, xs, ts, f, b->d_energy_partial,
-                                                 b->d_state, b->d_accepted);
+  if (mode == 0) {
+    blocks = (natoms + 127) / 128;
+    if (blocks > b->n_partial) blocks = b->n_partial;
+    pair_cells_kernel<<<(int)blocks, 128, 0, st>>>(b->bias->d, cg, pp, start, order, xs, ts, f, b->d_energy_partial,
+                                                   b->d_state, b->d_accepted);
+  } else {
+    blocks = 148 * 8;  // one wave of 8 resident CTAs (32 warps) per SM; warps stride over the cells
+    if (blocks > (cg.ncell + kPairWarps - 1) / kPairWarps) blocks = (cg.ncell + kPairWarps - 1) / kPairWarps;
+    if (blocks > b->n_partial) blocks = b->n_partial;
+    PairCtx ctx;
+    ctx.g = b->bias->d;
+    ctx.cg = cg;
+    ctx.pp = pp;
+    ctx.start = start;
+    ctx.order = order;
+    ctx.xs = xs;
+    ctx.xs32 = xs32;
+    ctx.ts = ts;
+    ctx.f = f;
+    ctx.partial = b->d_energy_partial;
+    ctx.st = b->d_state;
+    ctx.acc = b->d_accepted;
+    pair_cells_v4_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx);
+  }
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[1], st));
   count_launches(7);
   sum_partials2_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy_dev);

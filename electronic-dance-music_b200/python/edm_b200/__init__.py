@@ -53,6 +53,7 @@ EXPORTS = {
     "edm_last_error": (C.c_char_p, []),
     "edm_device_count": (C.c_int, [c_ip]),
     "edm_uniform": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint64]),
+    "edm_uniform_pair": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
     "edm_grid_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int]),
     "edm_grid_create_from_header": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, c_ip, c_dp, c_dp, c_ip, C.c_int, C.c_int]),
     "edm_gauss_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, c_dp, c_dp, c_dp, c_ip, C.c_int, c_dp]),
@@ -145,6 +146,10 @@ def launch_count():
 
 def uniform(seed, step, counter):
     return lib().edm_uniform(seed, step, counter)
+
+
+def uniform_pair(seed, step, pairkey, which):
+    return lib().edm_uniform_pair(seed, step, pairkey, which)
 
 
 def _d(a):

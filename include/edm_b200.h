@@ -48,6 +48,8 @@ int edm_device_count(int* count);
 /* Device-side counter-based uniform in [0,1) used when the caller passes no runiform array
  * (stand-in for LAMMPS RanMars, lammps/fix_edm.cpp:149-151); exposed so hosts can reproduce it. */
 double edm_uniform(uint64_t seed, uint64_t step, uint64_t counter);
+/* The two proposals of pair `pairkey` (which = 0, 1) share one hash: 32-bit resolution each. */
+double edm_uniform_pair(uint64_t seed, uint64_t step, uint64_t pairkey, int which);
 
 /* ------------------------------------------------------------------ Grid / GaussGrid */
 
@@ -181,7 +183,7 @@ typedef struct edm_pair_result {
  * [0,box)^3 with the neighbour search done on the device: every pair i<j with minimum-image
  * distance < cutoff whose types match (itype,jtype) is evaluated once (half list, both atoms
  * local), forces are accumulated into f, and if do_hills each pair proposes two hills
- * (fix_edm_pair.cpp:230-236) with uniforms edm_uniform(seed, step, 2*(i*natoms+j)+{0,1}),
+ * (fix_edm_pair.cpp:230-236) with uniforms edm_uniform_pair(seed, step, i*natoms+j, {0,1}),
  * accepted hills ordered by (i, j).  Lib-level order: all evaluations see the start-of-step bias
  * (SURVEY 3.2).  type may be NULL (all atoms match). */
 int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, const int* type, int itype,

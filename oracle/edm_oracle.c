@@ -1067,6 +1067,21 @@ void orc_uniform_fill(unsigned long long seed, unsigned long long step, unsigned
   for (long i = 0; i < n; i++) out[i] = orc_uniform(seed, step, first + (unsigned long long)i);
 }
 
+/* pair proposals: one hash per pair, 32-bit resolution per proposal (edm_uniform_pair) */
+double orc_uniform_pair(unsigned long long seed, unsigned long long step, unsigned long long pairkey, int which) {
+  uint64_t key = orc_mix64(seed ^ orc_mix64(step + 0x9E3779B97F4A7C15ULL));
+  uint64_t bits = orc_mix64(key + pairkey * 0x9E3779B97F4A7C15ULL);
+  uint64_t half = which == 0 ? (bits >> 32) : (bits & 0xffffffffULL);
+  return (double)half * (1.0 / 4294967296.0);
+}
+void orc_uniform_pair_fill(unsigned long long seed, unsigned long long step, long n,
+                           const unsigned long long* pairkeys, double* out) {
+  for (long i = 0; i < n; i++) {
+    out[2 * i] = orc_uniform_pair(seed, step, pairkeys[i], 0);
+    out[2 * i + 1] = orc_uniform_pair(seed, step, pairkeys[i], 1);
+  }
+}
+
 /* ------------------------------------------------------------------ CPU-baseline timers */
 
 static double now_s(void) {

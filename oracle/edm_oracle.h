@@ -134,6 +134,9 @@ long orc_build_half_list(long natoms, const double* x, const double* box, double
  * this oracle (the RNG is outside the parity boundary: add_hill takes runiform as an argument,
  * lib/edm_bias.cpp:528).  Same function as edm_uniform() in electronic-dance-music_b200/csrc. */
 double orc_uniform(unsigned long long seed, unsigned long long step, unsigned long long counter);
+double orc_uniform_pair(unsigned long long seed, unsigned long long step, unsigned long long pairkey, int which);
+void orc_uniform_pair_fill(unsigned long long seed, unsigned long long step, long n,
+                           const unsigned long long* pairkeys, double* out);
 void orc_uniform_fill(unsigned long long seed, unsigned long long step, unsigned long long first, long n,
                       double* out);
 

@@ -121,6 +121,8 @@ class _Lib:
                 "build_half_list": (l, [l, c_dp, c_dp, d, l, c_ip, c_ip, c_dp]),
                 "uniform": (d, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]),
                 "uniform_fill": (None, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, l, c_dp]),
+                "uniform_pair": (d, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, i]),
+                "uniform_pair_fill": (None, [C.c_ulonglong, C.c_ulonglong, l, C.POINTER(C.c_ulonglong), c_dp]),
             })
         else:
             sig.update({
@@ -463,4 +465,13 @@ def uniform_fill(seed, step, first, n):
     L = load("port")
     out = np.zeros(n)
     L.uniform_fill(seed, step, first, n, _dp(out))
+    return out
+
+
+def pair_uniforms(seed, step, pi, pj, natoms):
+    """The two uniforms of every pair (i < j) as the device draws them: key i*natoms+j (edm_uniform_pair)."""
+    L = load("port")
+    keys = np.ascontiguousarray(pi.astype(np.uint64) * np.uint64(natoms) + pj.astype(np.uint64))
+    out = np.zeros(2 * keys.size)
+    L.uniform_pair_fill(seed, step, keys.size, keys.ctypes.data_as(C.POINTER(C.c_ulonglong)), _dp(out))
     return out

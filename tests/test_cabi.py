@@ -59,6 +59,9 @@ def test_uniform_matches_oracle_rng(edm, port):
     L = port.load("port")
     for seed, step, ctr in [(0, 0, 0), (1, 2, 3), (20261018, 77, 2 ** 40 + 5), (2 ** 63, 2 ** 31, 2 ** 62)]:
         assert edm.uniform(seed, step, ctr) == L.uniform(seed, step, ctr)
+    for key in (0, 5, 10 ** 12 + 7):
+        for which in (0, 1):
+            assert edm.uniform_pair(3, 9, key, which) == L.uniform_pair(3, 9, key, which)
     u = port.uniform_fill(9, 4, 100, 1000)
     assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.05
 

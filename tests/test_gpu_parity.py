@@ -349,12 +349,9 @@ def test_pair_cells_parity(edm, port, tmp_path):
     for step in range(4):
         x = make_atoms(rng, n, L)
         pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
-        # the same counter-based uniforms the device draws: key 2*(i*n+j)+{0,1}
-        keys = (pi.astype(np.uint64) * np.uint64(n) + pj.astype(np.uint64)) * np.uint64(2)
-        u = np.empty(2 * pi.size)
+        # the same counter-based uniforms the device draws (edm_uniform_pair, key i*n+j)
         seed = 99
-        u[0::2] = [edm.uniform(seed, step, int(k)) for k in keys]
-        u[1::2] = [edm.uniform(seed, step, int(k) + 1) for k in keys]
+        u = port.pair_uniforms(seed, step, pi, pj, n)
         fo = np.zeros((n, 3))
         fd = np.zeros((n, 3))
         eo, r_o = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=est, uniforms=u)
