@@ -77,16 +77,24 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.skip = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:   # nvidia-smi needs a moment to start
+                time.sleep(0.02)
         except Exception:
             self.proc = None
+
+    def mark(self):
+        """Samples taken before this call are not part of the measured region."""
+        self.skip = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -102,7 +110,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for line in self.lines[self.skip:]:
             p = [t.strip() for t in line.split(",")]
             if len(p) < 7:
                 continue
@@ -276,6 +284,8 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     step_no = 0
     for _ in range(max(args.warmup, 3)):
         step_resident(step_no)
@@ -283,8 +293,7 @@ def run_gpu(args, rank, local_rank, world):
     barrier()
     st0 = bias.state()
     launches0 = edm.launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     pair_ms = []
     barrier()
@@ -298,7 +307,6 @@ def run_gpu(args, rank, local_rank, world):
         edm.check(L.edm_bias_profile_ms(bias.h, C.byref(ms)))   # waits for this step's pair kernel
         pair_ms.append(ms.value)
     barrier()
-    clk = clocks.stop()
     launches = edm.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
@@ -352,6 +360,7 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
     dep_ms = d0.elapsed_time(d1) / dep_reps
     hills_per_s = DEPOSIT_BATCH / (dep_ms * 1e-3)
+    clk = clocks.stop()   # covers the timed steps, the e2e steps and the deposit batches
 
     # ---- reduce over ranks: max time, summed work
     stats = torch.tensor([total_ms, e2e_s, float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)],
@@ -385,7 +394,7 @@ def run_gpu(args, rank, local_rank, world):
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
                       "in_situ_hill_events": int(hills_timed)},
-            "roofline": {"bound": "hbm", "kernel": "pair_cells_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "pair_cells_v4_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "note": "fp64-pipe bound, not HBM bound (SURVEY 8d): 2.9 B/pair of compulsory traffic"},

@@ -2,6 +2,7 @@
 // height scaling, bias_per_step limiter, overflow backlog and hill log (add_hills).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -219,6 +220,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ double s_h;
   __shared__ int s_go;
   __shared__ double s_prefactor;
+  if (st->round_mode == 2) return;  // the parallel round below already committed this round
   const int W1 = DIM + 1;
   const bool t0 = threadIdx.x == 0;
   const double bps = prm.bias_per_step;
@@ -367,6 +369,118 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   }
 }
 
+// ------------------------------------------------------------------ K4: the parallel hill round (1-D)
+//
+// Without local well-tempering a hill's height does not depend on the bias the earlier hills of the
+// round left behind, so the round splits into: plan (order the candidates, scale the heights) ->
+// owner-computes deposit staged into scratch with every hill's integral -> decide (the limiter's
+// running sum, in candidate order) -> commit.  If the backlog is not empty or the running sum
+// reaches bias_per_step the round is left untouched and the sequential kernel above runs instead,
+// so the limiter/undo/backlog semantics never have to be re-expressed here.
+
+__global__ void __launch_bounds__(512) round_plan_kernel(GridDesc target, RoundParams prm, int n_max, BiasDev* st,
+                                                         HillAccepted* acc, HillAccepted* acc_tmp,
+                                                         double* __restrict__ centres, double* __restrict__ heights) {
+  __shared__ double s_prefactor;
+  __shared__ int s_mode;
+  if (threadIdx.x == 0) {
+    s_mode = (st->left == 0 && st->right == 0 && !st->accepted_overflow && st->n_accepted <= n_max) ? 1 : 0;
+    st->round_mode = s_mode;
+    double pf = prm.hill_prefactor;
+    if (prm.global_tempering > 0) {
+      double avg = st->cum_bias / prm.total_volume;
+      if (avg >= prm.global_tempering)
+        pf *= exp(-(avg - prm.global_tempering) / (prm.global_tempering * (prm.bias_factor - 1) * prm.boltzmann_factor));
+    }
+    s_prefactor = pf;
+  }
+  __syncthreads();
+  if (s_mode == 0) {
+    if (threadIdx.x == 0) st->n_fast = 0;
+    return;
+  }
+  int nacc = st->n_accepted;
+  if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
+  cta_sort_accepted(acc, acc_tmp, nacc);
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    double pos[1] = {acc[k].x[0]};
+    double h = s_prefactor;
+    if (prm.b_targeting) h *= exp(d_get_value<1>(target, pos) - prm.expected_target);
+    if (prm.hill_density < 0)
+      h /= (double)(int)prm.est_hill_count;
+    else
+      h /= prm.hill_density;
+    h = fmin(h, 1.0 * prm.bias_per_step);
+    centres[k] = pos[0];
+    heights[k] = h;
+  }
+  if (threadIdx.x == 0) st->n_fast = nacc;
+}
+
+__global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundParams prm, BiasDev* st,
+                                                           const double* __restrict__ centres,
+                                                           const double* __restrict__ heights,
+                                                           const double* __restrict__ ba, edm_hill_event_t* log) {
+  __shared__ int s_ok, s_mode;
+  if (threadIdx.x == 0) s_mode = st->round_mode;
+  __syncthreads();
+  if (s_mode != 1) return;
+  const int n = st->n_fast;
+  if (threadIdx.x == 0) {
+    // the limiter's running sum, lib/edm_bias.cpp:465-474, in candidate order
+    double cum = 0.0;
+    int ok = 1;
+    for (int k = 0; k < n; k++) {
+      if (!(cum < prm.bias_per_step)) ok = 0;
+      cum += ba[k];
+      if (!(cum < prm.bias_per_step)) ok = 0;
+    }
+    if (st->log_n + n > prm.log_cap) ok = 0;
+    s_ok = ok;
+    if (ok) {
+      st->temp_hill_cum = cum;
+      st->hills_added = n;
+      st->skip = 0;
+    } else {
+      st->round_mode = 0;
+    }
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const double cov = st->cum_bias / prm.total_volume;
+  const int base = st->log_n;
+  const long long steps = st->steps;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    edm_hill_event_t& e = log[base + k];
+    e.steps = steps;
+    e.type = 'h';
+    e.hills_added = k + 1;
+    e.pos[0] = centres[k];
+    e.pos[1] = 0.0;
+    e.pos[2] = 0.0;
+    e.height = heights[k];
+    e.bias_added = ba[k];
+    e.cum_over_vol = cov;
+    if (hist.rec) {  // cv_hist_ bump: +1.0 adds are exact, so the atomic order does not matter
+      double xd = centres[k];
+      bool inside = !(!hist.periodic[0] && (xd < hist.min[0] || xd >= hist.upper[0]));
+      if (hist.periodic[0]) xd = d_wrap(xd, hist.min[0], hist.len[0]);
+      long long idx = (long long)floor(__ddiv_rn(__dsub_rn(xd, hist.min[0]), hist.dx[0]));
+      idx = idx < 0 ? 0 : (idx > hist.n[0] - 1 ? hist.n[0] - 1 : idx);
+      if (inside) atomicAdd(&hist.rec[idx * hist.rec_w], 1.0);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->log_n = base + n;
+    st->cum_bias += st->temp_hill_cum;
+    st->steps++;
+    st->round_mode = 2;
+  }
+}
+
+__global__ void reset_mode_kernel(BiasDev* st) { st->round_mode = 0; }
+
 __global__ void reset_accepted_kernel(BiasDev* st) {
   st->n_accepted = 0;
   st->accepted_overflow = 0;
@@ -458,6 +572,26 @@ int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
   const GridDesc& hist = b->hist ? b->hist->d : none;
   const GridDesc& target = b->target ? b->target->d : none;
   HillAccepted* tmp = b->d_accepted + b->accepted_cap;
+  const bool local_tempering = b->prm.b_tempering && b->prm.global_tempering < 0;
+  static int allow_fast = -1;
+  if (allow_fast < 0) allow_fast = getenv("EDM_NO_FAST_ROUND") ? 0 : 1;
+  if (allow_fast && b->prm.dim == 1 && !local_tempering && deposit1d_eligible(b->bias)) {
+    const long cap = b->accepted_cap;
+    EDM_TRY(b->fast.reserve(3 * (size_t)cap * sizeof(double)));
+    double* centres = b->fast.as<double>();
+    double* heights = centres + cap;
+    double* ba = heights + cap;
+    // the deposit grid is sized for the usual few hundred hills; larger rounds take the sequential path
+    const long n_max = cap < 2048 ? cap : 2048;
+    round_plan_kernel<<<1, 512, 0, st>>>(target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres, heights);
+    EDM_TRY(deposit1d_stage(b->bias, centres, heights, ba, &b->d_state->n_fast, n_max, st));
+    round_decide_kernel<<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
+    EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
+    count_launches(2);
+  } else {
+    reset_mode_kernel<<<1, 1, 0, st>>>(b->d_state);
+    count_launches(1);
+  }
   count_launches(1);
   switch (b->prm.dim) {
     case 1: hill_round_kernel<1><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
@@ -542,6 +676,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->io3.release();
   b->io4.release();
   b->cells.release();
+  b->fast.release();
   delete b;
   return EDM_OK;
 }

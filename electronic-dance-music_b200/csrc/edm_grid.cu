@@ -339,7 +339,8 @@ template <int DIM> __global__ void remap_kernel(GridDesc g, double* x) {
 // ------------------------------------------------------------------ kernels: deposit
 
 // duplicate_boundary, lib/gaussian_grid.h:571-630 (T13: values only)
-__global__ void dup_boundary_kernel(GridDesc g, int* flags) {
+__global__ void dup_boundary_kernel(GridDesc g, int* flags, const int* __restrict__ gate, int want) {
+  if (gate && *gate != want) return;
   if (flags[0] == 0) return;
   for (int k = threadIdx.x; k < g.n_dup; k += blockDim.x)
     g.rec[g.dup_pairs[2 * k] * g.rec_w] = g.rec[g.dup_pairs[2 * k + 1] * g.rec_w];
@@ -405,9 +406,11 @@ struct Hill1D {
   int ok;
 };
 
-__global__ void deposit1d_prepare_kernel(GridDesc g, long n, const double* __restrict__ centres,
-                                         const double* __restrict__ heights, Hill1D* __restrict__ out) {
+__global__ void deposit1d_prepare_kernel(GridDesc g, long n, const int* __restrict__ n_dev,
+                                         const double* __restrict__ centres, const double* __restrict__ heights,
+                                         Hill1D* __restrict__ out) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   if (i >= n) return;
   HillGeom<1> hg;
   double x0[1] = {centres[i]};
@@ -424,9 +427,11 @@ __global__ void deposit1d_prepare_kernel(GridDesc g, long n, const double* __res
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-__global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n, const Hill1D* __restrict__ hills,
-                                                              long chunk, int nslot, double* __restrict__ partial,
+__global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n, const int* __restrict__ n_dev,
+                                                              const Hill1D* __restrict__ hills, long chunk, int nslot,
+                                                              double* __restrict__ partial,
                                                               double* __restrict__ ba_slots, int* flags) {
+  if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
   const int nwarps = (g.n[0] + 31) >> 5;
@@ -559,7 +564,9 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
   if (dirty) flags[0] = 1;
 }
 
-__global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* __restrict__ partial) {
+__global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* __restrict__ partial,
+                                        const int* __restrict__ flag, int want) {
+  if (flag && *flag != want) return;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.n[0]) return;
   double v = 0.0, dv = 0.0;
@@ -576,8 +583,10 @@ __global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* _
   *reinterpret_cast<double2*>(g.rec + (long long)p * 2) = make_double2(v, dv);
 }
 
-__global__ void deposit1d_ba_kernel(long n, int nslot, const double* __restrict__ ba_slots, double* __restrict__ ba) {
+__global__ void deposit1d_ba_kernel(long n, const int* __restrict__ n_dev, int nslot,
+                                    const double* __restrict__ ba_slots, double* __restrict__ ba) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   if (i >= n) return;
   double t = 0.0;
   for (int s = 0; s < nslot; s++) t += ba_slots[i * (long)nslot + s];
@@ -587,6 +596,57 @@ __global__ void deposit1d_ba_kernel(long n, int nslot, const double* __restrict_
 }  // namespace edm
 
 using namespace edm;
+
+namespace edm {
+
+static int deposit1d_nslot(const GridDesc& d) {
+  const int nwarps = (d.n[0] + 31) / 32;
+  int nslot = (2 * d.minisize[0] + 1 + 31) / 32 + 2;
+  return nslot > nwarps ? nwarps : nslot;
+}
+
+bool deposit1d_eligible(const edm_grid* g) { return g->d.dim == 1 && g->d.is_gauss && g->d.minisize[0] < g->d.n[0]; }
+
+// one chunk: every grid point applies the hills in list order starting from its stored value, which
+// is exactly the reference's per-point rounding sequence
+int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, double* ba, const int* n_dev,
+                    long n_max, cudaStream_t st) {
+  const GridDesc& d = g->d;
+  const int npts = d.n[0], nwarps = (npts + 31) / 32, nslot = deposit1d_nslot(d);
+  size_t b_h = ((size_t)n_max * sizeof(Hill1D) + 255) / 256 * 256;
+  size_t b_p = ((size_t)npts * 2 * sizeof(double) + 255) / 256 * 256;
+  size_t b_s = (size_t)n_max * nslot * sizeof(double);
+  EDM_TRY(g->work.reserve(b_h + b_p + b_s));
+  char* basep = g->work.as<char>();
+  Hill1D* hl = reinterpret_cast<Hill1D*>(basep);
+  double* partial = reinterpret_cast<double*>(basep + b_h);
+  double* slots = reinterpret_cast<double*>(basep + b_h + b_p);
+  EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
+  deposit1d_prepare_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(d, n_max, n_dev, centres, heights, hl);
+  long chunk = (n_max + 31) / 32 * 32;
+  dim3 grid((nwarps + 3) / 4, 1);
+  deposit1d_owner_kernel<<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
+  deposit1d_ba_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(n_max, n_dev, nslot, slots, ba);
+  g->stage_partial = partial;
+  count_launches(3);
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st) {
+  const GridDesc& d = g->d;
+  const int npts = d.n[0];
+  deposit1d_commit_kernel<<<(npts + 255) / 256, 256, 0, st>>>(d, 1, g->stage_partial, flag, want);
+  count_launches(1);
+  if (d.n_dup) {
+    dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags, flag, want);
+    count_launches(1);
+  }
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
+}  // namespace edm
 
 // ------------------------------------------------------------------ C ABI: grids
 
@@ -965,15 +1025,15 @@ static int deposit_1d_owner(edm_grid* g, long n, const double* centres, const do
     double* partial = reinterpret_cast<double*>(basep + b_h);
     double* slots = reinterpret_cast<double*>(basep + b_h + b_p);
     EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
-    deposit1d_prepare_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, cnt, centres + off, heights + off, hl);
+    deposit1d_prepare_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, cnt, nullptr, centres + off, heights + off, hl);
     dim3 grid((nwarps + 3) / 4, nchunks);
-    deposit1d_owner_kernel<<<grid, 128, 0, st>>>(d, cnt, hl, chunk, nslot, partial, slots, g->d_flags);
-    deposit1d_commit_kernel<<<(npts + 255) / 256, 256, 0, st>>>(d, nchunks, partial);
-    if (ba) deposit1d_ba_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cnt, nslot, slots, ba + off);
+    deposit1d_owner_kernel<<<grid, 128, 0, st>>>(d, cnt, nullptr, hl, chunk, nslot, partial, slots, g->d_flags);
+    deposit1d_commit_kernel<<<(npts + 255) / 256, 256, 0, st>>>(d, nchunks, partial, nullptr, 0);
+    if (ba) deposit1d_ba_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cnt, nullptr, nslot, slots, ba + off);
     count_launches(ba ? 4 : 3);
     EDM_CUDA(cudaGetLastError());
   }
-  if (d.n_dup) dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags);
+  if (d.n_dup) dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags, nullptr, 0);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
@@ -994,7 +1054,7 @@ int edm_gauss_deposit_dev(edm_grid_t* g, long n, const double* centres, const do
     default: deposit_hills_kernel<3><<<blocks, 256, 0, st>>>(d, n, centres, heights, bias_added, g->d_flags); break;
   }
   EDM_CUDA(cudaGetLastError());
-  if (d.n_dup) dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags);
+  if (d.n_dup) dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags, nullptr, 0);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }

@@ -34,6 +34,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 int ensure_device(int device);
+// 1-D owner-computes deposit split in two so a caller can decide between them (edm_grid.cu):
+// stage = prepare + accumulate into scratch (+ per-hill integrals), commit = write the grid back
+// only if *flag == want.  n is read from *n_dev (clamped to n_max) when n_dev is not NULL.
+bool deposit1d_eligible(const edm_grid* g);
+int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, double* ba, const int* n_dev,
+                    long n_max, cudaStream_t st);
+int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st);
 void count_launches(int n);
 
 // Device scratch that grows on demand and is reused across calls (no allocation on the steady
@@ -58,6 +65,7 @@ struct edm_grid {
   edm::Scratch io;          // staging for upload/download/eval of host buffers
   edm::Scratch work;        // deposit scratch (prepared hills, partials, slots)
   int* d_flags = nullptr;   // [0] dirty-bounds flag
+  double* stage_partial = nullptr;  // accumulators left by the last deposit1d_stage call
 };
 
 struct HillAccepted {  // one selected candidate
@@ -77,7 +85,8 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int log_n;
   int log_dropped;
   int backlog_full;
-  int pad;
+  int round_mode;  // 0: sequential round, 1: parallel round planned, 2: parallel round committed
+  int n_fast;      // hills planned by the parallel round
   unsigned long long n_pairs;
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
 };
@@ -98,6 +107,7 @@ struct edm_bias {
   double* d_scalar = nullptr;          // [0] energy
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels
+  edm::Scratch fast;                   // centres | heights | bias_added of the parallel hill round
   // streaming triple
   int in_round = 0;
   long long round_est = 0;
