@@ -427,6 +427,7 @@ __global__ void deposit1d_prepare_kernel(GridDesc g, long n, const int* __restri
 
 __device__ __forceinline__ int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
+template <bool GPER>
 __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n, const int* __restrict__ n_dev,
                                                               const Hill1D* __restrict__ hills, long chunk, int nslot,
                                                               double* __restrict__ partial,
@@ -445,15 +446,16 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
   const int p0 = w * 32;
   const int p = p0 + lane;
   const bool have = p < npts;
-  const bool gper = g.periodic[0] != 0;
   const bool bper = g.bper[0] != 0;
-  const bool all_overlap = gper && (2 * m + 1 + 32 >= npts);
+  const bool all_overlap = GPER && (2 * m + 1 + 32 >= npts);
 
-  double xx = 0, valid = 0, uL = 0, uU = 0, t6 = 0, t7 = 0, Z = 1, Zd = 0;
+  // everything that depends on the grid point only lives in registers for the whole launch
+  double xx = 0, uL = 0, uU = 0, t6 = 0, t7 = 0, Z = 1, Zd = 0;
+  bool valid = false;
   if (have) {
     const double* row = g.ptab[0] + (long long)p * kPtabW;
     xx = row[0];
-    valid = row[1];
+    valid = row[1] != 0.0;
     uL = row[2];
     uU = row[3];
     t6 = row[4];
@@ -461,7 +463,11 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
     Z = row[6];
     Zd = row[7];
   }
-  const double sigma = g.sigma[0], len = g.len[0], sps = g.sqrtpi_sigma[0], vol = g.vol_element;
+  const double sigma = g.sigma[0], inv_sigma = 1.0 / sigma, len = g.len[0], vol = g.vol_element;
+  const double invZ = bper ? 1.0 / g.sqrtpi_sigma[0] : 1.0 / Z;
+  const double invZ2 = invZ * invZ;
+  const double ZdinvZ2 = Zd * invZ2;
+  const bool wall = !bper && (uL != 0.0 || uU != 0.0 || t6 != 0.0 || t7 != 0.0);  // within 2 sigma~ of a wall
   // chunk 0 starts from the stored value so that a single-chunk launch reproduces the reference's
   // rounding sequence ((g + t1) + t2) + ... exactly
   double acc_v = 0.0, acc_d = 0.0;
@@ -476,15 +482,13 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
     long mine = base + lane;
     bool ov = false;
     if (mine < h1) {
-      int ok = hills[mine].ok;
-      int xi = hills[mine].xi;
+      const int ok = hills[mine].ok;
+      const int xi = hills[mine].xi;
       if (ok) {
-        if (all_overlap) {
-          ov = true;
-        } else if (gper) {
+        if (GPER) {
           int d = (p0 - xi) % npts;
           if (d < 0) d += npts;
-          ov = (d <= m) || (d >= npts - m - 31);
+          ov = all_overlap || (d <= m) || (d >= npts - m - 31);
         } else {
           ov = (xi - m <= p0 + 31) && (xi + m >= p0);
         }
@@ -492,61 +496,71 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
     }
     unsigned mask = __ballot_sync(0xffffffffu, ov);
     while (mask) {
-      int b = __ffs(mask) - 1;
+      const int b = __ffs(mask) - 1;
       mask &= mask - 1;
       const Hill1D hl = hills[base + b];  // same address across the warp: one broadcast load
       int mult = 0;
-      if (have && valid != 0.0) {
-        if (gper) {
+      if (valid) {
+        if (GPER) {
           int o0 = (p - hl.xi) % npts;
           if (o0 < 0) o0 += npts;
-          // offsets o0 - k*npts inside [-m, m]
-          int khi = floor_div(o0 + m, npts), klo = -floor_div(m - o0, npts);
+          // window offsets o0 - k*npts inside [-m, m]: a window wider than the grid revisits points
+          const int khi = floor_div(o0 + m, npts), klo = -floor_div(m - o0, npts);
           mult = khi - klo + 1;
           if (mult < 0) mult = 0;
         } else {
-          int o = p - hl.xi;
+          const int o = p - hl.xi;
           mult = (o >= -m && o <= m) ? 1 : 0;
         }
       }
       double term_ba = 0.0;
       if (mult > 0) {
         double v = __dsub_rn(xx, hl.x);
-        if (gper) v = __dsub_rn(v, __dmul_rn(d_round(__ddiv_rn(v, len)), len));
-        const double dp = __ddiv_rn(v, sigma);
-        const double dp2 = __dmul_rn(dp, dp);
+        if (GPER) v = __dsub_rn(v, __dmul_rn(d_round(__ddiv_rn(v, len)), len));
+        // reciprocal first; the exactly rounded quotient only where it could change the support test
+        double dp = v * inv_sigma;
+        double dp2 = dp * dp;
+        if (fabs(dp2 - kGaussSupport) < 1e-12) {
+          dp = __ddiv_rn(v, sigma);
+          dp2 = __dmul_rn(dp, dp);
+        }
         if (dp2 < kGaussSupport) {
-          double expo = exp(-dp2);
+          const double E = exp(-dp2);
+          const double t5 = -2.0 * dp * inv_sigma;
           double etot, F;
-          if (!bper) {
-            double corr = (hl.t1 - expo) * uL + (hl.t3 - expo) * uU;
-            double t5 = -2.0 * dp / sigma;
-            F = t5 * expo;
-            F += (hl.t1 - expo) * t6 - t5 * expo * uL + (hl.t3 - expo) * t7 - t5 * expo * uU;
-            F = F * Z - Zd * (expo + corr);
-            F /= Z * Z;
-            corr /= Z;
-            expo /= Z;
-            etot = expo + corr;
+          if (wall) {  // McGDP + zero-force terms, lib/gaussian_grid.h:310-337
+            double corr = (hl.t1 - E) * uL + (hl.t3 - E) * uU;
+            F = t5 * E + (hl.t1 - E) * t6 - t5 * E * uL + (hl.t3 - E) * t7 - t5 * E * uU;
+            F = (F * Z - Zd * (E + corr)) * invZ2;
+            corr *= invZ;
+            etot = E * invZ + corr;
             dirty |= (corr * corr > 0.0);
-          } else {
-            expo /= sps;
-            etot = expo;
-            F = -(2.0 * dp / sigma * expo);
+          } else if (!bper) {  // interior of a non-periodic boundary: the correction terms vanish
+            etot = E * invZ;
+            F = E * (t5 * invZ - ZdinvZ2);
+          } else {  // periodic boundary, lib/gaussian_grid.h:340,352
+            etot = E * invZ;
+            F = t5 * etot;
           }
           const double add = hl.h * etot;
           const double addd = hl.h * F;
-          for (int k = 0; k < mult; k++) {
+          if (GPER) {
+            for (int k = 0; k < mult; k++) {
+              acc_v += add;
+              acc_d += addd;
+              term_ba += add * vol;
+            }
+          } else {
             acc_v += add;
             acc_d += addd;
-            term_ba += add * vol;
+            term_ba = add * vol;
           }
         }
       }
-      double tot = warp_sum(term_ba);
+      const double tot = warp_sum(term_ba);
       if (lane == 0) {
         int slot;
-        if (gper) {
+        if (GPER) {
           int s = (hl.xi - m) % npts;
           if (s < 0) s += npts;
           slot = (w - (s >> 5) + nwarps) % nwarps;
@@ -625,7 +639,10 @@ int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, d
   deposit1d_prepare_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(d, n_max, n_dev, centres, heights, hl);
   long chunk = (n_max + 31) / 32 * 32;
   dim3 grid((nwarps + 3) / 4, 1);
-  deposit1d_owner_kernel<<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
+  if (d.periodic[0])
+    deposit1d_owner_kernel<true><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
+  else
+    deposit1d_owner_kernel<false><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
   deposit1d_ba_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(n_max, n_dev, nslot, slots, ba);
   g->stage_partial = partial;
   count_launches(3);
@@ -1027,7 +1044,10 @@ static int deposit_1d_owner(edm_grid* g, long n, const double* centres, const do
     EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
     deposit1d_prepare_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(d, cnt, nullptr, centres + off, heights + off, hl);
     dim3 grid((nwarps + 3) / 4, nchunks);
-    deposit1d_owner_kernel<<<grid, 128, 0, st>>>(d, cnt, nullptr, hl, chunk, nslot, partial, slots, g->d_flags);
+    if (d.periodic[0])
+      deposit1d_owner_kernel<true><<<grid, 128, 0, st>>>(d, cnt, nullptr, hl, chunk, nslot, partial, slots, g->d_flags);
+    else
+      deposit1d_owner_kernel<false><<<grid, 128, 0, st>>>(d, cnt, nullptr, hl, chunk, nslot, partial, slots, g->d_flags);
     deposit1d_commit_kernel<<<(npts + 255) / 256, 256, 0, st>>>(d, nchunks, partial, nullptr, 0);
     if (ba) deposit1d_ba_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(cnt, nullptr, nslot, slots, ba + off);
     count_launches(ba ? 4 : 3);
