@@ -59,5 +59,39 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+HOST_SRCS = ["edm.cpp", "grid.cpp", "gaussian_grid.cpp", "edm_bias.cpp"]
+HOST_LIB = os.path.join(LIBDIR, "libedm.so")
+HOST_TEST = os.path.join(LIBDIR, "edm_host_test")
+CXX = "/usr/bin/g++"
+CXXFLAGS = ["-std=c++11", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
+
+
+def build_host_tests(force=False):
+    """libedm.so (the EDM:: C++ API over the C ABI), the restated reference tests, and a compile
+    check of the two LAMMPS fixes against the mock LAMMPS headers."""
+    build_lib()
+    edm_dir = os.path.join(HERE, "edm")
+    srcs = [os.path.join(edm_dir, s) for s in HOST_SRCS]
+    hdrs = [os.path.join(edm_dir, h) for h in ("edm.h", "grid.h", "gaussian_grid.h", "edm_bias.h")]
+    link = ["-L" + LIBDIR, "-ledm_b200", "-Wl,-rpath,$ORIGIN"]
+    if force or _stale(HOST_LIB, srcs + hdrs + [LIB]):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-shared", "-o", HOST_LIB] + srcs + link)
+    test_src = os.path.join(HERE, "tests_host", "edm_host_test.cpp")
+    if force or _stale(HOST_TEST, [test_src, HOST_LIB]):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-o", HOST_TEST, test_src, "-L" + LIBDIR, "-ledm", "-ledm_b200",
+                                                  "-Wl,-rpath,$ORIGIN"])
+    # LAMMPS fixes: <edm/edm_bias.h> resolves through the package directory itself
+    lmp = os.path.join(HERE, "lammps")
+    for f in ("fix_edm.cpp", "fix_edm_pair.cpp"):
+        obj = os.path.join(LIBDIR, f.replace(".cpp", ".o"))
+        src = os.path.join(lmp, f)
+        if force or _stale(obj, [src, os.path.join(lmp, f.replace(".cpp", ".h"))] + hdrs):
+            subprocess.check_call([CXX] + CXXFLAGS + ["-I" + HERE, "-I" + os.path.join(lmp, "mock"), "-I" + lmp,
+                                                      "-c", src, "-o", obj])
+    return HOST_TEST
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--host" in sys.argv:
+        print(build_host_tests(force="--force" in sys.argv))

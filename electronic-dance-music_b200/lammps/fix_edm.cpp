@@ -1,0 +1,96 @@
+// fix edm — coordinate collective variables, B200 build.
+// Reference entry point: lammps/fix_edm.cpp:134-162 (post_force).  The per-step work is two calls
+// into EDM::EDMBias, each of which is one batched launch sequence on the GPU.
+#include "fix_edm.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "atom.h"
+#include "domain.h"
+#include "error.h"
+#include "force.h"
+#include "memory.h"
+#include "neighbor.h"
+#include "random_mars.h"
+#include "respa.h"
+#include "update.h"
+
+using namespace LAMMPS_NS;
+using namespace FixConst;
+
+FixEDM::FixEDM(LAMMPS* lmp, int narg, char** arg)
+    : Fix(lmp, narg, arg), bias(NULL), random(NULL), random_numbers(NULL), random_capacity(0), edm_energy(0) {
+  if (narg < 9) error->all(FLERR, "Illegal fix EDM command");
+  if (!atom->tag_enable) error->all(FLERR, "fix EDM requires atom tags");
+  int me = 0;
+  MPI_Comm_rank(world, &me);
+  temperature = atof(arg[3]);
+  stride = atoi(arg[5]);
+  write_stride = atoi(arg[6]);
+  strncpy(bias_file, arg[7], sizeof(bias_file) - 1);
+  bias_file[sizeof(bias_file) - 1] = '\0';
+  seed = atoi(arg[8]);
+  if (stride < 0) error->all(FLERR, "Illegal stride given to EDM command");
+  if (write_stride < 0) error->all(FLERR, "Illegal write bias stride given to EDM command");
+  bias = new EDM::EDMBias(arg[4]);
+  thermo_energy = 1;
+  random = new RanMars(lmp, seed + me);
+}
+
+FixEDM::~FixEDM() {
+  delete bias;
+  delete random;
+  free(random_numbers);
+}
+
+int FixEDM::setmask() { return POST_FORCE | THERMO_ENERGY | POST_FORCE_RESPA | MIN_POST_FORCE; }
+
+void FixEDM::init() {
+  if (strcmp(update->integrate_style, "respa") == 0) nlevels_respa = ((Respa*)update->integrate)->nlevels;
+  bias->setup(temperature, force->boltz);
+  double skin[3] = {neighbor->skin, neighbor->skin, neighbor->skin};
+  // the bias grid is replicated on every GPU: the "sub-box" handed over is the whole box
+  bias->subdivide(domain->boxlo, domain->boxhi, domain->boxlo, domain->boxhi, domain->periodicity, skin);
+  bias->set_mask(atom->mask);
+  edm_energy = 0;
+}
+
+void FixEDM::setup(int vflag) {
+  if (strcmp(update->integrate_style, "verlet") == 0) {
+    post_force(vflag);
+  } else {
+    ((Respa*)update->integrate)->copy_flevel_f(nlevels_respa - 1);
+    post_force_respa(vflag, nlevels_respa - 1, 0);
+    ((Respa*)update->integrate)->copy_f_flevel(nlevels_respa - 1);
+  }
+}
+
+void FixEDM::min_setup(int vflag) { post_force(vflag); }
+
+void FixEDM::post_force(int) {
+  const int n = atom->nlocal;
+  bias->set_mask(atom->mask);
+  edm_energy = bias->update_forces(n, atom->x, atom->f, groupbit);
+  if (stride > 0 && update->ntimestep % stride == 0) {
+    if (random_capacity < n) {  // one uniform per local atom, drawn in atom order (fix_edm.cpp:149-151)
+      random_numbers = (double*)realloc(random_numbers, sizeof(double) * (size_t)atom->nmax);
+      random_capacity = atom->nmax;
+    }
+    for (int i = 0; i < n; i++) random_numbers[i] = random->uniform();
+    bias->add_hills(n, atom->x, random_numbers, groupbit);
+  }
+  if (write_stride > 0 && update->ntimestep % write_stride == 0) {
+    bias->write_bias(bias_file);
+    bias->write_histogram();
+    bias->clear_histogram();
+  }
+}
+
+void FixEDM::post_force_respa(int vflag, int ilevel, int) {
+  if (ilevel == nlevels_respa - 1) post_force(vflag);
+}
+
+void FixEDM::min_post_force(int vflag) { post_force(vflag); }
+
+double FixEDM::compute_scalar() { return edm_energy; }

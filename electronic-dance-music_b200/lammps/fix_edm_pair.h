@@ -1,0 +1,53 @@
+#ifdef FIX_CLASS
+
+FixStyle(edm_pair,FixEDMPair)
+
+#else
+
+#ifndef LMP_FIX_EDM_PAIR_H
+#define LMP_FIX_EDM_PAIR_H
+
+#include "fix.h"
+#include <edm/edm_bias.h>
+#include "neigh_list.h"
+
+#include <vector>
+
+namespace LAMMPS_NS {
+
+// fix ID group edm_pair T input.edm hill_stride write_stride bias_file seed itype jtype
+// Pair-distance CV entry point (reference: lammps/fix_edm_pair.{h,cpp}).  The half neighbour list
+// LAMMPS builds is flattened to CSR and the whole loop — r, bias energy and force at r, force
+// scatter, two hill proposals per local pair — runs as one kernel (edm_pair_step_list).
+class FixEDMPair : public Fix {
+ public:
+  FixEDMPair(class LAMMPS*, int, char**);
+  ~FixEDMPair();
+  int setmask();
+  void init();
+  void setup(int);
+  void min_setup(int);
+  void post_force(int);
+  void post_force_respa(int, int, int);
+  void min_post_force(int);
+  void init_list(int, class NeighList*);
+  double compute_scalar();
+
+ private:
+  EDM::EDMBias* bias;
+  class NeighList* list;
+  char bias_file[512];
+  char lammps_table_file[520];
+  double temperature, edm_energy;
+  int stride, write_stride;
+  unsigned int seed;
+  long long last_calls;
+  int ipair, jpair;
+  std::vector<long> first_;
+  std::vector<int> jlist_;
+};
+
+}  // namespace LAMMPS_NS
+
+#endif
+#endif
