@@ -1,0 +1,97 @@
+"""Run under torchrun on N GPUs: every rank evaluates its own atoms' pairs, selects hills locally,
+packs them on the device, all-gathers the blocks over NCCL and commits the concatenation.  Checks:
+replicas bit-identical across ranks; rank 0 equal (1e-10) to a single-rank oracle that sees the
+rank-major concatenation of all ranks' pairs."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "electronic-dance-music_b200", "python"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import edm_b200 as edm  # noqa: E402
+import pyoracle  # noqa: E402
+
+EDM_TEXT = ("tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.004\n"
+            "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025\n")
+
+
+def main():
+    tmp = sys.argv[1]
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = os.path.join(tmp, "r%d" % rank)
+    os.makedirs(d, exist_ok=True)
+    f = os.path.join(d, "c.edm")
+    open(f, "w").write(EDM_TEXT + "hills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (d, d))
+    L = edm.lib()
+    b = edm.bias_from_edm(f, 300.0, 0.0019872, [1.68], [5.0], [1.68], [5.0], [0], [0.0], device=local)
+    n, box_len, rc, cap, steps, seed = 5000, 34.0, 5.0, 2048, 5, 11
+    box = np.array([box_len] * 3)
+    boxp = box.ctypes.data_as(C.POINTER(C.c_double))
+    blk_n = L.edm_hill_block_doubles(1, cap)
+    block = torch.zeros(blk_n, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(blk_n * world, dtype=torch.float64, device="cuda")
+    fdev = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    edev = torch.zeros(1, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    est_total = 2 * 140000 * world
+    xs = []
+    for step in range(steps):
+        x = np.ascontiguousarray(np.random.default_rng([seed, rank, step]).uniform(0, box_len, size=(n, 3)))
+        xs.append(x)
+        xd = torch.from_numpy(x).cuda()
+        edm.check(L.edm_pair_select_cells_dev(b.h, n, xd.data_ptr(), fdev.data_ptr(), None, 0, 0, boxp, rc, est_total,
+                                              seed + rank, step, edev.data_ptr(), st))
+        edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, st))
+        dist.all_gather_into_tensor(gathered, block)
+        edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, est_total, st))
+    torch.cuda.synchronize()
+    v, dv = b.bias_grid.get_arrays()
+    # replicas identical across ranks
+    mine = torch.from_numpy(np.concatenate([v, dv.ravel()])).cuda()
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    same = torch.equal(mine, ref)
+    flags = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    assert int(flags.item()) == 1, "replicas differ across ranks"
+    # gather every rank's positions on rank 0 for the single-rank oracle
+    allx = [None] * world
+    dist.all_gather_object(allx, xs)
+    if rank == 0:
+        fo = os.path.join(tmp, "o.edm")
+        open(fo, "w").write(EDM_TEXT + "hills_filename %s/H\nhistogram_filename %s/G\n" % (tmp, tmp))
+        bo = pyoracle.Bias("port", fo)
+        bo.setup(300.0, 0.0019872)
+        bo.subdivide([1.68], [5.0], [1.68], [5.0], [0], [0.0])
+        for step in range(steps):
+            rs, us = [], []
+            for r in range(world):
+                x = allx[r][step]
+                pi, pj, sh = pyoracle.build_half_list(x, box, rc)
+                force = np.zeros((n, 3))
+                _, rr = bo.pair_step(pi, pj, x, force, shift=sh, do_hills=False)
+                rs.append(rr)
+                us.append(pyoracle.pair_uniforms(seed + r, step, pi, pj, n))
+            bo.pre_add_hill(est_total)
+            bo.add_hill_many(np.repeat(np.concatenate(rs), 2), np.concatenate(us))
+            bo.post_add_hill()
+        vo, do = bo.gauss.get_arrays()
+        scale = np.abs(vo).max()
+        assert np.abs(v - vo).max() <= 1e-10 * scale, np.abs(v - vo).max() / scale
+        ld, lo = b.log(), bo.log()
+        assert len(ld) == len(lo) and np.array_equal(ld["type"], lo["type"]) and np.array_equal(ld["pos"], lo["pos"])
+        assert b.backlog()[:2] == bo.backlog()[:2]
+        print("MULTI_GPU_CHECK_OK world=%d events=%d" % (world, len(ld)))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

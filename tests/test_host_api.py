@@ -64,10 +64,51 @@ def test_reference_fixes_compile_unchanged_against_this_api(fix, tmp_path):
     subprocess.check_call(cmd)
 
 
+def write_plumed_grid(path, dim, n, dx, mn, mx, per, force, values, derivs):
+    """PLUMED-1 grid text as the reference writes it (lib/grid.h:448-503), from stored arrays."""
+    import numpy as np
+    with open(path, "w") as fh:
+        fh.write("#! FORCE %d\n#! NVAR %d\n#! TYPE %s\n" % (force, dim, " ".join(["32"] * dim) + " "))
+        fh.write("#! BIN %s \n" % " ".join(str(int(n[i] if per[i] else n[i] - 1)) for i in range(dim)))
+        fh.write("#! MIN %s \n" % " ".join("%g" % mn[i] for i in range(dim)))
+        fh.write("#! MAX %s \n" % " ".join("%g" % (mx[i] if per[i] else mx[i] - dx[i]) for i in range(dim)))
+        fh.write("#! PBC %s \n" % " ".join(str(int(per[i])) for i in range(dim)))
+        idx = np.zeros(dim, dtype=np.int64)
+        for p in range(values.size):
+            t = p
+            for j in range(dim - 1):
+                idx[j] = t % n[j]
+                t = (t - idx[j]) // n[j]
+            idx[dim - 1] = t
+            row = ["%.8f" % (mn[j] + dx[j] * idx[j]) for j in range(dim)] + ["%.8f" % values[p]]
+            if force:
+                row += ["%.8f" % (-derivs[p, j]) for j in range(dim)]
+            fh.write(" ".join(row) + " \n")
+            if idx[0] == n[0] - 1:
+                fh.write("\n")
+
+
+def make_fixture_dir(tmp_path):
+    """1.grid 2.grid 3.grid read_test.edm rebuilt from tests/golden/plumed_grids.npz (the arrays the
+    reference's reader produced from its own fixtures), so the file-based cases run without the tree."""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "plumed_grids.npz"))
+    d = tmp_path / "fixtures"
+    d.mkdir()
+    for dim in (1, 2, 3):
+        s = str(dim)
+        write_plumed_grid(str(d / (s + ".grid")), dim, z["n" + s], z["dx" + s], z["min" + s], z["max" + s],
+                          z["periodic" + s], int(z["b_derivatives" + s]), z["grid" + s], z["deriv" + s])
+    (d / "read_test.edm").write_text("dimension 2\ntempering 0\nhill_prefactor 1.0\nhill_density 1\n"
+                                     "bias_spacing 1.0 1.0\nbias_sigma 2 1\ntarget_filename 2.grid.test\n"
+                                     "box_low 0 0 \nbox_high 5 5\n")
+    return str(d)
+
+
 @pytest.mark.gpu
 def test_restated_reference_unit_tests_on_gpu(host_test_binary, tmp_path):
     """tests/edm_test.cpp restated (tests_host/edm_host_test.cpp), run against the device."""
-    src = os.path.join(REF, "tests") if os.path.isdir(os.path.join(REF, "tests")) else "-"
+    src = make_fixture_dir(tmp_path)
     r = subprocess.run([host_test_binary, src], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:])
     print(r.stderr[-2000:])
