@@ -371,7 +371,10 @@ def run_gpu(args, rank, local_rank, world):
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms, e2e_s = float(mx[0]), float(mx[1])
-        pairs_all, e2e_pairs_all, hills_all, launches_all = float(sm[2]), float(sm[3]), float(sm[4]), float(sm[5])
+        mn = stats.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        # hills are NOT sharded: every replica deposits every hill, so the job's rate is one replica's
+        pairs_all, e2e_pairs_all, hills_all, launches_all = float(sm[2]), float(sm[3]), float(mn[4]), float(sm[5])
     else:
         pairs_all, e2e_pairs_all, hills_all, launches_all = float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)
 
