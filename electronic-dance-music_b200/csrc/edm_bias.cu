@@ -677,6 +677,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->io4.release();
   b->cells.release();
   b->fast.release();
+  b->cand.release();
   delete b;
   return EDM_OK;
 }

@@ -107,6 +107,7 @@ struct edm_bias {
   double* d_scalar = nullptr;          // [0] energy
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels
+  edm::Scratch cand;                   // candidate pair list of the split pair search
   edm::Scratch fast;                   // centres | heights | bias_added of the parallel hill round
   // streaming triple
   int in_round = 0;

@@ -50,30 +50,69 @@ __global__ void cell_count_kernel(long n, const double* __restrict__ x, CellGrid
   atomicAdd(&count[c], 1);
 }
 
-// exclusive scan of count[0..n) into start[0..n]; one CTA, each thread scans a contiguous slice
-__global__ void __launch_bounds__(1024) cell_scan_kernel(int n, const int* __restrict__ count, int* __restrict__ start) {
-  __shared__ int part[1024];
-  int per = (n + blockDim.x - 1) / blockDim.x;
-  int lo = threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+// exclusive scan of count[0..n) into start[0..n], two passes over tiles of 2048 cells:
+// (1) per-tile totals, (2) every tile sums the totals before it and scans its own cells
+constexpr int kScanTile = 2048;  // 256 threads x 8 cells
+
+__global__ void __launch_bounds__(256) cell_scan_totals_kernel(int n, const int* __restrict__ count,
+                                                               int* __restrict__ tile_total) {
+  __shared__ int wsum[8];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * 8;
   int s = 0;
-  for (int i = lo; i < hi; i++) s += count[i];
-  part[threadIdx.x] = s;
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    if (base + k < n) s += count[base + k];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
-    int run = 0;
-    for (int t = 0; t < blockDim.x; t++) {
-      int v = part[t];
-      part[t] = run;
-      run += v;
-    }
-    start[n] = run;
+    int t = 0;
+    for (int i = 0; i < 8; i++) t += wsum[i];
+    tile_total[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) cell_scan_kernel(int n, const int* __restrict__ count,
+                                                        const int* __restrict__ tile_total, int* __restrict__ start) {
+  __shared__ int wsum[8];
+  __shared__ int s_offset;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // offset of this tile: sum of the totals of the tiles before it
+  int part = 0;
+  for (int t = threadIdx.x; t < (int)blockIdx.x; t += blockDim.x) part += tile_total[t];
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+  if (lane == 0) wsum[wid] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; i++) t += wsum[i];
+    s_offset = t;
   }
   __syncthreads();
-  int run = part[threadIdx.x];
-  for (int i = lo; i < hi; i++) {
-    start[i] = run;
-    run += count[i];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * 8;
+  int v[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    v[k] = (base + k < n) ? count[base + k] : 0;
+    s += v[k];
   }
+  int incl = s;  // inclusive scan of the per-thread sums across the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  __syncthreads();
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < wid; i++) woff += wsum[i];
+  int run = s_offset + woff + incl - s;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    if (base + k < n) start[base + k] = run;
+    run += v[k];
+  }
+  if (base <= n - 1 && n - 1 < base + 8) start[n] = run;  // the thread that owns the last cell closes the array
 }
 
 __global__ void cell_fill_kernel(long n, const int* __restrict__ cell_of, const int* __restrict__ start,
@@ -564,6 +603,258 @@ __global__ void __launch_bounds__(kPairWarps * 32, EDM_PAIR_MINBLOCKS) pair_cell
   if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
 }
 
+// ---- v5: the same search split in two kernels -------------------------------------------------
+//
+// pair_find_kernel   STAGE + TEST of v4; instead of a shared-memory queue feeding an in-kernel heavy
+//                    path it appends the candidate pairs (slot_i, slot_j | shift code) to a global
+//                    list, in chunks a warp allocates with one atomic per 256 candidates.
+// pair_eval_kernel   one lane per candidate, fully populated warps, no shared memory: exact fp64
+//                    separation + cutoff, bias at r, hill proposals, force scatter.  Candidates of a
+//                    home atom are contiguous in a chunk, so the home side is a segmented shuffle scan
+//                    with one RED triple per run; the neighbour side is one RED triple per pair.
+// Splitting lets each kernel run at its own occupancy (the search needs shared memory and few
+// registers, the evaluation the opposite) at the price of 8 B written + read per candidate.
+constexpr int kChunk = 256;
+
+struct FindWarpSmem {
+  float jx[kJCap], jy[kJCap], jz[kJCap];
+  float ix[kICap], iy[kICap], iz[kICap];
+  int jpack[kJCap];  // slot | code << 26
+};
+
+struct CandList {
+  int2* items;                  // x = slot_i (-1: padding), y = slot_j | code << 26
+  unsigned long long cap;       // entries
+  unsigned long long* count;    // entries allocated so far (multiple of kChunk)
+  int* overflow;
+};
+
+__global__ void __launch_bounds__(kPairWarps * 32, 8) pair_find_kernel(const __grid_constant__ PairCtx c, CandList cl) {
+  __shared__ FindWarpSmem wsm[kPairWarps];
+  FindWarpSmem& w = wsm[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * kPairWarps;
+  const CellGrid& cg = c.cg;
+  const PairParams& pp = c.pp;
+  const float rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;
+  const float csx = (float)cg.cs[0], csy = (float)cg.cs[1], csz = (float)cg.cs[2];
+  long long chunk_base = -1;  // -1: candidates are dropped (list full)
+  int used = kChunk;          // forces an allocation on first use
+
+  for (int cell = gw; cell < cg.ncell; cell += nwarps) {
+    const int clo = c.start[cell], chi = c.start[cell + 1];
+    if (clo == chi) continue;
+    const int cx = cell % cg.nc[0], cy = (cell / cg.nc[0]) % cg.nc[1], cz = cell / (cg.nc[0] * cg.nc[1]);
+    for (int ilo = clo; ilo < chi; ilo += kICap) {
+      const int ni = min(kICap, chi - ilo);
+      for (int a = lane; a < ni; a += 32) {
+        w.ix[a] = c.xs32[3 * (long)(ilo + a) + 0] + csx;
+        w.iy[a] = c.xs32[3 * (long)(ilo + a) + 1] + csy;
+        w.iz[a] = c.xs32[3 * (long)(ilo + a) + 2] + csz;
+      }
+      int nj = 0;
+      int self_hi = 0, self_slot0 = 0;
+      __syncwarp();
+
+      auto run_tests = [&]() {
+        __syncwarp();
+        for (int ii = 0; ii < ni; ii++) {
+          const int si = ilo + ii;
+          int ti = 0;
+          if (pp.use_types) {
+            ti = c.ts[si];
+            if (ti != pp.itype && ti != pp.jtype) continue;
+          }
+          const float xi = w.ix[ii], yi = w.iy[ii], zi = w.iz[ii];
+          const int selfcut = si - self_slot0;
+          for (int jb = 0; jb < nj; jb += 128) {
+            bool take[4];
+            int pk[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int jj = jb + 32 * u + lane;
+              take[u] = false;
+              pk[u] = 0;
+              if (jj < nj) {
+                const float dx = xi - w.jx[jj], dy = yi - w.jy[jj], dz = zi - w.jz[jj];
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                take[u] = (d2 < rc2m) && (jj >= self_hi || jj > selfcut);
+                pk[u] = w.jpack[jj];
+                if (take[u] && pp.use_types) {
+                  const int tj = c.ts[pk[u] & 0x3ffffff];
+                  take[u] = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const unsigned m = __ballot_sync(0xffffffffu, take[u]);
+              if (m == 0u) continue;
+              const int k = __popc(m);
+              if (used + k > kChunk) {  // close the chunk with padding and take a new one
+                if (chunk_base >= 0)
+                  for (int a = used + lane; a < kChunk; a += 32) cl.items[chunk_base + a] = make_int2(-1, 0);
+                unsigned long long nb = 0;
+                if (lane == 0) nb = atomicAdd(cl.count, (unsigned long long)kChunk);
+                nb = __shfl_sync(0xffffffffu, nb, 0);
+                if (nb + kChunk > cl.cap) {
+                  chunk_base = -1;
+                  if (lane == 0) *cl.overflow = 1;
+                } else {
+                  chunk_base = (long long)nb;
+                }
+                used = 0;
+              }
+              if (take[u] && chunk_base >= 0)
+                cl.items[chunk_base + used + __popc(m & ((1u << lane) - 1u))] = make_int2(si, pk[u]);
+              used += k;
+            }
+          }
+        }
+      };
+
+      for (int row = 0; row < 5; row++) {
+        const int oy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3);
+        const int oz = (row < 2) ? 0 : 1;
+        const int ox0 = (row == 0) ? 0 : -1;
+        int qy = cy + oy, qz = cz + oz, ycode = 0;
+        if (qy >= cg.nc[1]) { qy -= cg.nc[1]; ycode |= 4; } else if (qy < 0) { qy += cg.nc[1]; ycode |= 8; }
+        if (qz >= cg.nc[2]) { qz -= cg.nc[2]; ycode |= 16; } else if (qz < 0) { qz += cg.nc[2]; ycode |= 32; }
+        const float offy = (float)(oy + 1) * csy, offz = (float)(oz + 1) * csz;
+        const int rowbase = (qz * cg.nc[1] + qy) * cg.nc[0];
+        for (int ox = ox0; ox <= 1; ox++) {
+          int qx = cx + ox, code = ycode;
+          if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
+          int ncell = 1;
+          while (ox + ncell <= 1 && qx + ncell < cg.nc[0] && !(code & 2)) ncell++;
+          if ((code & 2)) ncell = 1;
+          const int q0 = rowbase + qx;
+          const int b0 = c.start[q0];
+          const int b1 = c.start[q0 + 1];
+          const int b2 = (ncell > 1) ? c.start[q0 + 2] : b1;
+          const int b3 = (ncell > 2) ? c.start[q0 + 3] : b2;
+          const float offx0 = (float)(ox + 1) * csx;
+          const bool own = (row == 0 && ox == 0);
+          int lo = b0;
+          const int hi = b3;
+          while (lo < hi) {
+            if (nj == kJCap) {
+              run_tests();
+              nj = 0;
+              self_hi = 0;
+              __syncwarp();
+            }
+            const int takeN = min(kJCap - nj, hi - lo);
+            if (own && lo < b1) {
+              self_slot0 = lo;
+              self_hi = min(takeN, b1 - lo);
+            }
+            for (int a = lane; a < takeN; a += 32) {
+              const int sl = lo + a;
+              const float offx = offx0 + (float)((sl >= b1) + (sl >= b2)) * csx;
+              w.jx[nj + a] = c.xs32[3 * (long)sl + 0] + offx;
+              w.jy[nj + a] = c.xs32[3 * (long)sl + 1] + offy;
+              w.jz[nj + a] = c.xs32[3 * (long)sl + 2] + offz;
+              w.jpack[nj + a] = sl | (code << 26);
+            }
+            nj += takeN;
+            lo += takeN;
+          }
+          ox += ncell - 1;
+        }
+      }
+      if (nj) run_tests();
+      __syncwarp();
+    }
+  }
+  if (chunk_base >= 0)
+    for (int a = used + lane; a < kChunk; a += 32) cl.items[chunk_base + a] = make_int2(-1, 0);
+}
+
+__global__ void __launch_bounds__(256) pair_eval_kernel(const __grid_constant__ PairCtx c, CandList cl) {
+  __shared__ double red[33];
+  const int lane = threadIdx.x & 31;
+  unsigned long long total = *cl.count;
+  if (total > cl.cap) total = cl.cap - cl.cap % kChunk;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  double e = 0.0;
+  unsigned long long npairs = 0;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total;
+       base += stride) {
+    const int2 it = cl.items[base + lane];  // total is a multiple of 32
+    int si = it.x;
+    int oi = -1;
+    bool on = si >= 0;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (on) {
+      const long sj = it.y & 0x3ffffff;
+      const int code = (int)((unsigned)it.y >> 26);
+      const double sx = (code & 1) ? c.cg.box[0] : ((code & 2) ? -c.cg.box[0] : 0.0);
+      const double sy = (code & 4) ? c.cg.box[1] : ((code & 8) ? -c.cg.box[1] : 0.0);
+      const double sz = (code & 16) ? c.cg.box[2] : ((code & 32) ? -c.cg.box[2] : 0.0);
+      // exactly the oracle's separation: (x_i - x_j) - image shift, squares summed in x, y, z order
+      const double dx = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 0], c.xs[3 * sj + 0]), sx);
+      const double dy = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 1], c.xs[3 * sj + 1]), sy);
+      const double dz = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 2], c.xs[3 * sj + 2]), sz);
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      on = d2 < c.pp.rc2;
+      oi = c.order[si];
+      if (on) {
+        const int oj = c.order[sj];
+        const double rinv = rsqrt(d2);
+        const double r = d2 * rinv;
+        double force;
+        e += pair_eval_fast(c.g, r, force);
+        npairs++;
+        const double s = rinv * force;
+        px = dx * s;
+        py = dy * s;
+        pz = dz * s;
+        if (c.pp.do_hills) {
+          const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
+          propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
+        }
+        atomicAdd(&c.f[3 * (long)oj + 0], -px);
+        atomicAdd(&c.f[3 * (long)oj + 1], -py);
+        atomicAdd(&c.f[3 * (long)oj + 2], -pz);
+      }
+    }
+    // home side: segmented inclusive scan (head flags: a slot_i may reappear later in the list when a
+    // neighbourhood was staged in two parts), one RED triple per run
+    const int iprev = __shfl_up_sync(0xffffffffu, si, 1);
+    int head = (lane == 0 || iprev != si) ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int uh = __shfl_up_sync(0xffffffffu, head, o);
+      const double ux = __shfl_up_sync(0xffffffffu, px, o);
+      const double uy = __shfl_up_sync(0xffffffffu, py, o);
+      const double uz = __shfl_up_sync(0xffffffffu, pz, o);
+      if (lane >= o && !head) {
+        px += ux;
+        py += uy;
+        pz += uz;
+        head = uh;
+      }
+    }
+    const int inext = __shfl_down_sync(0xffffffffu, si, 1);
+    if (si >= 0 && (lane == 31 || inext != si)) {
+      atomicAdd(&c.f[3 * (long)oi + 0], px);
+      atomicAdd(&c.f[3 * (long)oi + 1], py);
+      atomicAdd(&c.f[3 * (long)oi + 2], pz);
+    }
+  }
+  double tot = block_sum(e, red);
+  if (threadIdx.x == 0) c.partial[blockIdx.x] = tot;
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+  if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
+}
+
+__global__ void reset_cand_kernel(unsigned long long* count, int* overflow) {
+  *count = 0;
+  *overflow = 0;
+}
+
 // Neighbour-list form: one thread per listed i-row (lammps/fix_edm_pair.cpp:177-240).
 __global__ void __launch_bounds__(128) pair_list_kernel(GridDesc g, PairParams pp, long nlocal, long inum,
                                                         const int* __restrict__ ilist, const long* __restrict__ first,
@@ -707,7 +998,8 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   size_t n = (size_t)natoms, nc1 = (size_t)ncell + 1;
   size_t off_cell = 0, off_order = off_cell + n * 4, off_ts = off_order + n * 4, off_count = off_ts + n * 4;
   size_t off_start = off_count + nc1 * 4;
-  size_t off_xs = (off_start + nc1 * 4 + 255) / 256 * 256;
+  size_t off_tiles = off_start + nc1 * 4;
+  size_t off_xs = (off_tiles + ((size_t)ncell / 2048 + 2) * 4 + 255) / 256 * 256;
   size_t off_xs32 = off_xs + 3 * n * sizeof(double);
   size_t total = off_xs32 + 3 * n * sizeof(float);
   EDM_TRY(b->cells.reserve(total));
@@ -717,13 +1009,16 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   int* ts = reinterpret_cast<int*>(base + off_ts);
   int* count = reinterpret_cast<int*>(base + off_count);
   int* start = reinterpret_cast<int*>(base + off_start);
+  int* tile_total = reinterpret_cast<int*>(base + off_tiles);
   double* xs = reinterpret_cast<double*>(base + off_xs);
   float* xs32 = reinterpret_cast<float*>(base + off_xs32);
 
   EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
   unsigned nb = (unsigned)((natoms + 255) / 256);
   cell_count_kernel<<<nb, 256, 0, st>>>(natoms, x, cg, cell_of, count);
-  cell_scan_kernel<<<1, 1024, 0, st>>>(cg.ncell, count, start);
+  const int ntiles = (cg.ncell + kScanTile - 1) / kScanTile;
+  cell_scan_totals_kernel<<<ntiles, 256, 0, st>>>(cg.ncell, count, tile_total);
+  cell_scan_kernel<<<ntiles, 256, 0, st>>>(cg.ncell, count, tile_total, start);
   EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
   cell_fill_kernel<<<nb, 256, 0, st>>>(natoms, cell_of, start, count, order);
   cell_sort_gather_kernel<<<(cg.ncell + 127) / 128, 128, 0, st>>>(cg, start, order, x, type, xs, xs32, type ? ts : nullptr);
@@ -735,7 +1030,7 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   static int mode = -1;
   if (mode < 0) {
     const char* ev = getenv("EDM_PAIR_MODE");
-    mode = ev ? atoi(ev) : 1;
+    mode = ev ? atoi(ev) : 2;
   }
   long long blocks;
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[0], st));
@@ -761,10 +1056,31 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
     ctx.partial = b->d_energy_partial;
     ctx.st = b->d_state;
     ctx.acc = b->d_accepted;
-    pair_cells_v4_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx);
+    if (mode == 1) {
+      pair_cells_v4_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx);
+    } else {
+      // candidate list: expected pairs at uniform density x 1.5 + chunk slack; an overflow is flagged
+      double vol = box[0] * box[1] * box[2];
+      double expect = 0.5 * (double)natoms * ((double)natoms / vol) * (4.0 / 3.0) * M_PI * cutoff * cutoff * cutoff;
+      unsigned long long cap = (unsigned long long)(1.5 * expect) + 8ULL * 148 * 8 * kPairWarps * kChunk / 8 + (1u << 16);
+      cap = (cap + kChunk - 1) / kChunk * kChunk;
+      EDM_TRY(b->cand.reserve(cap * sizeof(int2) + 64));
+      CandList cl;
+      cl.count = b->cand.as<unsigned long long>();
+      cl.overflow = reinterpret_cast<int*>(b->cand.as<char>() + 8);
+      cl.items = reinterpret_cast<int2*>(b->cand.as<char>() + 64);
+      cl.cap = cap;
+      reset_cand_kernel<<<1, 1, 0, st>>>(cl.count, cl.overflow);
+      pair_find_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx, cl);
+      int eblocks = 148 * 8;
+      if (eblocks > b->n_partial) eblocks = b->n_partial;
+      blocks = eblocks;
+      pair_eval_kernel<<<eblocks, 256, 0, st>>>(ctx, cl);
+      count_launches(2);
+    }
   }
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[1], st));
-  count_launches(7);
+  count_launches(8);
   sum_partials2_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy_dev);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
