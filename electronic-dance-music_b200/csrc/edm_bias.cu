@@ -669,7 +669,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   if (b->d_log) cudaFree(b->d_log);
   if (b->d_energy_partial) cudaFree(b->d_energy_partial);
   if (b->d_scalar) cudaFree(b->d_scalar);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 3; i++)
     if (b->ev_pair[i]) cudaEventDestroy(b->ev_pair[i]);
   b->io.release();
   b->io2.release();
@@ -678,6 +678,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->cells.release();
   b->fast.release();
   b->cand.release();
+  if (b->h_pair_flags) cudaFreeHost((void*)b->h_pair_flags);
   delete b;
   return EDM_OK;
 }
@@ -908,6 +909,7 @@ int edm_bias_set_profiling(edm_bias_t* b, int on) {
   if (on && !b->ev_pair[0]) {
     EDM_CUDA(cudaEventCreate(&b->ev_pair[0]));
     EDM_CUDA(cudaEventCreate(&b->ev_pair[1]));
+    EDM_CUDA(cudaEventCreate(&b->ev_pair[2]));
   }
   b->profiling = on;
   return EDM_OK;
@@ -920,6 +922,23 @@ int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms) {
   float ms = 0;
   EDM_CUDA(cudaEventElapsedTime(&ms, b->ev_pair[0], b->ev_pair[1]));
   *pair_kernel_ms = ms;
+  return EDM_OK;
+}
+
+int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms) {
+  EDM_REQUIRE(b && search_ms && eval_ms && b->ev_pair[0], "profiling was never enabled");
+  EDM_TRY(ensure_device(b->device));
+  EDM_CUDA(cudaEventSynchronize(b->ev_pair[1]));
+  float a = 0, c = 0;
+  // ev_pair[2] sits between the block search and the block evaluation; it is not recorded when the
+  // generic search ran instead
+  if (cudaEventElapsedTime(&a, b->ev_pair[0], b->ev_pair[2]) != cudaSuccess ||
+      cudaEventElapsedTime(&c, b->ev_pair[2], b->ev_pair[1]) != cudaSuccess) {
+    cudaGetLastError();
+    a = c = 0;
+  }
+  *search_ms = a;
+  *eval_ms = c;
   return EDM_OK;
 }
 

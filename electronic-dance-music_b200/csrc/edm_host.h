@@ -107,12 +107,17 @@ struct edm_bias {
   double* d_scalar = nullptr;          // [0] energy
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels
-  edm::Scratch cand;                   // candidate pair list of the split pair search
+  edm::Scratch cand;                   // candidate items of the block pair search, one slice per brick
+  volatile int* h_pair_flags = nullptr; // host-mapped: [0] = a pair step fell back to the direct search
+  int* d_pair_flags = nullptr;
+  int brick_dims[3] = {0, 0, 0};       // bricks of the last pair step (0: direct search)
+  long long pair_fallbacks = 0;        // steps that fell back to the direct search
+  double brick_scale = 1.0;            // density inflation used to size the bricks (grows after a fallback)
   edm::Scratch fast;                   // centres | heights | bias_added of the parallel hill round
   // streaming triple
   int in_round = 0;
   long long round_est = 0;
   unsigned long long round_count = 0;
   int profiling = 0;
-  cudaEvent_t ev_pair[2] = {nullptr, nullptr};
+  cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };

@@ -24,11 +24,13 @@ struct CellGrid {
 struct PairParams {
   int itype, jtype, use_types;
   int do_hills, accept_all;
+  int lean;  // interpolated, non-periodic grid and boundary: pair_eval_fast applies
   double thresh;
   uint64_t thresh_bits;  // ceil(thresh * 2^32), saturated
   int dbg;
   uint64_t key;
   double rc2;
+  float rc2m;  // fp32 prefilter radius^2: cutoff^2 enlarged by 1e-4 (the fp32 error is ~1e-5 absolute)
   long natoms;
   long acc_cap;
 };
@@ -115,48 +117,6 @@ __global__ void __launch_bounds__(256) cell_scan_kernel(int n, const int* __rest
   if (base <= n - 1 && n - 1 < base + 8) start[n] = run;  // the thread that owns the last cell closes the array
 }
 
-__global__ void cell_fill_kernel(long n, const int* __restrict__ cell_of, const int* __restrict__ start,
-                                 int* __restrict__ fill, int* __restrict__ order) {
-  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int c = cell_of[i];
-  int slot = start[c] + atomicAdd(&fill[c], 1);
-  order[slot] = (int)i;
-}
-
-// canonical order inside a cell (ascending atom index) + gather of positions/types into slot order,
-// so the result does not depend on the order the atomics above happened to resolve in
-__global__ void cell_sort_gather_kernel(CellGrid cg, const int* __restrict__ start, int* __restrict__ order,
-                                        const double* __restrict__ x, const int* __restrict__ type,
-                                        double* __restrict__ xs, float* __restrict__ xs32, int* __restrict__ ts) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cg.ncell) return;
-  int lo = start[c], hi = start[c + 1];
-  for (int a = lo + 1; a < hi; a++) {
-    int v = order[a];
-    int b = a - 1;
-    while (b >= lo && order[b] > v) {
-      order[b + 1] = order[b];
-      b--;
-    }
-    order[b + 1] = v;
-  }
-  // cell-relative fp32 copy for the pair kernel's prefilter (error ~cs * 6e-8, box-size independent)
-  const double cx = (c % cg.nc[0]) * cg.cs[0], cy = ((c / cg.nc[0]) % cg.nc[1]) * cg.cs[1];
-  const double cz = (c / (cg.nc[0] * cg.nc[1])) * cg.cs[2];
-  for (int a = lo; a < hi; a++) {
-    int i = order[a];
-    const double px = x[3 * (long)i + 0], py = x[3 * (long)i + 1], pz = x[3 * (long)i + 2];
-    xs[3 * (long)a + 0] = px;
-    xs[3 * (long)a + 1] = py;
-    xs[3 * (long)a + 2] = pz;
-    xs32[3 * (long)a + 0] = (float)(px - cx);
-    xs32[3 * (long)a + 1] = (float)(py - cy);
-    xs32[3 * (long)a + 2] = (float)(pz - cz);
-    if (ts) ts[a] = type ? type[i] : 0;
-  }
-}
-
 // 1-D bias evaluation at r with update_force's sign (lib/edm_bias.cpp:297-311): returns V(r),
 // force = -dV/dr.
 __device__ __forceinline__ double pair_eval(const GridDesc& g, double r, double& force) {
@@ -167,174 +127,36 @@ __device__ __forceinline__ double pair_eval(const GridDesc& g, double r, double&
   return v;
 }
 
-// The two hill proposals of a pair (lammps/fix_edm_pair.cpp:230-236) draw their uniforms from one
-// hash: u_which = 32-bit half of pair_bits() * 2^-32 (edm_uniform_pair).  u < thresh is decided on
-// the integers: bits32 < ceil(thresh * 2^32).
-__device__ __forceinline__ void propose_hills(const PairParams& pp, unsigned long long pairkey, double r, BiasDev* st,
-                                              HillAccepted* acc) {
-  const uint64_t bits = pair_bits(pp.key, pairkey);
-#pragma unroll
-  for (int which = 0; which < 2; which++) {
-    const uint64_t half = which == 0 ? (bits >> 32) : (bits & 0xffffffffULL);
-    if (pp.accept_all || half < pp.thresh_bits) {
-      int slot = atomicAdd(&st->n_accepted, 1);
-      if (slot < pp.acc_cap) {
-        acc[slot].key = 2ULL * pairkey + which;
-        acc[slot].x[0] = r;
-        acc[slot].x[1] = 0.0;
-        acc[slot].x[2] = 0.0;
-      } else {
-        st->accepted_overflow = 1;
-      }
-    }
-  }
-}
-
-// v1: one thread per atom (slot order), half shell of 13 forward cells + own cell.
-__global__ void __launch_bounds__(128) pair_cells_kernel(GridDesc g, CellGrid cg, PairParams pp,
-                                                         const int* __restrict__ start, const int* __restrict__ order,
-                                                         const double* __restrict__ xs, const int* __restrict__ ts,
-                                                         double* __restrict__ f, double* __restrict__ partial,
-                                                         BiasDev* st, HillAccepted* acc) {
-  __shared__ double red[33];
-  double e = 0.0;
-  unsigned long long npairs = 0;
-  long stride = (long)gridDim.x * blockDim.x;
-  for (long a = (long)blockIdx.x * blockDim.x + threadIdx.x; a < pp.natoms; a += stride) {
-    const double xi = xs[3 * a + 0], yi = xs[3 * a + 1], zi = xs[3 * a + 2];
-    const int ti = pp.use_types ? ts[a] : 0;
-    if (pp.use_types && ti != pp.itype && ti != pp.jtype) continue;
-    const int oi = order[a];
-    int cx = cell_coord(xi, cg.cs[0], cg.nc[0]);
-    int cy = cell_coord(yi, cg.cs[1], cg.nc[1]);
-    int cz = cell_coord(zi, cg.cs[2], cg.nc[2]);
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (int nb = 0; nb < 14; nb++) {
-      // nb 0 = own cell; 1..13 = offsets with (dz,dy,dx) lexicographically positive
-      int t = nb + 13;  // 13..26 in the 3x3x3 enumeration, 13 = centre
-      int ox = t % 3 - 1, oy = (t / 3) % 3 - 1, oz = t / 9 - 1;
-      int qx = cx + ox, qy = cy + oy, qz = cz + oz;
-      double sx = 0.0, sy = 0.0, sz = 0.0;
-      if (qx >= cg.nc[0]) { qx -= cg.nc[0]; sx = cg.box[0]; } else if (qx < 0) { qx += cg.nc[0]; sx = -cg.box[0]; }
-      if (qy >= cg.nc[1]) { qy -= cg.nc[1]; sy = cg.box[1]; } else if (qy < 0) { qy += cg.nc[1]; sy = -cg.box[1]; }
-      if (qz >= cg.nc[2]) { qz -= cg.nc[2]; sz = cg.box[2]; } else if (qz < 0) { qz += cg.nc[2]; sz = -cg.box[2]; }
-      int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
-      long jlo = start[q], jhi = start[q + 1];
-      if (nb == 0) jlo = a + 1;
-      for (long j = jlo; j < jhi; j++) {
-        // separation exactly as the oracle forms it: (x_i - x_j) - image shift, squares summed in x,y,z order
-        double dx = __dsub_rn(__dsub_rn(xi, xs[3 * j + 0]), sx);
-        double dy = __dsub_rn(__dsub_rn(yi, xs[3 * j + 1]), sy);
-        double dz = __dsub_rn(__dsub_rn(zi, xs[3 * j + 2]), sz);
-        double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (!(d2 < pp.rc2)) continue;
-        if (pp.use_types) {
-          int tj = ts[j];
-          bool match = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
-          if (!match) continue;
-        }
-        const int oj = order[j];
-        // the pair is oriented (i = lower atom index) as in a half list sorted by (i, j)
-        double sgn = (oi < oj) ? 1.0 : -1.0;
-        double r = sqrt(d2);
-        double rinv = 1.0 / r;
-        double force;
-        e += pair_eval(g, r, force);
-        npairs++;
-        double px = dx * rinv * force, py = dy * rinv * force, pz = dz * rinv * force;
-        fx += px;
-        fy += py;
-        fz += pz;
-        atomicAdd(&f[3 * (long)oj + 0], -px);
-        atomicAdd(&f[3 * (long)oj + 1], -py);
-        atomicAdd(&f[3 * (long)oj + 2], -pz);
-        (void)sgn;
-        if (pp.do_hills) {
-          unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
-          propose_hills(pp, lo * (unsigned long long)pp.natoms + hi, r, st, acc);
-        }
-      }
-    }
-    atomicAdd(&f[3 * (long)oi + 0], fx);
-    atomicAdd(&f[3 * (long)oi + 1], fy);
-    atomicAdd(&f[3 * (long)oi + 2], fz);
-  }
-  double tot = block_sum(e, red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-  // pair count: integer, so the atomic order is irrelevant
-  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
-  if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&st->n_pairs, npairs);
-}
-
-// ---- v4: warp per home cell, fp32 prefilter, warp-level compaction ---------------------------
-//
-// Only 1 in 6.5 tested pairs lies inside the cutoff, so a thread-per-atom loop (v1 above) runs the
-// heavy per-pair path (square root, interpolation, hashing, force scatter) with ~15 % of its lanes
-// active.  Here a warp owns one home cell:
-//   * STAGE: the atoms of the own cell and of the 13 forward neighbour cells are copied, x-row by
-//     x-row (cells adjacent in x are contiguous in slot order), into shared memory as fp32
-//     coordinates relative to the corner of the 3x3x3 neighbourhood (built from the cell-relative
-//     fp32 copy the binning kernel leaves, so no image shift and no dependence on the box size);
-//   * TEST: for each home atom (warp-uniform) the lanes sweep the staged atoms 32 at a time and
-//     compare an fp32 distance against a 1e-4 enlarged cutoff (full-rate fp32); accepted (i, j)
-//     index pairs are compacted into a per-warp queue with a ballot;
-//   * HEAVY: whenever 32 pairs are queued each lane takes one: it reloads both atoms in fp64, forms
-//     the separation exactly in the oracle's operation order, applies the exact cutoff test,
-//     evaluates the bias at r, hashes the two hill proposals and scatters the forces.
-// The prefilter only decides what reaches the exact test, so results do not depend on it.
-// Home-atom forces: segmented shuffle scan over the batch (entries of one atom are contiguous),
-// the last lane of each run adds the run total to a shared-memory accumulator; neighbour-atom
-// forces leave as fp64 REDs.
-#ifndef EDM_PAIR_MINBLOCKS
-#define EDM_PAIR_MINBLOCKS 5
-#endif
-constexpr int kPairWarps = 4;
-constexpr int kJCap = 192;
-constexpr int kICap = 64;
-constexpr int kQCap = 64;
-
-struct PairWarpSmem {
-  double fi[kICap][3];
-  float jx[kJCap], jy[kJCap], jz[kJCap];
-  float ix[kICap], iy[kICap], iz[kICap];
-  int jslot[kJCap];
-  int queue[kQCap];            // (ii << 16) | jj
-  unsigned char jcode[kJCap];  // image shift code, 2 bits per dim
-};
-
-struct PairCtx {
-  GridDesc g;
-  CellGrid cg;
-  PairParams pp;
-  const int* start;
-  const int* order;
-  const double* xs;
-  const float* xs32;  // cell-relative fp32 copy of xs
-  const int* ts;
-  double* f;
-  double* partial;
-  BiasDev* st;
-  HillAccepted* acc;
-};
-
-__device__ __noinline__ double pair_eval_slow(const GridDesc& g, double r, double& force) {
-  return pair_eval(g, r, force);
+__device__ __noinline__ double2 pair_eval_slow(const GridDesc& g, double r) {
+  double force;
+  const double v = pair_eval(g, r, force);
+  return make_double2(v, force);
 }
 
 // lean 1-D evaluation for the pair path: the arithmetic of d_eval_point<1> for an interpolated
-// non-periodic grid; everything else (remap, periodic wrap) goes through the generic routine
-__device__ __forceinline__ double pair_eval_fast(const GridDesc& g, double r, double& force) {
+// non-periodic Gaussian grid with a non-periodic boundary (what fix edm_pair sets up,
+// lammps/fix_edm_pair.cpp:96-104): outside the boundary remap changes nothing and the bias is 0
+// (lib/gaussian_grid.h:128-135).  Anything else goes through the generic routine.
+__device__ __forceinline__ double pair_eval_fast(const GridDesc& g, const double* __restrict__ cellrec, bool lean,
+                                                 double r, double& force) {
+  if (!lean) {
+    const double2 vf = pair_eval_slow(g, r);
+    force = vf.y;
+    return vf.x;
+  }
   force = 0.0;
-  if (r < g.bmin[0] || r > g.bmax[0] || g.periodic[0] || !g.b_interp) return pair_eval_slow(g, r, force);
-  if (r < g.min[0] || r >= g.upper[0]) return 0.0;
+  if (r < g.bmin[0] || r > g.bmax[0] || r < g.min[0] || r >= g.upper[0]) return 0.0;
   const double t = __dsub_rn(r, g.min[0]);
   int idx = (int)(t * g.inv_dx[0]);  // a one-off at a cell edge is harmless: the interpolant is C1 there
   const int hi = g.n[0] - 2;
   idx = idx < 0 ? 0 : (idx > hi ? hi : idx);
   const double where = __dsub_rn(t, __dmul_rn((double)idx, g.dx[0]));
   const double X = where * g.inv_dx[0];
-  const double2 r0 = *reinterpret_cast<const double2*>(g.rec + (long)idx * 2);
-  const double2 r1 = *reinterpret_cast<const double2*>(g.rec + (long)idx * 2 + 2);
+  // both corners of the cell in one aligned 32 B record: one sector, one 256-bit load
+  double2 r0, r1;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+      : "=d"(r0.x), "=d"(r0.y), "=d"(r1.x), "=d"(r1.y)
+      : "l"(cellrec + (long)idx * 4));
   const double Y = fabs(X - 1.0);
   const double X2 = X * X, X3 = X2 * X, Y2 = Y * Y, Y3 = Y2 * Y;
   const double td0 = !(fabs(r0.x) < kInterpZero) ? r0.y : 0.0;
@@ -372,487 +194,577 @@ __device__ __forceinline__ void propose_hills_d2(const PairParams& pp, unsigned 
   }
 }
 
-__device__ __noinline__ void pair_heavy_batch(const PairCtx& c, PairWarpSmem& w, int first, int count, int ilo,
-                                              double& e, unsigned long long& npairs) {
+// Atoms in cell order ("slots"): one 32 B record per atom, one aligned sector per gather.
+struct __align__(32) AtomRec {
+  double x, y, z;
+  long long tag;  // original atom index; staged copies add the image-shift code in bits 32..37
+};
+
+// slot = start[cell] + (count[cell]-- - 1): reuses the histogram as the fill counter
+__global__ void cell_fill_kernel(long n, const int* __restrict__ cell_of, const int* __restrict__ start,
+                                 int* __restrict__ count, int* __restrict__ order) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cell_of[i];
+  int slot = start[c] + atomicSub(&count[c], 1) - 1;
+  order[slot] = (int)i;
+}
+
+// Canonical order inside a cell (ascending atom index, so the slot order does not depend on how the
+// atomics above resolved) + gather into slot order.  One thread per atom: its rank is the number of
+// cell mates with a smaller index.  xs32 = position relative to the cell corner in fp32 (error
+// ~cs * 6e-8, box-size independent) with the type in .w, for the search prefilter.
+__global__ void cell_rank_gather_kernel(long n, CellGrid cg, const int* __restrict__ cell_of,
+                                        const int* __restrict__ start, const int* __restrict__ order,
+                                        const double* __restrict__ x, const int* __restrict__ type,
+                                        AtomRec* __restrict__ arec, float4* __restrict__ xs32) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cell_of[i];
+  const int lo = start[c], hi = start[c + 1];
+  int rank = 0;
+  for (int a = lo; a < hi; a++) rank += (order[a] < (int)i);
+  const long s = lo + rank;
+  const double px = x[3 * i + 0], py = x[3 * i + 1], pz = x[3 * i + 2];
+  const double cx = (c % cg.nc[0]) * cg.cs[0], cy = ((c / cg.nc[0]) % cg.nc[1]) * cg.cs[1];
+  const double cz = (c / (cg.nc[0] * cg.nc[1])) * cg.cs[2];
+  AtomRec r;
+  r.x = px;
+  r.y = py;
+  r.z = pz;
+  r.tag = (long long)i;
+  arec[s] = r;
+  xs32[s] = make_float4((float)(px - cx), (float)(py - cy), (float)(pz - cz), __int_as_float(type ? type[i] : 0));
+}
+
+struct PairCtx {
+  GridDesc g;
+  CellGrid cg;
+  PairParams pp;
+  const int* start;
+  const AtomRec* arec;
+  const float4* xs32;
+  double* f;
+  BiasDev* st;
+  HillAccepted* acc;
+  int* fallback;  // set by the block search when a region does not fit: the direct search takes the step
+  const double* cellrec;                // per grid cell {V_k, V'_k, V_k+1, V'_k+1}, 32 B aligned (pair_prep_kernel)
+  const unsigned long long* fmax_bits;  // bit pattern of a bound on |dV/dr| over the grid
+};
+
+// Per step: the 1-D bias grid regrouped by cell, so the interpolation's two corners are one aligned
+// 32 B gather, and a bound on |dV/dr|: inside a cell the Hermite derivative is
+// dV/dx * 6X(1-X) + V'_k (1-4X+3X^2) + V'_k+1 (3X^2-2X), at most 1.5 |dV|/dx + max(|V'_k|, |V'_k+1|).
+// The bound scales the fixed-point force accumulators of block_eval_kernel.
+__global__ void __launch_bounds__(256) pair_prep_kernel(GridDesc g, double* __restrict__ cellrec,
+                                                        unsigned long long* fmax_bits) {
+  const int n = g.n[0];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  double bound = 0.0;
+  if (k < n) {
+    const int k1 = (k + 1 < n) ? k + 1 : (g.periodic[0] ? 0 : k);
+    const double v0 = g.rec[2 * (long)k], d0 = g.rec[2 * (long)k + 1];
+    const double v1 = g.rec[2 * (long)k1], d1 = g.rec[2 * (long)k1 + 1];
+    if (k + 1 < n) {
+      cellrec[4 * (long)k + 0] = v0;
+      cellrec[4 * (long)k + 1] = d0;
+      cellrec[4 * (long)k + 2] = v1;
+      cellrec[4 * (long)k + 3] = d1;
+    }
+    bound = 1.5 * fabs(v1 - v0) * g.inv_dx[0] + fmax(fabs(d0), fabs(d1));
+  }
+  for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_down_sync(0xffffffffu, bound, o));
+  // non-negative doubles order like their bit patterns
+  if ((threadIdx.x & 31) == 0 && bound > 0.0) atomicMax(fmax_bits, (unsigned long long)__double_as_longlong(bound));
+}
+
+__device__ __forceinline__ double shift_of(int code, int d, const CellGrid& cg) {
+  return (code & (1 << (2 * d))) ? cg.box[d] : ((code & (2 << (2 * d))) ? -cg.box[d] : 0.0);
+}
+
+// One candidate pair, exactly: separation as the oracle forms it ((x_i - x_j) - image shift, squares
+// summed in x, y, z order), exact cutoff, bias at r, two hill proposals.  Returns false when the
+// pair is outside the cutoff; p = force on i (the force on j is -p).
+__device__ __forceinline__ bool pair_exact(const PairCtx& c, const AtomRec& ri, const AtomRec& rj, int code, double& e,
+                                           double& px, double& py, double& pz) {
+  const double dx = __dsub_rn(__dsub_rn(ri.x, rj.x), shift_of(code, 0, c.cg));
+  const double dy = __dsub_rn(__dsub_rn(ri.y, rj.y), shift_of(code, 1, c.cg));
+  const double dz = __dsub_rn(__dsub_rn(ri.z, rj.z), shift_of(code, 2, c.cg));
+  const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  if (!(d2 < c.pp.rc2)) return false;
+  const double rinv = rsqrt(d2);
+  const double r = d2 * rinv;  // within 2 ulp of sqrt(d2): enough for V(r); hills take the exact root
+  double force;
+  e += pair_eval_fast(c.g, c.cellrec, c.pp.lean != 0, r, force);
+  const double s = rinv * force;
+  px = dx * s;
+  py = dy * s;
+  pz = dz * s;
+  if (c.pp.do_hills) {
+    const unsigned long long oi = (unsigned long long)(ri.tag & 0xffffffffLL), oj = (unsigned long long)(rj.tag & 0xffffffffLL);
+    const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
+    propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
+  }
+  return true;
+}
+
+// Segmented inclusive scan over runs of equal keys (contiguous lanes); afterwards the last lane of
+// each run holds the run total.  Returns true on those lanes.
+template <typename T> __device__ __forceinline__ bool run_totals(int key, T& px, T& py, T& pz) {
   const int lane = threadIdx.x & 31;
-  bool on = lane < count;
-  int ii = -1;
-  double px = 0.0, py = 0.0, pz = 0.0;
-  if (on) {
-    const int q = w.queue[first + lane];
-    ii = q >> 16;
-    const int jj = q & 0xffff;
-    const long si = ilo + ii, sj = w.jslot[jj];
-    const int code = w.jcode[jj];
-    const double sx = (code & 1) ? c.cg.box[0] : ((code & 2) ? -c.cg.box[0] : 0.0);
-    const double sy = (code & 4) ? c.cg.box[1] : ((code & 8) ? -c.cg.box[1] : 0.0);
-    const double sz = (code & 16) ? c.cg.box[2] : ((code & 32) ? -c.cg.box[2] : 0.0);
-    // exactly the oracle's separation: (x_i - x_j) - image shift, squares summed in x, y, z order
-    const double dx = __dsub_rn(__dsub_rn(c.xs[3 * si + 0], c.xs[3 * sj + 0]), sx);
-    const double dy = __dsub_rn(__dsub_rn(c.xs[3 * si + 1], c.xs[3 * sj + 1]), sy);
-    const double dz = __dsub_rn(__dsub_rn(c.xs[3 * si + 2], c.xs[3 * sj + 2]), sz);
-    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    on = d2 < c.pp.rc2;
-    if (on) {
-      const int oi = c.order[si], oj = c.order[sj];
-      const double rinv = rsqrt(d2);
-      const double r = d2 * rinv;  // within 2 ulp of sqrt(d2): enough for V(r); hills take the exact root
-      double force = 1.0;
-      if (!(c.pp.dbg & 2)) e += pair_eval_fast(c.g, r, force);
-      npairs++;
-      const double s = rinv * force;
-      px = dx * s;
-      py = dy * s;
-      pz = dz * s;
-      if (c.pp.do_hills && !(c.pp.dbg & 4)) {
-        const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
-        propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
-      }
-      if (!(c.pp.dbg & 1)) {
-      atomicAdd(&c.f[3 * (long)oj + 0], -px);
-      atomicAdd(&c.f[3 * (long)oj + 1], -py);
-      atomicAdd(&c.f[3 * (long)oj + 2], -pz);
-      }
-    }
-  }
-  if (c.pp.dbg & 16) {
-    if (on) {
-      const long o = 3 * (long)c.order[ilo + ii];
-      atomicAdd(&c.f[o + 0], px);
-      atomicAdd(&c.f[o + 1], py);
-      atomicAdd(&c.f[o + 2], pz);
-    }
-    return;
-  }
-  // home-atom side: inclusive segmented scan over runs of equal ii (contiguous in the queue)
+  const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  int head = (lane == 0 || kprev != key) ? 1 : 0;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int iu = __shfl_up_sync(0xffffffffu, ii, o);
-    const double ux = __shfl_up_sync(0xffffffffu, px, o);
-    const double uy = __shfl_up_sync(0xffffffffu, py, o);
-    const double uz = __shfl_up_sync(0xffffffffu, pz, o);
-    if (lane >= o && iu == ii) {
+    const int uh = __shfl_up_sync(0xffffffffu, head, o);
+    const T ux = __shfl_up_sync(0xffffffffu, px, o);
+    const T uy = __shfl_up_sync(0xffffffffu, py, o);
+    const T uz = __shfl_up_sync(0xffffffffu, pz, o);
+    if (lane >= o && !head) {
       px += ux;
       py += uy;
       pz += uz;
+      head = uh;
     }
   }
-  const int inext = __shfl_down_sync(0xffffffffu, ii, 1);
-  if (ii >= 0 && (lane == 31 || inext != ii)) {
-    w.fi[ii][0] += px;
-    w.fi[ii][1] += py;
-    w.fi[ii][2] += pz;
-  }
-  __syncwarp();
+  const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+  return key >= 0 && (lane == 31 || knext != key);
 }
 
-__global__ void __launch_bounds__(kPairWarps * 32, EDM_PAIR_MINBLOCKS) pair_cells_v4_kernel(const __grid_constant__ PairCtx c) {
-  __shared__ PairWarpSmem wsm[kPairWarps];
+// ---- direct search: the last resort -----------------------------------------------------------------
+//
+// One thread per home atom, half shell of 13 forward cells + own cell straight from global memory,
+// pair_exact on every pair inside the fp32 prefilter, all forces as fp64 REDs.  No capacity of any
+// kind, so it takes the step whatever the density looks like; it runs (returns at once otherwise)
+// only when the block search below gave up, and is several times slower than it.
+__global__ void __launch_bounds__(128) pair_direct_kernel(const __grid_constant__ PairCtx c,
+                                                          double* __restrict__ partial) {
   __shared__ double red[33];
-  PairWarpSmem& w = wsm[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * kPairWarps;
+  if (*c.fallback == 0) {
+    if (threadIdx.x == 0) partial[blockIdx.x] = 0.0;
+    return;
+  }
   const CellGrid& cg = c.cg;
   const PairParams& pp = c.pp;
   double e = 0.0;
   unsigned long long npairs = 0;
-  const float rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;  // prefilter radius; the fp32 error is ~1e-6 relative
-  const float csx = (float)cg.cs[0], csy = (float)cg.cs[1], csz = (float)cg.cs[2];
-
-  for (int cell = gw; cell < cg.ncell; cell += nwarps) {
-    const int clo = c.start[cell], chi = c.start[cell + 1];
-    if (clo == chi) continue;
-    const int cx = cell % cg.nc[0], cy = (cell / cg.nc[0]) % cg.nc[1], cz = cell / (cg.nc[0] * cg.nc[1]);
-    for (int ilo = clo; ilo < chi; ilo += kICap) {
-      const int ni = min(kICap, chi - ilo);
-      for (int a = lane; a < ni; a += 32) {
-        w.ix[a] = c.xs32[3 * (long)(ilo + a) + 0] + csx;
-        w.iy[a] = c.xs32[3 * (long)(ilo + a) + 1] + csy;
-        w.iz[a] = c.xs32[3 * (long)(ilo + a) + 2] + csz;
-        w.fi[a][0] = 0.0;
-        w.fi[a][1] = 0.0;
-        w.fi[a][2] = 0.0;
-      }
-      int nj = 0, nq = 0;
-      // own-cell atoms are always staged at the head of the list: entries [0, self_hi) hold slots
-      // self_slot0, self_slot0 + 1, ...; of those only partners with a larger slot than i count
-      int self_hi = 0, self_slot0 = 0;
-      __syncwarp();
-
-      // TEST (+ HEAVY on full batches) over the staged list; drains the queue at the end because
-      // queue entries index the staged list
-      auto run_tests = [&]() {
-        __syncwarp();
-        for (int ii = 0; ii < ni; ii++) {
-          const int si = ilo + ii;
-          int ti = 0;
-          if (pp.use_types) {
-            ti = c.ts[si];
-            if (ti != pp.itype && ti != pp.jtype) continue;
-          }
-          const float xi = w.ix[ii], yi = w.iy[ii], zi = w.iz[ii];
-          const int selfcut = si - self_slot0;
-          // four staged atoms per lane and trip: independent fp32 chains hide the LDS latency and
-          // the loop/queue bookkeeping is paid once per 128 tests
-          for (int jb = 0; jb < nj; jb += 128) {
-            bool take[4];
-            int jjs[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int jj = jb + 32 * u + lane;
-              jjs[u] = jj;
-              take[u] = false;
-              if (jj < nj) {
-                const float dx = xi - w.jx[jj], dy = yi - w.jy[jj], dz = zi - w.jz[jj];
-                const float d2 = dx * dx + dy * dy + dz * dz;
-                take[u] = (d2 < rc2m) && (jj >= self_hi || jj > selfcut);
-                if (take[u] && pp.use_types) {
-                  const int tj = c.ts[w.jslot[jj]];
-                  take[u] = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const unsigned m = __ballot_sync(0xffffffffu, take[u]);
-              if (m == 0u) continue;
-              if (take[u]) w.queue[nq + __popc(m & ((1u << lane) - 1u))] = (ii << 16) | jjs[u];
-              nq += __popc(m);
-              if (nq >= 32) {
-                __syncwarp();
-                nq -= 32;
-                if (!(pp.dbg & 8)) pair_heavy_batch(c, w, nq, 32, ilo, e, npairs);
-              }
-            }
-          }
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long a = (long)blockIdx.x * blockDim.x + threadIdx.x; a < pp.natoms; a += stride) {
+    const AtomRec ri = c.arec[a];
+    const int ti = __float_as_int(c.xs32[a].w);
+    if (pp.use_types && ti != pp.itype && ti != pp.jtype) continue;
+    const int cx = cell_coord(ri.x, cg.cs[0], cg.nc[0]);
+    const int cy = cell_coord(ri.y, cg.cs[1], cg.nc[1]);
+    const int cz = cell_coord(ri.z, cg.cs[2], cg.nc[2]);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for (int nb = 0; nb < 14; nb++) {
+      // nb 0 = own cell; 1..13 = offsets with (dz,dy,dx) lexicographically positive
+      const int t = nb + 13;  // 13..26 in the 3x3x3 enumeration, 13 = centre
+      int qx = cx + t % 3 - 1, qy = cy + (t / 3) % 3 - 1, qz = cz + t / 9 - 1, code = 0;
+      if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
+      if (qy >= cg.nc[1]) { qy -= cg.nc[1]; code |= 4; } else if (qy < 0) { qy += cg.nc[1]; code |= 8; }
+      if (qz >= cg.nc[2]) { qz -= cg.nc[2]; code |= 16; } else if (qz < 0) { qz += cg.nc[2]; code |= 32; }
+      const int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
+      long jlo = c.start[q];
+      const long jhi = c.start[q + 1];
+      if (nb == 0) jlo = a + 1;
+      for (long j = jlo; j < jhi; j++) {
+        if (pp.use_types) {
+          const int tj = __float_as_int(c.xs32[j].w);
+          if ((ti == pp.itype) ? (tj != pp.jtype) : (tj != pp.itype)) continue;
         }
-        __syncwarp();
-        if (nq && !(pp.dbg & 8)) pair_heavy_batch(c, w, 0, nq, ilo, e, npairs);
-        nq = 0;
-      };
-
-      // half shell as 5 x-rows: (oy,oz) = (0,0) with ox = 0..1 (own cell first), then
-      // (1,0), (-1,1), (0,1), (1,1) with ox = -1..1
-      for (int row = 0; row < 5; row++) {
-        const int oy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3);
-        const int oz = (row < 2) ? 0 : 1;
-        const int ox0 = (row == 0) ? 0 : -1;
-        int qy = cy + oy, qz = cz + oz, ycode = 0;
-        if (qy >= cg.nc[1]) { qy -= cg.nc[1]; ycode |= 4; } else if (qy < 0) { qy += cg.nc[1]; ycode |= 8; }
-        if (qz >= cg.nc[2]) { qz -= cg.nc[2]; ycode |= 16; } else if (qz < 0) { qz += cg.nc[2]; ycode |= 32; }
-        const float offy = (float)(oy + 1) * csy, offz = (float)(oz + 1) * csz;
-        const int rowbase = (qz * cg.nc[1] + qy) * cg.nc[0];
-        for (int ox = ox0; ox <= 1; ox++) {
-          int qx = cx + ox, code = ycode;
-          if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
-          // merge the following cells of the row while they stay contiguous (no wrap in between)
-          int ncell = 1;
-          while (ox + ncell <= 1 && qx + ncell < cg.nc[0] && !(code & 2)) ncell++;
-          if ((code & 2)) ncell = 1;  // the wrapped-low cell stands alone; the rest restarts at qx = 0
-          const int q0 = rowbase + qx;
-          const int b0 = c.start[q0];
-          const int b1 = c.start[q0 + 1];
-          const int b2 = (ncell > 1) ? c.start[q0 + 2] : b1;
-          const int b3 = (ncell > 2) ? c.start[q0 + 3] : b2;
-          const float offx0 = (float)(ox + 1) * csx;
-          const bool own = (row == 0 && ox == 0);
-          int lo = b0;
-          const int hi = b3;
-          while (lo < hi) {
-            if (nj == kJCap) {
-              run_tests();
-              nj = 0;
-              self_hi = 0;
-              __syncwarp();
-            }
-            const int takeN = min(kJCap - nj, hi - lo);
-            if (own && lo < b1) {  // nj == 0 here: the own cell opens the list, also after a refill
-              self_slot0 = lo;
-              self_hi = min(takeN, b1 - lo);
-            }
-            for (int a = lane; a < takeN; a += 32) {
-              const int sl = lo + a;
-              const float offx = offx0 + (float)((sl >= b1) + (sl >= b2)) * csx;
-              w.jx[nj + a] = c.xs32[3 * (long)sl + 0] + offx;
-              w.jy[nj + a] = c.xs32[3 * (long)sl + 1] + offy;
-              w.jz[nj + a] = c.xs32[3 * (long)sl + 2] + offz;
-              w.jslot[nj + a] = sl;
-              w.jcode[nj + a] = (unsigned char)code;
-            }
-            nj += takeN;
-            lo += takeN;
-          }
-          ox += ncell - 1;
-        }
+        const AtomRec rj = c.arec[j];
+        double px, py, pz;
+        if (!pair_exact(c, ri, rj, code, e, px, py, pz)) continue;
+        npairs++;
+        fx += px;
+        fy += py;
+        fz += pz;
+        atomicAdd(&c.f[3 * rj.tag + 0], -px);
+        atomicAdd(&c.f[3 * rj.tag + 1], -py);
+        atomicAdd(&c.f[3 * rj.tag + 2], -pz);
       }
-      if (nj) run_tests();
-      __syncwarp();
-      for (int a = lane; a < ni; a += 32) {
-        const long o = 3 * (long)c.order[ilo + a];
-        atomicAdd(&c.f[o + 0], w.fi[a][0]);
-        atomicAdd(&c.f[o + 1], w.fi[a][1]);
-        atomicAdd(&c.f[o + 2], w.fi[a][2]);
-      }
-      __syncwarp();
     }
+    atomicAdd(&c.f[3 * ri.tag + 0], fx);
+    atomicAdd(&c.f[3 * ri.tag + 1], fy);
+    atomicAdd(&c.f[3 * ri.tag + 2], fz);
   }
   double tot = block_sum(e, red);
-  if (threadIdx.x == 0) c.partial[blockIdx.x] = tot;
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
   for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
-  if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
+  if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
 }
 
-// ---- v5: the same search split in two kernels -------------------------------------------------
-//
-// pair_find_kernel   STAGE + TEST of v4; instead of a shared-memory queue feeding an in-kernel heavy
-//                    path it appends the candidate pairs (slot_i, slot_j | shift code) to a global
-//                    list, in chunks a warp allocates with one atomic per 256 candidates.
-// pair_eval_kernel   one lane per candidate, fully populated warps, no shared memory: exact fp64
-//                    separation + cutoff, bias at r, hill proposals, force scatter.  Candidates of a
-//                    home atom are contiguous in a chunk, so the home side is a segmented shuffle scan
-//                    with one RED triple per run; the neighbour side is one RED triple per pair.
-// Splitting lets each kernel run at its own occupancy (the search needs shared memory and few
-// registers, the evaluation the opposite) at the price of 8 B written + read per candidate.
 constexpr int kChunk = 256;
 
-struct FindWarpSmem {
-  float jx[kJCap], jy[kJCap], jz[kJCap];
-  float ix[kICap], iy[kICap], iz[kICap];
-  int jpack[kJCap];  // slot | code << 26
+// ---- block search: a CTA owns a brick of home cells ---------------------------------------------
+//
+// A pair evaluation that gathers both atoms from global memory and returns both forces as REDs is
+// bound by scattered traffic, not arithmetic: per pair two position gathers, a 32 B grid gather and
+// three fp64 REDs, all through L1/L2 (ncu on the previous list-based kernel: L1 84 %, L2 68 % busy,
+// 84 M RED requests per step).  Here a CTA owns a brick of bd[0] x bd[1] x bd[2] home
+// cells and keeps everything those cells touch — the brick plus its forward half-shell halo, the
+// REGION — in shared memory:
+//   block_find_kernel  region positions as fp32 relative to the region corner.  A warp takes a home
+//                      cell: each lane keeps up to 6 partner atoms in registers (the 14 neighbour
+//                      cells are 5 contiguous runs of region indices), then for each home atom one
+//                      broadcast LDS.128 and 6 distance tests per lane.  Accepted pairs go out as
+//                      4 B items (li << 16 | lj, region indices) into chunks inside the block's own
+//                      slice of the candidate buffer.
+//   block_eval_kernel  region atoms as fp64 records + fp64 force accumulators in shared memory.
+//                      One lane per candidate: both atoms from shared memory, pair_exact, partner
+//                      force into the accumulator (shared-memory CAS add), home force through the
+//                      segmented scan; one RED triple per region atom when the block is done —
+//                      about 0.4 REDs per pair instead of 3.3.
+// Both kernels number the region atoms the same way (region cells x fastest, slot order inside a
+// cell), from the same start[] array.
+constexpr int kBlkCap = 1920;    // region atoms: 56 B each in block_eval_kernel -> two CTAs per SM
+constexpr int kRegCells = 256;   // region cells
+constexpr int kFindThreads = 256;
+constexpr int kEvalThreads = 512;
+constexpr unsigned kPad = 0xffffffffu;
+
+struct BlockGeom {
+  int bd[3];       // home cells per brick side
+  int nb[3];       // bricks per dimension
+  unsigned capb;   // candidate items per brick (multiple of kChunk)
 };
 
-struct CandList {
-  int2* items;                  // x = slot_i (-1: padding), y = slot_j | code << 26
-  unsigned long long cap;       // entries
-  unsigned long long* count;    // entries allocated so far (multiple of kChunk)
-  int* overflow;
+struct Region {
+  int cstart[kRegCells + 1];  // region index of the first atom of each region cell
+  int cslot[kRegCells];       // its slot
+  unsigned char ccode[kRegCells];
+  int hn[3], rd[3];           // home cells / region cells per side of this brick
+  int nrc, nreg;
 };
 
-__global__ void __launch_bounds__(kPairWarps * 32, 8) pair_find_kernel(const __grid_constant__ PairCtx c, CandList cl) {
-  __shared__ FindWarpSmem wsm[kPairWarps];
-  FindWarpSmem& w = wsm[threadIdx.x >> 5];
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * kPairWarps;
-  const CellGrid& cg = c.cg;
-  const PairParams& pp = c.pp;
-  const float rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;
-  const float csx = (float)cg.cs[0], csy = (float)cg.cs[1], csz = (float)cg.cs[2];
-  long long chunk_base = -1;  // -1: candidates are dropped (list full)
-  int used = kChunk;          // forces an allocation on first use
-
-  for (int cell = gw; cell < cg.ncell; cell += nwarps) {
-    const int clo = c.start[cell], chi = c.start[cell + 1];
-    if (clo == chi) continue;
-    const int cx = cell % cg.nc[0], cy = (cell / cg.nc[0]) % cg.nc[1], cz = cell / (cg.nc[0] * cg.nc[1]);
-    for (int ilo = clo; ilo < chi; ilo += kICap) {
-      const int ni = min(kICap, chi - ilo);
-      for (int a = lane; a < ni; a += 32) {
-        w.ix[a] = c.xs32[3 * (long)(ilo + a) + 0] + csx;
-        w.iy[a] = c.xs32[3 * (long)(ilo + a) + 1] + csy;
-        w.iz[a] = c.xs32[3 * (long)(ilo + a) + 2] + csz;
-      }
-      int nj = 0;
-      int self_hi = 0, self_slot0 = 0;
-      __syncwarp();
-
-      auto run_tests = [&]() {
-        __syncwarp();
-        for (int ii = 0; ii < ni; ii++) {
-          const int si = ilo + ii;
-          int ti = 0;
-          if (pp.use_types) {
-            ti = c.ts[si];
-            if (ti != pp.itype && ti != pp.jtype) continue;
-          }
-          const float xi = w.ix[ii], yi = w.iy[ii], zi = w.iz[ii];
-          const int selfcut = si - self_slot0;
-          for (int jb = 0; jb < nj; jb += 128) {
-            bool take[4];
-            int pk[4];
+// false (for the whole CTA) when the region holds more than kBlkCap atoms
+__device__ __forceinline__ bool region_setup(const CellGrid& cg, const BlockGeom& bg, const int* __restrict__ start,
+                                             Region& R) {
+  int b = blockIdx.x;
+  const int bx = b % bg.nb[0];
+  b /= bg.nb[0];
+  const int by = b % bg.nb[1], bz = b / bg.nb[1];
+  const int h0[3] = {bx * bg.bd[0], by * bg.bd[1], bz * bg.bd[2]};
+  int hn[3], rd[3];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const int jj = jb + 32 * u + lane;
-              take[u] = false;
-              pk[u] = 0;
-              if (jj < nj) {
-                const float dx = xi - w.jx[jj], dy = yi - w.jy[jj], dz = zi - w.jz[jj];
-                const float d2 = dx * dx + dy * dy + dz * dz;
-                take[u] = (d2 < rc2m) && (jj >= self_hi || jj > selfcut);
-                pk[u] = w.jpack[jj];
-                if (take[u] && pp.use_types) {
-                  const int tj = c.ts[pk[u] & 0x3ffffff];
-                  take[u] = (ti == pp.itype) ? (tj == pp.jtype) : (tj == pp.itype);
-                }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              const unsigned m = __ballot_sync(0xffffffffu, take[u]);
-              if (m == 0u) continue;
-              const int k = __popc(m);
-              if (used + k > kChunk) {  // close the chunk with padding and take a new one
-                if (chunk_base >= 0)
-                  for (int a = used + lane; a < kChunk; a += 32) cl.items[chunk_base + a] = make_int2(-1, 0);
-                unsigned long long nb = 0;
-                if (lane == 0) nb = atomicAdd(cl.count, (unsigned long long)kChunk);
-                nb = __shfl_sync(0xffffffffu, nb, 0);
-                if (nb + kChunk > cl.cap) {
-                  chunk_base = -1;
-                  if (lane == 0) *cl.overflow = 1;
-                } else {
-                  chunk_base = (long long)nb;
-                }
-                used = 0;
-              }
-              if (take[u] && chunk_base >= 0)
-                cl.items[chunk_base + used + __popc(m & ((1u << lane) - 1u))] = make_int2(si, pk[u]);
-              used += k;
-            }
-          }
-        }
-      };
-
-      for (int row = 0; row < 5; row++) {
-        const int oy = (row == 0) ? 0 : (row == 1 ? 1 : row - 3);
-        const int oz = (row < 2) ? 0 : 1;
-        const int ox0 = (row == 0) ? 0 : -1;
-        int qy = cy + oy, qz = cz + oz, ycode = 0;
-        if (qy >= cg.nc[1]) { qy -= cg.nc[1]; ycode |= 4; } else if (qy < 0) { qy += cg.nc[1]; ycode |= 8; }
-        if (qz >= cg.nc[2]) { qz -= cg.nc[2]; ycode |= 16; } else if (qz < 0) { qz += cg.nc[2]; ycode |= 32; }
-        const float offy = (float)(oy + 1) * csy, offz = (float)(oz + 1) * csz;
-        const int rowbase = (qz * cg.nc[1] + qy) * cg.nc[0];
-        for (int ox = ox0; ox <= 1; ox++) {
-          int qx = cx + ox, code = ycode;
-          if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
-          int ncell = 1;
-          while (ox + ncell <= 1 && qx + ncell < cg.nc[0] && !(code & 2)) ncell++;
-          if ((code & 2)) ncell = 1;
-          const int q0 = rowbase + qx;
-          const int b0 = c.start[q0];
-          const int b1 = c.start[q0 + 1];
-          const int b2 = (ncell > 1) ? c.start[q0 + 2] : b1;
-          const int b3 = (ncell > 2) ? c.start[q0 + 3] : b2;
-          const float offx0 = (float)(ox + 1) * csx;
-          const bool own = (row == 0 && ox == 0);
-          int lo = b0;
-          const int hi = b3;
-          while (lo < hi) {
-            if (nj == kJCap) {
-              run_tests();
-              nj = 0;
-              self_hi = 0;
-              __syncwarp();
-            }
-            const int takeN = min(kJCap - nj, hi - lo);
-            if (own && lo < b1) {
-              self_slot0 = lo;
-              self_hi = min(takeN, b1 - lo);
-            }
-            for (int a = lane; a < takeN; a += 32) {
-              const int sl = lo + a;
-              const float offx = offx0 + (float)((sl >= b1) + (sl >= b2)) * csx;
-              w.jx[nj + a] = c.xs32[3 * (long)sl + 0] + offx;
-              w.jy[nj + a] = c.xs32[3 * (long)sl + 1] + offy;
-              w.jz[nj + a] = c.xs32[3 * (long)sl + 2] + offz;
-              w.jpack[nj + a] = sl | (code << 26);
-            }
-            nj += takeN;
-            lo += takeN;
-          }
-          ox += ncell - 1;
-        }
-      }
-      if (nj) run_tests();
-      __syncwarp();
-    }
+  for (int d = 0; d < 3; d++) {
+    hn[d] = min(bg.bd[d], cg.nc[d] - h0[d]);
+    rd[d] = hn[d] + (d < 2 ? 2 : 1);
   }
-  if (chunk_base >= 0)
-    for (int a = used + lane; a < kChunk; a += 32) cl.items[chunk_base + a] = make_int2(-1, 0);
-}
-
-__global__ void __launch_bounds__(256) pair_eval_kernel(const __grid_constant__ PairCtx c, CandList cl) {
-  __shared__ double red[33];
-  const int lane = threadIdx.x & 31;
-  unsigned long long total = *cl.count;
-  if (total > cl.cap) total = cl.cap - cl.cap % kChunk;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  double e = 0.0;
-  unsigned long long npairs = 0;
-  for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total;
-       base += stride) {
-    const int2 it = cl.items[base + lane];  // total is a multiple of 32
-    int si = it.x;
-    int oi = -1;
-    bool on = si >= 0;
-    double px = 0.0, py = 0.0, pz = 0.0;
-    if (on) {
-      const long sj = it.y & 0x3ffffff;
-      const int code = (int)((unsigned)it.y >> 26);
-      const double sx = (code & 1) ? c.cg.box[0] : ((code & 2) ? -c.cg.box[0] : 0.0);
-      const double sy = (code & 4) ? c.cg.box[1] : ((code & 8) ? -c.cg.box[1] : 0.0);
-      const double sz = (code & 16) ? c.cg.box[2] : ((code & 32) ? -c.cg.box[2] : 0.0);
-      // exactly the oracle's separation: (x_i - x_j) - image shift, squares summed in x, y, z order
-      const double dx = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 0], c.xs[3 * sj + 0]), sx);
-      const double dy = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 1], c.xs[3 * sj + 1]), sy);
-      const double dz = __dsub_rn(__dsub_rn(c.xs[3 * (long)si + 2], c.xs[3 * sj + 2]), sz);
-      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      on = d2 < c.pp.rc2;
-      oi = c.order[si];
-      if (on) {
-        const int oj = c.order[sj];
-        const double rinv = rsqrt(d2);
-        const double r = d2 * rinv;
-        double force;
-        e += pair_eval_fast(c.g, r, force);
-        npairs++;
-        const double s = rinv * force;
-        px = dx * s;
-        py = dy * s;
-        pz = dz * s;
-        if (c.pp.do_hills) {
-          const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
-          propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
-        }
-        atomicAdd(&c.f[3 * (long)oj + 0], -px);
-        atomicAdd(&c.f[3 * (long)oj + 1], -py);
-        atomicAdd(&c.f[3 * (long)oj + 2], -pz);
-      }
+  const int nrc = rd[0] * rd[1] * rd[2];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      R.hn[d] = hn[d];
+      R.rd[d] = rd[d];
     }
-    // home side: segmented inclusive scan (head flags: a slot_i may reappear later in the list when a
-    // neighbourhood was staged in two parts), one RED triple per run
-    const int iprev = __shfl_up_sync(0xffffffffu, si, 1);
-    int head = (lane == 0 || iprev != si) ? 1 : 0;
+    R.nrc = nrc;
+  }
+  for (int rc = threadIdx.x; rc < nrc; rc += blockDim.x) {
+    const int rx = rc % rd[0], ry = (rc / rd[0]) % rd[1], rz = rc / (rd[0] * rd[1]);
+    int qx = h0[0] - 1 + rx, qy = h0[1] - 1 + ry, qz = h0[2] + rz, code = 0;
+    if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
+    if (qy >= cg.nc[1]) { qy -= cg.nc[1]; code |= 4; } else if (qy < 0) { qy += cg.nc[1]; code |= 8; }
+    if (qz >= cg.nc[2]) { qz -= cg.nc[2]; code |= 16; }
+    const int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
+    const int s0 = start[q];
+    R.cslot[rc] = s0;
+    R.cstart[rc] = start[q + 1] - s0;  // count for now
+    R.ccode[rc] = (unsigned char)code;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // exclusive scan of up to 256 counts, 8 per lane
+    const int lane = threadIdx.x, base = lane * 8;
+    int v[8], s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      v[k] = (base + k < nrc) ? R.cstart[base + k] : 0;
+      s += v[k];
+    }
+    int incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int uh = __shfl_up_sync(0xffffffffu, head, o);
-      const double ux = __shfl_up_sync(0xffffffffu, px, o);
-      const double uy = __shfl_up_sync(0xffffffffu, py, o);
-      const double uz = __shfl_up_sync(0xffffffffu, pz, o);
-      if (lane >= o && !head) {
-        px += ux;
-        py += uy;
-        pz += uz;
-        head = uh;
-      }
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
     }
-    const int inext = __shfl_down_sync(0xffffffffu, si, 1);
-    if (si >= 0 && (lane == 31 || inext != si)) {
-      atomicAdd(&c.f[3 * (long)oi + 0], px);
-      atomicAdd(&c.f[3 * (long)oi + 1], py);
-      atomicAdd(&c.f[3 * (long)oi + 2], pz);
+    __syncwarp();
+    int run = incl - s;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (base + k < nrc) R.cstart[base + k] = run;
+      run += v[k];
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) {
+      R.cstart[nrc] = total;
+      R.nreg = total;
     }
   }
-  double tot = block_sum(e, red);
-  if (threadIdx.x == 0) c.partial[blockIdx.x] = tot;
-  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
-  if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, npairs);
+  __syncthreads();
+  return R.nreg <= kBlkCap;
 }
 
-__global__ void reset_cand_kernel(unsigned long long* count, int* overflow) {
-  *count = 0;
-  *overflow = 0;
+// region cell holding region index l
+__device__ __forceinline__ int region_cell_of(const Region& R, int l) {
+  int lo = 0, hi = R.nrc;  // cstart[lo] <= l < cstart[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (R.cstart[mid] <= l) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// Pads the rest of the open chunk and takes the next one of the brick's slice.  When the slice is
+// exhausted the step falls back to the generic search, so later items may land anywhere inside it.
+__device__ __noinline__ unsigned* next_chunk(unsigned* chunk, int used, unsigned* slice, int* nchunks, int maxchunks,
+                                             bool& dropped) {
+  const int lane = threadIdx.x & 31;
+  for (int a = used + lane; a < kChunk; a += 32) chunk[a] = kPad;
+  int idx = 0;
+  if (lane == 0) idx = atomicAdd(nchunks, 1);
+  idx = __shfl_sync(0xffffffffu, idx, 0);
+  if (idx >= maxchunks) {
+    dropped = true;
+    return slice;
+  }
+  return slice + (size_t)idx * kChunk;
+}
+
+struct FindSmem {
+  Region R;
+  float4 p[kBlkCap];  // region-relative fp32 position, type in .w
+  int nchunks;
+};
+
+template <bool TYPES>
+__global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const __grid_constant__ PairCtx c,
+                                                                  const __grid_constant__ BlockGeom bg,
+                                                                  unsigned* __restrict__ items,
+                                                                  int* __restrict__ nchunks_out) {
+  __shared__ FindSmem S;
+  Region& R = S.R;
+  const CellGrid& cg = c.cg;
+  const PairParams& pp = c.pp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) S.nchunks = 0;
+  if (!region_setup(cg, bg, c.start, R)) {
+    if (threadIdx.x == 0) {
+      *c.fallback = 1;
+      nchunks_out[blockIdx.x] = 0;
+    }
+    return;
+  }
+  const float csx = (float)cg.cs[0], csy = (float)cg.cs[1], csz = (float)cg.cs[2];
+  const int rd0 = R.rd[0], rd1 = R.rd[1];
+  for (int l = threadIdx.x; l < R.nreg; l += kFindThreads) {
+    const int rc = region_cell_of(R, l);
+    float4 v = c.xs32[R.cslot[rc] + (l - R.cstart[rc])];
+    v.x += (float)(rc % rd0) * csx;
+    v.y += (float)((rc / rd0) % rd1) * csy;
+    v.z += (float)(rc / (rd0 * rd1)) * csz;
+    S.p[l] = v;
+  }
+  __syncthreads();
+
+  const float rc2m = pp.rc2m;
+  const int maxchunks = (int)(bg.capb / kChunk);
+  unsigned* const slice = items + (size_t)blockIdx.x * bg.capb;
+  unsigned* chunk = slice;
+  int used = kChunk;  // forces an allocation on first use
+  bool dropped = false;
+  const unsigned ltmask = (1u << lane) - 1u;
+  const int nhome = R.hn[0] * R.hn[1] * R.hn[2];
+
+  for (int h = warp; h < nhome; h += kFindThreads / 32) {
+    const int hx = h % R.hn[0], hy = (h / R.hn[0]) % R.hn[1], hz = h / (R.hn[0] * R.hn[1]);
+    const int rx = hx + 1, ry = hy + 1, rz = hz;
+    const int c00 = (rz * rd1 + ry) * rd0 + rx;
+    const int ilo = R.cstart[c00], ihi = R.cstart[c00 + 1];
+    if (ilo == ihi) continue;
+    // the 14 cells of the half shell as 5 runs of region indices
+    const int c1 = c00 + rd0, c2 = c00 + rd0 * rd1 - rd0, c3 = c00 + rd0 * rd1, c4 = c3 + rd0;
+    const int s0 = ilo, s1 = R.cstart[c1 - 1], s2 = R.cstart[c2 - 1], s3 = R.cstart[c3 - 1], s4 = R.cstart[c4 - 1];
+    const int o1 = R.cstart[c00 + 2] - s0;
+    const int o2 = o1 + R.cstart[c1 + 2] - s1;
+    const int o3 = o2 + R.cstart[c2 + 2] - s2;
+    const int o4 = o3 + R.cstart[c3 + 2] - s3;
+    const int nj = o4 + R.cstart[c4 + 2] - s4;
+
+    for (int p0 = 0; p0 < nj; p0 += 192) {
+      // partner u of this lane: position and ljc = region index << 2 | type class (bit 0: is itype,
+      // bit 1: is jtype).  Every partner outside the own cell has a larger region index than any
+      // home atom, so "li < lj" is exactly the own-cell rule (count each pair of cell mates once).
+      float jx[6], jy[6], jz[6];
+      int ljc[6];
+#pragma unroll
+      for (int u = 0; u < 6; u++) {
+        const int k = p0 + 32 * u + lane;
+        const int l = k < o1 ? s0 + k : (k < o2 ? s1 + (k - o1) : (k < o3 ? s2 + (k - o2) : (k < o4 ? s3 + (k - o3) : s4 + (k - o4))));
+        ljc[u] = 0;
+        jx[u] = 1e30f;
+        jy[u] = 0.f;
+        jz[u] = 0.f;
+        if (k < nj) {
+          const float4 v = S.p[l];
+          jx[u] = v.x;
+          jy[u] = v.y;
+          jz[u] = v.z;
+          int cls = 3;
+          if (TYPES) {
+            const int tj = __float_as_int(v.w);
+            cls = (tj == pp.itype ? 1 : 0) | (tj == pp.jtype ? 2 : 0);
+          }
+          ljc[u] = (l << 2) | cls;
+        }
+      }
+      for (int li = ilo; li < ihi; li++) {
+        const float4 pi = S.p[li];
+        int want = 3;
+        if (TYPES) {  // an itype atom pairs with jtype partners and the other way round
+          const int ti = __float_as_int(pi.w);
+          if (ti != pp.itype && ti != pp.jtype) continue;
+          want = (ti == pp.itype) ? 2 : 1;
+        }
+        const int lic = (li << 2) | 3;
+        unsigned m[6];
+        int tot = 0;
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          const float dx = pi.x - jx[u], dy = pi.y - jy[u], dz = pi.z - jz[u];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          bool take = (d2 < rc2m) && (lic < ljc[u]);
+          if (TYPES) take = take && (ljc[u] & want);
+          m[u] = __ballot_sync(0xffffffffu, take);
+          tot += __popc(m[u]);
+        }
+        if (tot == 0) continue;
+        if (used + tot > kChunk) {  // at most 192 per home atom and pass, so a fresh chunk always fits
+          chunk = next_chunk(chunk, used, slice, &S.nchunks, maxchunks, dropped);
+          used = 0;
+        }
+        const unsigned hi16 = (unsigned)li << 16;
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+          if ((m[u] >> lane) & 1u) chunk[used + __popc(m[u] & ltmask)] = hi16 | (unsigned)(ljc[u] >> 2);
+          used += __popc(m[u]);
+        }
+      }
+    }
+  }
+  for (int a = used + lane; a < kChunk; a += 32) chunk[a] = kPad;
+  if (dropped && lane == 0) *c.fallback = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) nchunks_out[blockIdx.x] = min(S.nchunks, maxchunks);
+}
+
+struct EvalSmem {
+  Region R;
+  double red[33];
+  double2 pa[kBlkCap];   // {x, y}
+  double2 pb[kBlkCap];   // {z, bits: original index | image-shift code << 32}
+  // fixed-point force accumulators, 64 bits as (lo, hi) words with native 32-bit shared atomics
+  unsigned lo[3][kBlkCap];
+  int hi[3][kBlkCap];
+};
+
+// acc += q (two's complement, 64 bits split in two words): add the low word, carry into the high one
+__device__ __forceinline__ void fx_add(unsigned* lo, int* hi, long long q) {
+  const unsigned ql = (unsigned)q;
+  int qh = (int)(q >> 32);
+  const unsigned old = atomicAdd(lo, ql);
+  qh += (old + ql < old) ? 1 : 0;
+  if (qh) atomicAdd(hi, qh);
+}
+
+__global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __grid_constant__ PairCtx c,
+                                                                     const __grid_constant__ BlockGeom bg,
+                                                                     const unsigned* __restrict__ items,
+                                                                     const int* __restrict__ nchunks_in,
+                                                                     double* __restrict__ partial) {
+  extern __shared__ __align__(32) unsigned char smem_raw[];
+  EvalSmem& S = *reinterpret_cast<EvalSmem*>(smem_raw);
+  Region& R = S.R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (*c.fallback != 0) {
+    if (threadIdx.x == 0) partial[blockIdx.x] = 0.0;
+    return;
+  }
+  region_setup(c.cg, bg, c.start, R);  // fits: block_find_kernel checked the same numbers
+  for (int l = threadIdx.x; l < R.nreg; l += kEvalThreads) {
+    const int rc = region_cell_of(R, l);
+    const AtomRec r = c.arec[R.cslot[rc] + (l - R.cstart[rc])];
+    S.pa[l] = make_double2(r.x, r.y);
+    S.pb[l] = make_double2(r.z, __longlong_as_double(r.tag | ((long long)R.ccode[rc] << 32)));
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      S.lo[k][l] = 0u;
+      S.hi[k][l] = 0;
+    }
+  }
+  // Fixed point: a pair force component is at most fmax < 2^ex in magnitude and a region atom has
+  // fewer than kBlkCap < 2^11 partners, so with scale 2^(51-ex) no sum reaches 2^62; one unit is
+  // 2^-51 of the largest possible pair force, the resolution fp64 itself has there.  Integer sums
+  // do not depend on the order the atomics resolve in.
+  const double fmax_grid = __longlong_as_double((long long)*c.fmax_bits);
+  const double scale = fmax_grid > 0.0 ? scalbn(1.0, 51 - (ilogb(fmax_grid) + 1)) : 1.0;
+  __syncthreads();
+
+  const unsigned* const slice = items + (size_t)blockIdx.x * bg.capb;
+  const int nbatch = nchunks_in[blockIdx.x] * (kChunk / 32);
+  double e = 0.0;
+  unsigned npairs = 0;
+  unsigned it_next = warp < nbatch ? slice[(size_t)warp * 32 + lane] : kPad;
+  for (int bt = warp; bt < nbatch; bt += kEvalThreads / 32) {
+    const unsigned it = it_next;
+    const int bn = bt + kEvalThreads / 32;
+    it_next = bn < nbatch ? slice[(size_t)bn * 32 + lane] : kPad;  // in flight while this batch is evaluated
+    if (__ballot_sync(0xffffffffu, it != kPad) == 0u) continue;
+    int li = -1;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (it != kPad) {
+      li = (int)(it >> 16);
+      const int lj = (int)(it & 0xffffu);
+      const double2 ia = S.pa[li], ib = S.pb[li], ja = S.pa[lj], jb = S.pb[lj];
+      AtomRec ri, rj;
+      ri.x = ia.x; ri.y = ia.y; ri.z = ib.x; ri.tag = __double_as_longlong(ib.y);
+      rj.x = ja.x; rj.y = ja.y; rj.z = jb.x; rj.tag = __double_as_longlong(jb.y);
+      if (pair_exact(c, ri, rj, (int)(rj.tag >> 32), e, px, py, pz)) {
+        npairs++;
+        fx_add(&S.lo[0][lj], &S.hi[0][lj], -__double2ll_rn(px * scale));
+        fx_add(&S.lo[1][lj], &S.hi[1][lj], -__double2ll_rn(py * scale));
+        fx_add(&S.lo[2][lj], &S.hi[2][lj], -__double2ll_rn(pz * scale));
+      }
+    }
+    if (run_totals(li, px, py, pz)) {
+      fx_add(&S.lo[0][li], &S.hi[0][li], __double2ll_rn(px * scale));
+      fx_add(&S.lo[1][li], &S.hi[1][li], __double2ll_rn(py * scale));
+      fx_add(&S.lo[2][li], &S.hi[2][li], __double2ll_rn(pz * scale));
+    }
+  }
+  __syncthreads();
+  const double inv_scale = 1.0 / scale;
+  for (int l = threadIdx.x; l < R.nreg; l += kEvalThreads) {
+    long long q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) q[k] = ((long long)S.hi[k][l] << 32) + (long long)S.lo[k][l];
+    if (q[0] | q[1] | q[2]) {
+      const long long o = 3 * (__double_as_longlong(S.pb[l].y) & 0xffffffffLL);
+      atomicAdd(&c.f[o + 0], (double)q[0] * inv_scale);
+      atomicAdd(&c.f[o + 1], (double)q[1] * inv_scale);
+      atomicAdd(&c.f[o + 2], (double)q[2] * inv_scale);
+    }
+  }
+  double tot = block_sum(e, S.red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
+  if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, (unsigned long long)npairs);
+}
+
+__global__ void pair_reset_kernel(BiasDev* st, int* fallback, int fallback_init, unsigned long long* fmax_bits) {
+  st->n_pairs = 0;
+  *fallback = fallback_init;
+  *fmax_bits = 0ull;
 }
 
 // Neighbour-list form: one thread per listed i-row (lammps/fix_edm_pair.cpp:177-240).
@@ -944,12 +856,20 @@ __global__ void reset_pairs_kernel(BiasDev* st, unsigned long long* ncalls) {
   if (ncalls) *ncalls = 0;
 }
 
-__global__ void sum_partials2_kernel(int n, const double* __restrict__ partial, double* out) {
+// closes a pair step: energy = sum of the per-CTA partials; reports a fallback to the host-mapped flag
+__global__ void sum_partials2_kernel(int n, const double* __restrict__ partial, double* out, const int* fallback,
+                                     volatile int* host_flag) {
   __shared__ double red[33];
   double e = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) e += partial[i];
   double tot = block_sum(e, red);
-  if (threadIdx.x == 0) out[0] = tot;
+  if (threadIdx.x == 0) {
+    out[0] = tot;
+    if (host_flag && fallback && *fallback) {
+      *host_flag = 1;
+      __threadfence_system();
+    }
+  }
 }
 
 }  // namespace edm
@@ -964,6 +884,10 @@ static PairParams pair_params(const edm_bias* b, const int* type, int itype, int
   pp.use_types = type != nullptr;
   pp.do_hills = do_hills;
   pp.accept_all = b->prm.hill_density < 0;
+  {
+    const GridDesc& g = b->bias->d;
+    pp.lean = g.is_gauss && g.b_interp && g.b_deriv && !g.periodic[0] && !g.bper[0];
+  }
   pp.thresh = pp.accept_all ? 2.0 : b->prm.hill_density / (double)(int)est;
   {
     double tb = ceil(pp.thresh * 4294967296.0);
@@ -972,12 +896,48 @@ static PairParams pair_params(const edm_bias* b, const int* type, int itype, int
   pp.key = uniform_key(seed, step);
   pp.dbg = getenv("EDM_DBG") ? atoi(getenv("EDM_DBG")) : 0;
   pp.rc2 = cutoff * cutoff;
+  pp.rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;
   pp.natoms = natoms;
   pp.acc_cap = b->accepted_cap;
   return pp;
 }
 
-// binning + pair kernel on device pointers; leaves the energy in b->d_scalar[0]
+// bricks of home cells for the block search: the largest home/region ratio whose region fits the
+// shared-memory budget with a margin over the mean occupancy (10 % + 6 sigma of a Poisson count).
+// `scale` inflates the assumed density: it grows after a step that had to fall back (non-uniform
+// systems), which shrinks the bricks.
+static bool choose_bricks(const CellGrid& cg, long natoms, double cutoff, double scale, BlockGeom& bg) {
+  const double m = scale * (double)natoms / (double)cg.ncell;
+  double best = 0.0;
+  for (int bz = 1; bz <= 8 && bz <= cg.nc[2]; bz++)
+    for (int by = 1; by <= 8 && by <= cg.nc[1]; by++)
+      for (int bx = 1; bx <= 8 && bx <= cg.nc[0]; bx++) {
+        const int rcells = (bx + 2) * (by + 2) * (bz + 1);
+        if (rcells > kRegCells) continue;
+        const double mean = rcells * m;
+        if (1.1 * mean + 6.0 * sqrt(mean) > kBlkCap) continue;
+        const double score = (double)(bx * by * bz) / rcells + 1e-6 * bx;
+        if (score > best) {
+          best = score;
+          bg.bd[0] = bx;
+          bg.bd[1] = by;
+          bg.bd[2] = bz;
+        }
+      }
+  if (best == 0.0) return false;
+  for (int d = 0; d < 3; d++) bg.nb[d] = (cg.nc[d] + bg.bd[d] - 1) / bg.bd[d];
+  const double vol = cg.box[0] * cg.box[1] * cg.box[2];
+  const double per_cell = 0.5 * m * (scale * (double)natoms / vol) * (4.0 / 3.0) * M_PI * cutoff * cutoff * cutoff;
+  const double expect = per_cell * bg.bd[0] * bg.bd[1] * bg.bd[2];
+  unsigned long long cap = (unsigned long long)(1.5 * expect + 8.0 * sqrt(expect + 1.0)) + (kFindThreads / 32 + 1) * kChunk;
+  cap = (cap + kChunk - 1) / kChunk * kChunk;
+  const unsigned long long total = cap * (unsigned long long)bg.nb[0] * bg.nb[1] * bg.nb[2];
+  if (cap > (1ull << 30) || total * sizeof(unsigned) > (24ull << 30)) return false;
+  bg.capb = (unsigned)cap;
+  return true;
+}
+
+// binning + pair kernels on device pointers; leaves the energy in *energy_dev
 static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* f, const int* type, int itype,
                              int jtype, const double* box, double cutoff, int do_hills, long long est, uint64_t seed,
                              uint64_t step, double* energy_dev, cudaStream_t st) {
@@ -994,94 +954,107 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   }
   EDM_REQUIRE(ncell < 2000000000LL, "too many cells");
   cg.ncell = (int)ncell;
-  // scratch: cell_of[n], order[n], ts[n], count[ncell+1], start[ncell+1], xs[3n]
-  size_t n = (size_t)natoms, nc1 = (size_t)ncell + 1;
-  size_t off_cell = 0, off_order = off_cell + n * 4, off_ts = off_order + n * 4, off_count = off_ts + n * 4;
-  size_t off_start = off_count + nc1 * 4;
-  size_t off_tiles = off_start + nc1 * 4;
-  size_t off_xs = (off_tiles + ((size_t)ncell / 2048 + 2) * 4 + 255) / 256 * 256;
-  size_t off_xs32 = off_xs + 3 * n * sizeof(double);
-  size_t total = off_xs32 + 3 * n * sizeof(float);
+
+  // feedback from earlier steps (device-written, host-mapped): a fallback shrinks the bricks
+  if (!b->h_pair_flags) {
+    EDM_CUDA(cudaHostAlloc(&b->h_pair_flags, 64, cudaHostAllocMapped));
+    memset((void*)b->h_pair_flags, 0, 64);
+    EDM_CUDA(cudaHostGetDevicePointer(&b->d_pair_flags, (void*)b->h_pair_flags, 0));
+  }
+  if (b->h_pair_flags[0]) {
+    b->h_pair_flags[0] = 0;
+    b->pair_fallbacks++;
+    if (b->brick_scale < 64.0) b->brick_scale *= 1.5;
+  }
+  // EDM_PAIR_MODE=0 forces the direct search (A/B measurements, tests of the last resort)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* ev = getenv("EDM_PAIR_MODE");
+    mode = ev ? atoi(ev) : 6;
+  }
+  BlockGeom bg;
+  const bool bricks = (mode != 0) && choose_bricks(cg, natoms, cutoff, b->brick_scale, bg);
+  const int nblocks = bricks ? bg.nb[0] * bg.nb[1] * bg.nb[2] : 0;
+  for (int d = 0; d < 3; d++) b->brick_dims[d] = bricks ? bg.bd[d] : 0;
+  const int dblocks = 148 * 8;  // direct search: grid-stride over the atoms
+
+  // scratch: cell_of[n] order[n] | count[ncell+1] start[ncell+1] tiles | flags | nchunks[nblocks] |
+  //          partial[nblocks + dblocks] | arec[n] | xs32[n]
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t n = (size_t)natoms, nc1 = (size_t)ncell + 1;
+  const size_t off_cell = 0, off_order = up(off_cell + n * 4), off_count = up(off_order + n * 4);
+  const size_t off_start = up(off_count + nc1 * 4), off_tiles = up(off_start + nc1 * 4);
+  const size_t off_flags = up(off_tiles + ((size_t)ncell / kScanTile + 2) * 4);
+  const size_t off_nch = up(off_flags + 64), off_part = up(off_nch + (size_t)nblocks * 4 + 4);
+  const size_t off_rec = up(off_part + ((size_t)nblocks + dblocks) * 8);
+  const size_t off_xs32 = up(off_rec + n * sizeof(AtomRec));
+  const size_t off_crec = up(off_xs32 + n * sizeof(float4));
+  const size_t total = off_crec + (size_t)b->bias->d.n[0] * 4 * sizeof(double);
   EDM_TRY(b->cells.reserve(total));
   char* base = b->cells.as<char>();
   int* cell_of = reinterpret_cast<int*>(base + off_cell);
   int* order = reinterpret_cast<int*>(base + off_order);
-  int* ts = reinterpret_cast<int*>(base + off_ts);
   int* count = reinterpret_cast<int*>(base + off_count);
   int* start = reinterpret_cast<int*>(base + off_start);
   int* tile_total = reinterpret_cast<int*>(base + off_tiles);
-  double* xs = reinterpret_cast<double*>(base + off_xs);
-  float* xs32 = reinterpret_cast<float*>(base + off_xs32);
+  int* fallback = reinterpret_cast<int*>(base + off_flags);
+  int* nchunks = reinterpret_cast<int*>(base + off_nch);
+  double* partial = reinterpret_cast<double*>(base + off_part);
+  AtomRec* arec = reinterpret_cast<AtomRec*>(base + off_rec);
+  float4* xs32 = reinterpret_cast<float4*>(base + off_xs32);
+  double* cellrec = reinterpret_cast<double*>(base + off_crec);
+  unsigned long long* fmax_bits = reinterpret_cast<unsigned long long*>(base + off_flags + 8);
+  if (bricks) EDM_TRY(b->cand.reserve((size_t)nblocks * bg.capb * sizeof(unsigned)));
 
   EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
-  unsigned nb = (unsigned)((natoms + 255) / 256);
+  const unsigned nb = (unsigned)((natoms + 255) / 256);
   cell_count_kernel<<<nb, 256, 0, st>>>(natoms, x, cg, cell_of, count);
   const int ntiles = (cg.ncell + kScanTile - 1) / kScanTile;
   cell_scan_totals_kernel<<<ntiles, 256, 0, st>>>(cg.ncell, count, tile_total);
   cell_scan_kernel<<<ntiles, 256, 0, st>>>(cg.ncell, count, tile_total, start);
-  EDM_CUDA(cudaMemsetAsync(count, 0, nc1 * 4, st));
   cell_fill_kernel<<<nb, 256, 0, st>>>(natoms, cell_of, start, count, order);
-  cell_sort_gather_kernel<<<(cg.ncell + 127) / 128, 128, 0, st>>>(cg, start, order, x, type, xs, xs32, type ? ts : nullptr);
+  cell_rank_gather_kernel<<<nb, 256, 0, st>>>(natoms, cg, cell_of, start, order, x, type, arec, xs32);
+  pair_reset_kernel<<<1, 1, 0, st>>>(b->d_state, fallback, bricks ? 0 : 1, fmax_bits);
+  pair_prep_kernel<<<(b->bias->d.n[0] + 255) / 256, 256, 0, st>>>(b->bias->d, cellrec, fmax_bits);
   EDM_CUDA(cudaGetLastError());
 
-  PairParams pp = pair_params(b, type, itype, jtype, do_hills, est, seed, step, cutoff, natoms);
-  reset_pairs_kernel<<<1, 1, 0, st>>>(b->d_state, nullptr);
-  // EDM_PAIR_MODE=0 selects the v1 thread-per-atom kernel (kept for A/B measurements)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* ev = getenv("EDM_PAIR_MODE");
-    mode = ev ? atoi(ev) : 2;
-  }
-  long long blocks;
+  PairCtx ctx;
+  ctx.g = b->bias->d;
+  ctx.cg = cg;
+  ctx.pp = pair_params(b, type, itype, jtype, do_hills, est, seed, step, cutoff, natoms);
+  ctx.start = start;
+  ctx.arec = arec;
+  ctx.xs32 = xs32;
+  ctx.f = f;
+  ctx.st = b->d_state;
+  ctx.acc = b->d_accepted;
+  ctx.fallback = fallback;
+  ctx.cellrec = cellrec;
+  ctx.fmax_bits = fmax_bits;
+
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[0], st));
-  if (mode == 0) {
-    blocks = (natoms + 127) / 128;
-    if (blocks > b->n_partial) blocks = b->n_partial;
-    pair_cells_kernel<<<(int)blocks, 128, 0, st>>>(b->bias->d, cg, pp, start, order, xs, ts, f, b->d_energy_partial,
-                                                   b->d_state, b->d_accepted);
-  } else {
-    blocks = 148 * 8;  // one wave of 8 resident CTAs (32 warps) per SM; warps stride over the cells
-    if (blocks > (cg.ncell + kPairWarps - 1) / kPairWarps) blocks = (cg.ncell + kPairWarps - 1) / kPairWarps;
-    if (blocks > b->n_partial) blocks = b->n_partial;
-    PairCtx ctx;
-    ctx.g = b->bias->d;
-    ctx.cg = cg;
-    ctx.pp = pp;
-    ctx.start = start;
-    ctx.order = order;
-    ctx.xs = xs;
-    ctx.xs32 = xs32;
-    ctx.ts = ts;
-    ctx.f = f;
-    ctx.partial = b->d_energy_partial;
-    ctx.st = b->d_state;
-    ctx.acc = b->d_accepted;
-    if (mode == 1) {
-      pair_cells_v4_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx);
-    } else {
-      // candidate list: expected pairs at uniform density x 1.5 + chunk slack; an overflow is flagged
-      double vol = box[0] * box[1] * box[2];
-      double expect = 0.5 * (double)natoms * ((double)natoms / vol) * (4.0 / 3.0) * M_PI * cutoff * cutoff * cutoff;
-      unsigned long long cap = (unsigned long long)(1.5 * expect) + 8ULL * 148 * 8 * kPairWarps * kChunk / 8 + (1u << 16);
-      cap = (cap + kChunk - 1) / kChunk * kChunk;
-      EDM_TRY(b->cand.reserve(cap * sizeof(int2) + 64));
-      CandList cl;
-      cl.count = b->cand.as<unsigned long long>();
-      cl.overflow = reinterpret_cast<int*>(b->cand.as<char>() + 8);
-      cl.items = reinterpret_cast<int2*>(b->cand.as<char>() + 64);
-      cl.cap = cap;
-      reset_cand_kernel<<<1, 1, 0, st>>>(cl.count, cl.overflow);
-      pair_find_kernel<<<(int)blocks, kPairWarps * 32, 0, st>>>(ctx, cl);
-      int eblocks = 148 * 8;
-      if (eblocks > b->n_partial) eblocks = b->n_partial;
-      blocks = eblocks;
-      pair_eval_kernel<<<eblocks, 256, 0, st>>>(ctx, cl);
-      count_launches(2);
+  int launched = 7;
+  if (bricks) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      EDM_CUDA(cudaFuncSetAttribute(block_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EvalSmem)));
+      attr_set = true;
     }
+    if (type)
+      block_find_kernel<true><<<nblocks, kFindThreads, 0, st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks);
+    else
+      block_find_kernel<false><<<nblocks, kFindThreads, 0, st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks);
+    if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[2], st));
+    block_eval_kernel<<<nblocks, kEvalThreads, sizeof(EvalSmem), st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks, partial);
+    launched += 2;
+  } else if (b->profiling) {
+    EDM_CUDA(cudaEventRecord(b->ev_pair[2], st));
   }
+  // returns at once unless the fallback flag is up
+  pair_direct_kernel<<<dblocks, 128, 0, st>>>(ctx, partial + nblocks);
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[1], st));
-  count_launches(8);
-  sum_partials2_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy_dev);
+  sum_partials2_kernel<<<1, 256, 0, st>>>(nblocks + dblocks, partial, energy_dev, fallback, bricks ? b->d_pair_flags : nullptr);
+  count_launches(launched + 2);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
@@ -1158,6 +1131,20 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
   return EDM_OK;
 }
 
+int edm_pair_search_info(edm_bias_t* b, int* brick_dims, double* density_scale, long long* fallbacks) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  if (b->h_pair_flags && b->h_pair_flags[0]) {  // a fallback reported since the last launch
+    b->h_pair_flags[0] = 0;
+    b->pair_fallbacks++;
+    if (b->brick_scale < 64.0) b->brick_scale *= 1.5;
+  }
+  if (brick_dims)
+    for (int d = 0; d < 3; d++) brick_dims[d] = b->brick_dims[d];
+  if (density_scale) *density_scale = b->brick_scale;
+  if (fallbacks) *fallbacks = b->pair_fallbacks;
+  return EDM_OK;
+}
+
 int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
                        int jtype, long inum, const int* ilist, const long* first, const int* jlist, int do_hills,
                        long long est_hill_count, const double* runiform, uint64_t seed, uint64_t step,
@@ -1196,7 +1183,7 @@ int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, d
                                          b->io.as<double>(), type ? reinterpret_cast<int*>(base + o_ty) : nullptr,
                                          runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, b->io2.as<double>(),
                                          b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
-  sum_partials2_kernel<<<1, 256>>>((int)blocks, b->d_energy_partial, b->d_scalar);
+  sum_partials2_kernel<<<1, 256>>>((int)blocks, b->d_energy_partial, b->d_scalar, nullptr, nullptr);
   count_launches(3);
   EDM_CUDA(cudaGetLastError());
   if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, 0));
@@ -1207,3 +1194,4 @@ int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, d
 }
 
 }  // extern "C"
+

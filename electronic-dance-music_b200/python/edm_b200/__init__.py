@@ -105,6 +105,8 @@ EXPORTS = {
     "edm_launch_count": (C.c_int, [C.POINTER(C.c_longlong)]),
     "edm_bias_set_profiling": (C.c_int, [vp, C.c_int]),
     "edm_bias_profile_ms": (C.c_int, [vp, c_dp]),
+    "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
+    "edm_pair_search_info": (C.c_int, [vp, c_ip, c_dp, C.POINTER(C.c_longlong)]),
     "edm_bias_hills_commit_dev": (C.c_int, [vp, vp, C.c_int, C.c_long, C.c_longlong, vp]),
 }
 
@@ -364,6 +366,13 @@ class Bias:
                                          jtype, _dp(_d(box)), float(cutoff), int(do_hills), int(est), seed, step,
                                          C.byref(r)))
         return dict(energy=r.energy, n_pairs=r.n_pairs, n_calls=r.n_calls)
+
+    def pair_search_info(self):
+        bd = (C.c_int * 3)()
+        sc = C.c_double(0)
+        fb = C.c_longlong(0)
+        check(self.L.edm_pair_search_info(self.h, bd, C.byref(sc), C.byref(fb)))
+        return dict(bricks=tuple(bd), density_scale=sc.value, fallbacks=fb.value)
 
     def pair_step_list(self, x, f, nlocal, ilist, first, jlist, do_hills=False, est=0, runiform=None, seed=0, step=0,
                        types=None, itype=0, jtype=0):

@@ -203,6 +203,11 @@ int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, d
                        int do_hills, long long est_hill_count, const double* runiform, uint64_t seed,
                        uint64_t step, edm_pair_result_t* result);
 
+/* How the last edm_pair_*_cells step searched for pairs: the brick of home cells a CTA owned
+ * (0,0,0 = direct search), the density inflation used to size bricks, and how many steps so far
+ * had to fall back to the direct search (which then shrinks the bricks).  Outputs may be NULL. */
+int edm_pair_search_info(edm_bias_t* b, int* brick_dims, double* density_scale, long long* fallbacks);
+
 /* ------------------------------------------------------------------ multi-GPU hill exchange */
 
 /* Replaces flush_buffers / check_for_flush, lib/edm_bias.cpp:614-706 (broadcast mode): each rank
@@ -229,6 +234,9 @@ int edm_launch_count(long long* count);
 int edm_bias_set_profiling(edm_bias_t* b, int on);
 /* Duration of the last profiled pair kernel in ms (synchronises on its end event). */
 int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms);
+/* The same interval split at the boundary between the block search and the block evaluation
+ * kernel (both 0 when the generic search ran). */
+int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms);
 
 #ifdef __cplusplus
 }

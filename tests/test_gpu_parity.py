@@ -365,6 +365,91 @@ def test_pair_cells_parity(edm, port, tmp_path):
     compare_bias(bd, bo)
 
 
+def _typed_half_list(port, x, box, rc, types, itype, jtype):
+    pi, pj, sh = port.build_half_list(x, box, rc)
+    ti, tj = types[pi], types[pj]
+    keep = ((ti == itype) & (tj == jtype)) | ((ti == jtype) & (tj == itype))  # fix_edm_pair.cpp:180-203
+    return pi[keep], pj[keep], sh[keep]
+
+
+def test_pair_cells_types(edm, port, tmp_path):
+    """Type filter of fix edm_pair (ipair/jpair, lammps/fix_edm_pair.cpp:180-203) in the block search."""
+    rng = np.random.default_rng(23)
+    n, L, rc = 6000, 36.0, 5.0
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+    types = rng.integers(1, 4, n).astype(np.int32)
+    for itype, jtype in ((1, 2), (2, 2)):
+        for step in range(2):
+            x = make_atoms(rng, n, L)
+            pi, pj, sh = _typed_half_list(port, x, [L, L, L], rc, types, itype, jtype)
+            u = port.pair_uniforms(7, step, pi, pj, n)
+            fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+            eo, _ = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=2 * pi.size, uniforms=u)
+            res = bd.pair_step_cells(x, fd, [L, L, L], rc, do_hills=True, est=2 * pi.size, seed=7, step=step,
+                                     types=types, itype=itype, jtype=jtype)
+            assert res["n_pairs"] == pi.size
+            if step > 0 or itype == 2:
+                assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+                assert_close(fd, fo, "typed pair forces %d-%d step %d" % (itype, jtype, step))
+    assert bd.pair_search_info()["bricks"] != (0, 0, 0) and bd.pair_search_info()["fallbacks"] == 0
+    compare_bias(bd, bo)
+
+
+def test_pair_cells_minimal_box(edm, port, tmp_path):
+    """3 cells per side: every brick wraps around the box and the same cell enters a region twice with
+    different image shifts."""
+    rng = np.random.default_rng(24)
+    n, rc = 900, 5.0
+    box = [15.2, 16.0, 19.9]
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+    for step in range(3):
+        x = np.ascontiguousarray(rng.uniform(0, 1, size=(n, 3)) * np.array(box))
+        pi, pj, sh = port.build_half_list(x, box, rc)
+        u = port.pair_uniforms(8, step, pi, pj, n)
+        fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+        eo, _ = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=2 * pi.size, uniforms=u)
+        res = bd.pair_step_cells(x, fd, box, rc, do_hills=True, est=2 * pi.size, seed=8, step=step)
+        assert res["n_pairs"] == pi.size
+        if step > 0:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "minimal-box pair forces step %d" % step)
+    compare_bias(bd, bo)
+
+
+def test_pair_cells_nonuniform_density_falls_back_and_adapts(edm, port, tmp_path):
+    """A density step (half of the atoms in a quarter of the box) overflows the bricks sized for the mean
+    density: that step runs on the direct search, later steps on smaller bricks; a tight cluster that
+    no brick can hold stays on the direct search.  Results never depend on which search ran."""
+    rng = np.random.default_rng(25)
+    n, L, rc = 16000, 46.0, 5.0
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+
+    def check(x, step, seed):
+        pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
+        u = port.pair_uniforms(seed, step, pi, pj, n)
+        fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+        eo, _ = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=2 * pi.size, uniforms=u)
+        res = bd.pair_step_cells(x, fd, [L, L, L], rc, do_hills=True, est=2 * pi.size, seed=seed, step=step)
+        assert res["n_pairs"] == pi.size
+        if step > 0:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "non-uniform pair forces step %d" % step)
+
+    for step in range(4):
+        x = make_atoms(rng, n, L)
+        x[: n // 2, 0] *= 0.25
+        check(np.ascontiguousarray(x), step, 9)
+    info = bd.pair_search_info()
+    assert 1 <= info["fallbacks"] <= 3 and info["density_scale"] > 1.0 and info["bricks"] != (0, 0, 0), info
+    before = info["fallbacks"]
+    for step in range(4, 6):
+        x = make_atoms(rng, n, L)
+        x[:4000] = 20.0 + 2.5 * rng.uniform(0, 1, size=(4000, 3))   # 4000 atoms in one cell
+        check(np.ascontiguousarray(x), step, 9)
+    assert bd.pair_search_info()["fallbacks"] == before + 2
+    compare_bias(bd, bo)
+
+
 def test_pair_list_parity(edm, port, tmp_path):
     """The neighbour-list form with caller-supplied uniforms and ghost atoms (j >= nlocal)."""
     rng = np.random.default_rng(22)
