@@ -41,6 +41,9 @@ PREWARM_HILLS = 20000        # hills deposited before timing so the evaluated bi
 DEPOSIT_BATCH = 1 << 20      # hills in the batched-deposit throughput measurement
 HILL_CAP = 4096              # records per rank in the exchange block
 ALG_BYTES_PER_ATOM = 76      # 24 B x + 48 B f read-modify-write + 4 B type, per atom per step
+# dram__bytes_read.sum + dram__bytes_write.sum of one block_eval_kernel launch on this workload
+NCU_TRAFFIC_BYTES = 188_917_504
+NCU_TRAFFIC_SOURCE = "profiles/r01_d_block_pair_ncu_selected.txt (ncu --set full, one launch)"
 
 
 def write_edm(tmpdir):
@@ -295,7 +298,7 @@ def run_gpu(args, rank, local_rank, world):
     launches0 = edm.launch_count()
     clocks.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    pair_ms = []
+    pair_ms, find_ms, eval_ms = [], [], []
     barrier()
     for k in range(args.steps):
         flush.zero_()                         # evict L2 between timed iterations (outside the event pair)
@@ -306,6 +309,10 @@ def run_gpu(args, rank, local_rank, world):
         ms = C.c_double(0)
         edm.check(L.edm_bias_profile_ms(bias.h, C.byref(ms)))   # waits for this step's pair kernel
         pair_ms.append(ms.value)
+        ms_a, ms_b = C.c_double(0), C.c_double(0)
+        edm.check(L.edm_bias_profile_pair_ms(bias.h, C.byref(ms_a), C.byref(ms_b)))
+        find_ms.append(ms_a.value)
+        eval_ms.append(ms_b.value)
     barrier()
     launches = edm.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -381,8 +388,9 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0:
         peak, peak_src = measured_peak()
         value = pairs_all / (total_ms * 1e-3)
-        kernel_ms = float(np.mean(pair_ms))
+        kernel_ms = float(np.mean(eval_ms)) if np.mean(eval_ms) > 0 else float(np.mean(pair_ms))
         alg_bytes = ALG_BYTES_PER_ATOM * N_ATOMS
+        info = bias.pair_search_info()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         st_hills = st1["steps"] - st0["steps"]
         out = {
@@ -397,10 +405,14 @@ def run_gpu(args, rank, local_rank, world):
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
                       "in_situ_hill_events": int(hills_timed)},
-            "roofline": {"bound": "hbm", "kernel": "pair_cells_v4_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "block_eval_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "fp64-pipe bound, not HBM bound (SURVEY 8d): 2.9 B/pair of compulsory traffic"},
+                         "search_kernel_ms": float(np.mean(find_ms)), "pair_kernels_ms": float(np.mean(pair_ms)),
+                         "bricks": list(info["bricks"]), "fallbacks": info["fallbacks"],
+                         "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "note": "not HBM bound (SURVEY 8d: 2.9 B/pair of compulsory traffic): ncu shows the LSU data "
+                                 "pipe (shared-memory gathers, atomics, shuffles) and the issue slots near 75 %"},
             "e2e": {"value": e2e_pairs_all / e2e_s, "unit": "evals/s",
                     "h2d_bytes_per_step": 2 * N_ATOMS * 24, "d2h_bytes_per_step": N_ATOMS * 24 + 24,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},

@@ -43,7 +43,8 @@ def build_lib(force=False, verbose=False):
         obj = os.path.join(LIBDIR, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            extra = os.environ.get("EDM_NVCC_EXTRA", "").split()  # e.g. -DEDM_RUN_REDUX=0 for A/B builds
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
     if jobs:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:

@@ -679,6 +679,10 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->fast.release();
   b->cand.release();
   if (b->h_pair_flags) cudaFreeHost((void*)b->h_pair_flags);
+  if (b->st_main) cudaStreamDestroy(b->st_main);
+  if (b->st_copy) cudaStreamDestroy(b->st_copy);
+  if (b->ev_f_up) cudaEventDestroy(b->ev_f_up);
+  if (b->ev_f_final) cudaEventDestroy(b->ev_f_final);
   delete b;
   return EDM_OK;
 }

@@ -119,5 +119,7 @@ struct edm_bias {
   long long round_est = 0;
   unsigned long long round_count = 0;
   int profiling = 0;
+  cudaStream_t st_main = nullptr, st_copy = nullptr;  // host-buffer pair step: kernels / overlapped copies
+  cudaEvent_t ev_f_up = nullptr, ev_f_final = nullptr;
   cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };

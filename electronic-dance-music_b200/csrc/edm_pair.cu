@@ -287,9 +287,12 @@ __device__ __forceinline__ double shift_of(int code, int d, const CellGrid& cg) 
 // pair is outside the cutoff; p = force on i (the force on j is -p).
 __device__ __forceinline__ bool pair_exact(const PairCtx& c, const AtomRec& ri, const AtomRec& rj, int code, double& e,
                                            double& px, double& py, double& pz) {
-  const double dx = __dsub_rn(__dsub_rn(ri.x, rj.x), shift_of(code, 0, c.cg));
-  const double dy = __dsub_rn(__dsub_rn(ri.y, rj.y), shift_of(code, 1, c.cg));
-  const double dz = __dsub_rn(__dsub_rn(ri.z, rj.z), shift_of(code, 2, c.cg));
+  double dx = __dsub_rn(ri.x, rj.x), dy = __dsub_rn(ri.y, rj.y), dz = __dsub_rn(ri.z, rj.z);
+  if (code) {  // only partners reached across the box boundary; subtracting a zero shift changes nothing
+    dx = __dsub_rn(dx, shift_of(code, 0, c.cg));
+    dy = __dsub_rn(dy, shift_of(code, 1, c.cg));
+    dz = __dsub_rn(dz, shift_of(code, 2, c.cg));
+  }
   const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   if (!(d2 < c.pp.rc2)) return false;
   const double rinv = rsqrt(d2);
@@ -330,6 +333,7 @@ template <typename T> __device__ __forceinline__ bool run_totals(int key, T& px,
   const int knext = __shfl_down_sync(0xffffffffu, key, 1);
   return key >= 0 && (lane == 31 || knext != key);
 }
+
 
 // ---- direct search: the last resort -----------------------------------------------------------------
 //
@@ -729,17 +733,24 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
       AtomRec ri, rj;
       ri.x = ia.x; ri.y = ia.y; ri.z = ib.x; ri.tag = __double_as_longlong(ib.y);
       rj.x = ja.x; rj.y = ja.y; rj.z = jb.x; rj.tag = __double_as_longlong(jb.y);
-      if (pair_exact(c, ri, rj, (int)(rj.tag >> 32), e, px, py, pz)) {
-        npairs++;
-        fx_add(&S.lo[0][lj], &S.hi[0][lj], -__double2ll_rn(px * scale));
-        fx_add(&S.lo[1][lj], &S.hi[1][lj], -__double2ll_rn(py * scale));
-        fx_add(&S.lo[2][lj], &S.hi[2][lj], -__double2ll_rn(pz * scale));
-      }
+      if (pair_exact(c, ri, rj, (int)(rj.tag >> 32), e, px, py, pz)) npairs++;
     }
-    if (run_totals(li, px, py, pz)) {
-      fx_add(&S.lo[0][li], &S.hi[0][li], __double2ll_rn(px * scale));
-      fx_add(&S.lo[1][li], &S.hi[1][li], __double2ll_rn(py * scale));
-      fx_add(&S.lo[2][li], &S.hi[2][li], __double2ll_rn(pz * scale));
+    // the partner takes -q, the home atom the run's sum of the same integers: the bias force on
+    // the block's atoms adds up to exactly zero
+    const long long qx = __double2ll_rn(px * scale), qy = __double2ll_rn(py * scale), qz = __double2ll_rn(pz * scale);
+    if (qx | qy | qz) {
+      const int lj = (int)(it & 0xffffu);
+      fx_add(&S.lo[0][lj], &S.hi[0][lj], -qx);
+      fx_add(&S.lo[1][lj], &S.hi[1][lj], -qy);
+      fx_add(&S.lo[2][lj], &S.hi[2][lj], -qz);
+    }
+    // (a warp-reduce per run mask, REDUX on 21-bit limbs, was measured 30 % slower than this scan:
+    // with several runs in a batch the masks differ per lane and the reduce serialises per mask)
+    long long sx = qx, sy = qy, sz = qz;
+    if (run_totals(li, sx, sy, sz)) {
+      fx_add(&S.lo[0][li], &S.hi[0][li], sx);
+      fx_add(&S.lo[1][li], &S.hi[1][li], sy);
+      fx_add(&S.lo[2][li], &S.hi[2][li], sz);
     }
   }
   __syncthreads();
@@ -940,7 +951,10 @@ static bool choose_bricks(const CellGrid& cg, long natoms, double cutoff, double
 // binning + pair kernels on device pointers; leaves the energy in *energy_dev
 static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* f, const int* type, int itype,
                              int jtype, const double* box, double cutoff, int do_hills, long long est, uint64_t seed,
-                             uint64_t step, double* energy_dev, cudaStream_t st) {
+                             uint64_t step, double* energy_dev, cudaStream_t st, cudaEvent_t forces_ready = nullptr,
+                             cudaEvent_t forces_done = nullptr) {
+  // forces_ready: waited for before the first kernel that touches f (the search before it only reads
+  // x); forces_done: recorded once f is final (before any hill work the caller appends)
   EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");  // fix_edm_pair.cpp:52-53
   EDM_REQUIRE(natoms > 0 && natoms < 2000000000L, "bad atom count");
   CellGrid cg;
@@ -1045,13 +1059,16 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
     else
       block_find_kernel<false><<<nblocks, kFindThreads, 0, st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks);
     if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[2], st));
+    if (forces_ready) EDM_CUDA(cudaStreamWaitEvent(st, forces_ready, 0));
     block_eval_kernel<<<nblocks, kEvalThreads, sizeof(EvalSmem), st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks, partial);
     launched += 2;
-  } else if (b->profiling) {
-    EDM_CUDA(cudaEventRecord(b->ev_pair[2], st));
+  } else {
+    if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[2], st));
+    if (forces_ready) EDM_CUDA(cudaStreamWaitEvent(st, forces_ready, 0));
   }
   // returns at once unless the fallback flag is up
   pair_direct_kernel<<<dblocks, 128, 0, st>>>(ctx, partial + nblocks);
+  if (forces_done) EDM_CUDA(cudaEventRecord(forces_done, st));
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[1], st));
   sum_partials2_kernel<<<1, 256, 0, st>>>(nblocks + dblocks, partial, energy_dev, fallback, bricks ? b->d_pair_flags : nullptr);
   count_launches(launched + 2);
@@ -1112,21 +1129,40 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
                         uint64_t step, edm_pair_result_t* result) {
   EDM_REQUIRE(b && x && f && box && natoms > 0, "bad argument");
   EDM_TRY(ensure_device(b->device));
-  size_t bx = (size_t)natoms * 3 * sizeof(double);
+  // Two streams so the copies hide behind the kernels that do not need them (pinned host buffers
+  // make the copies truly asynchronous; pageable ones still work, staged by the driver):
+  //   main: x up | binning, search                | evaluation | hill round
+  //   copy:      | f up (needed by the evaluation) |            | f down (final once the evaluation ends)
+  if (!b->st_main) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
+  }
+  const size_t bx = (size_t)natoms * 3 * sizeof(double);
   EDM_TRY(b->io.reserve(bx));
   EDM_TRY(b->io2.reserve(bx));
+  EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
   const int* dt = nullptr;
   if (type) {
     EDM_TRY(b->io3.reserve((size_t)natoms * sizeof(int)));
-    EDM_CUDA(cudaMemcpyAsync(b->io3.p, type, (size_t)natoms * sizeof(int), cudaMemcpyHostToDevice, 0));
+    EDM_CUDA(cudaMemcpyAsync(b->io3.p, type, (size_t)natoms * sizeof(int), cudaMemcpyHostToDevice, b->st_main));
     dt = b->io3.as<int>();
   }
-  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
-  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, b->st_main));
+  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, b->st_copy));
+  EDM_CUDA(cudaEventRecord(b->ev_f_up, b->st_copy));
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
+  EDM_TRY(pair_cells_launch(b, natoms, b->io.as<double>(), b->io2.as<double>(), dt, itype, jtype, box, cutoff, do_hills,
+                            est_hill_count, seed, step, b->d_scalar, b->st_main, b->ev_f_up, b->ev_f_final));
+  EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_f_final, 0));
+  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, b->st_copy));
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, b->st_main));
+  EDM_CUDA(cudaStreamSynchronize(b->st_main));
   edm_pair_result_t local;
-  EDM_TRY(edm_pair_step_cells_dev(b, natoms, b->io.as<double>(), b->io2.as<double>(), dt, itype, jtype, box, cutoff,
-                                  do_hills, est_hill_count, seed, step, &local, nullptr));
-  EDM_CUDA(cudaMemcpy(f, b->io2.p, bx, cudaMemcpyDeviceToHost));
+  EDM_TRY(read_pair_result(b, &local, nullptr));
+  if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  EDM_CUDA(cudaStreamSynchronize(b->st_copy));
   if (result) *result = local;
   return EDM_OK;
 }
