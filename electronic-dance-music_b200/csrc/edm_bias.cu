@@ -14,21 +14,49 @@ namespace edm {
 
 // EDMBias::update_forces, lib/edm_bias.cpp:276-295: thread per atom, coalesced row loads,
 // f -= dV/dx, energy reduced per CTA in a fixed order (partials summed in CTA order afterwards).
+// Random coordinates make every evaluation a chain of dependent DRAM round trips (x -> corner
+// records -> f): the old force is loaded together with the coordinate, before the grid walk, and
+// the register budget is set for the occupancy that measured fastest on B200 (C3: 3 CTAs/SM
+// 0.70 ms vs 0.81 / 0.86 ms at 2 / 4; C4: 2 CTAs/SM).  Two or four points per thread did not help:
+// ncu shows DRAM at ~4.4 TB/s of mostly half-used 64 B bursts (a 32 B record per corner), i.e. the
+// gather is DRAM-bound on real traffic, 3.5x the algorithmic bytes.
+#ifndef EDM_FORCES_UNROLL
+#define EDM_FORCES_UNROLL 1
+#endif
 template <int DIM>
-__global__ void __launch_bounds__(256) forces_kernel(GridDesc g, long n, const double* __restrict__ x, long xs,
+__global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) forces_kernel(GridDesc g, long n, const double* __restrict__ x, long xs,
                                                      double* __restrict__ f, long fs, const int* __restrict__ mask,
                                                      int apply_mask, double* __restrict__ partial) {
   __shared__ double red[33];
+  constexpr int U = EDM_FORCES_UNROLL;
   double e = 0.0;
-  long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if (apply_mask >= 0 && !(mask[i] & apply_mask)) continue;
-    double xi[DIM], der[DIM];
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    double xi[U][DIM], fo[U][DIM], der[U][DIM];
+    bool on[U];
 #pragma unroll
-    for (int d = 0; d < DIM; d++) xi[d] = x[i * xs + d];
-    e += d_eval_point<DIM>(g, xi, der, g.b_interp != 0);
+    for (int u = 0; u < U; u++) {
+      const long i = i0 + u * stride;
+      on[u] = i < n && !(apply_mask >= 0 && !(mask[i] & apply_mask));
+      if (on[u]) {
 #pragma unroll
-    for (int d = 0; d < DIM; d++) f[i * fs + d] -= der[d];
+        for (int d = 0; d < DIM; d++) {
+          xi[u][d] = x[i * xs + d];
+          fo[u][d] = f[i * fs + d];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (on[u]) e += d_eval_point<DIM>(g, xi[u], der[u], g.b_interp != 0);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (on[u]) {
+        const long i = i0 + u * stride;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) f[i * fs + d] = fo[u][d] - der[u][d];
+      }
+    }
   }
   double tot = block_sum(e, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
@@ -760,7 +788,7 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
   EDM_REQUIRE(xstride >= b->prm.dim && fstride >= b->prm.dim, "stride < dim");
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
-  long long blocks = (n + 255) / 256;
+  long long blocks = (n + 256 * EDM_FORCES_UNROLL - 1) / (256 * EDM_FORCES_UNROLL);
   if (blocks > b->n_partial) blocks = b->n_partial;
   if (blocks < 1) blocks = 1;
   const GridDesc& g = b->bias->d;
