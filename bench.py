@@ -46,10 +46,33 @@ NCU_TRAFFIC_BYTES = 188_917_504
 NCU_TRAFFIC_SOURCE = "profiles/r01_d_block_pair_ncu_selected.txt (ncu --set full, one launch)"
 
 
-def write_edm(tmpdir):
-    f = os.path.join(tmpdir, "c2.edm")
+# The other BASELINE.json configs (parity-test cases first; measurable on request with --workload).
+# Coordinate workloads (fix edm): one step = update_forces over every atom + add_hills (stride 1).
+COORD_WORKLOADS = {
+    "c1_coord_1d": dict(
+        text="tempering 0\nhill_prefactor 0.25\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.009765625\n"
+             "bias_sigma 0.025\nhill_density 250\n",
+        T=1.0, kB=1.0, lo=[0.0], hi=[10.0], atoms=100_000, atoms_scale_with_gpus=False, prewarm=2000, warm_h=0.001),
+    "c3_coord_2d": dict(
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 250\ndimension 2\nbox_low 0 0\nbox_high 64 64\nbias_spacing 0.015625 0.015625\n"
+             "bias_sigma 0.0625 0.0625\n",
+        T=300.0, kB=0.0019872, lo=[0.0, 0.0], hi=[64.0, 64.0], atoms=10_000_000, atoms_scale_with_gpus=False,
+        prewarm=20000, warm_h=0.02 / 250),
+    "c4_coord_3d": dict(
+        text="tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 250\ndimension 3\nbox_low 0 0 0\n"
+             "box_high 64 64 64\nbias_spacing 0.125 0.125 0.125\nbias_sigma 0.25 0.25 0.25\n",
+        T=300.0, kB=0.0019872, lo=[0.0] * 3, hi=[64.0] * 3, atoms=10_000_000, atoms_scale_with_gpus=False,
+        prewarm=20000, warm_h=0.02 / 250),
+}
+C5_TEXT = ("tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.0002\n"
+           "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025\n")
+
+
+def write_edm(tmpdir, text=None):
+    f = os.path.join(tmpdir, "bench.edm")
     with open(f, "w") as fh:
-        fh.write(EDM_TEXT + "hills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmpdir, tmpdir))
+        fh.write((text or EDM_TEXT) + "hills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmpdir, tmpdir))
     return f
 
 
@@ -243,7 +266,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = edm.lib()
     tmp = tempfile.mkdtemp()
-    edm_file = write_edm(tmp)
+    edm_file = write_edm(tmp, C5_TEXT if args.workload == "c5_pair_rdf_backlog" else None)
     bias = edm.bias_from_edm(edm_file, TEMPERATURE, BOLTZ, [1.68], [5.0], [1.68], [5.0], [0], [0.0], device=local_rank)
     warm_rng = np.random.default_rng(1234 + 1)
     warm = prewarm_hills(warm_rng)          # same hills on every rank: replicas start identical
@@ -397,14 +420,15 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "c2_pair_rdf", "atoms_per_gpu": N_ATOMS, "number_density": DENSITY,
+            "config": {"workload": args.workload, "atoms_per_gpu": N_ATOMS, "number_density": DENSITY,
                        "cutoff": CUTOFF, "pairs_per_gpu_per_step": pairs_per_step[0], "grid_points": 13281,
                        "hill_density": 250, "hill_rounds_timed": st_hills,
                        "l2": "flushed between timed steps (512 MiB memset outside the per-step CUDA-event pair)",
                        "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
-                      "in_situ_hill_events": int(hills_timed)},
+                      "in_situ_hill_events": int(hills_timed), "rounds": bias.round_info(),
+                      "backlog": list(bias.backlog()[:2])},
             "roofline": {"bound": "hbm", "kernel": "block_eval_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
@@ -438,6 +462,167 @@ def run_gpu(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------ GPU arm, coordinate workloads
+
+def run_coord(args, rank, local_rank, world):
+    """fix edm (lammps/fix_edm.cpp:134-162) on synthetic coordinates: K1 over every atom, then the hill round."""
+    import torch
+    import ctypes as C
+    import edm_b200 as edm
+
+    if edm.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = COORD_WORKLOADS[args.workload]
+    L = edm.lib()
+    tmp = tempfile.mkdtemp()
+    edm_file = write_edm(tmp, cfg["text"])
+    D = len(cfg["lo"])
+    bias = edm.bias_from_edm(edm_file, cfg["T"], cfg["kB"], cfg["lo"], cfg["hi"], cfg["lo"], cfg["hi"], [1] * D,
+                             [0.0] * D, device=local_rank)
+    geo = bias.bias_grid.info()
+    n_pts = int(np.prod(geo["n"][:D]))
+    warm_rng = np.random.default_rng(1234 + 3)
+    wc = warm_rng.uniform(cfg["lo"][0], cfg["hi"][0], size=(cfg["prewarm"], D))
+    bias.bias_grid.add_values(np.ascontiguousarray(wc), np.full(cfg["prewarm"], cfg["warm_h"]))
+
+    n_atoms = cfg["atoms"] // world          # strong split of the config's atom count: BASELINE names the total
+    rng = np.random.default_rng(1234 + 3 + 1000 * rank)
+    n_sets = 2
+    xs_host = [torch.from_numpy(rng.uniform(cfg["lo"][0], cfg["hi"][0], size=(n_atoms, D))).pin_memory()
+               for _ in range(n_sets)]
+    xs_dev = [x.cuda(non_blocking=True) for x in xs_host]
+    f_dev = torch.zeros((n_atoms, D), dtype=torch.float64, device="cuda")
+    f_host = torch.zeros((n_atoms, D), dtype=torch.float64).pin_memory()
+    energy_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    blk_doubles = L.edm_hill_block_doubles(D, HILL_CAP)
+    block = torch.zeros(blk_doubles, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(blk_doubles * world, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    seed = 20261018
+    est_total = n_atoms * world
+
+    def forces(step):
+        x = xs_dev[step % n_sets]
+        edm.check(L.edm_bias_update_forces_dev(bias.h, n_atoms, x.data_ptr(), D, f_dev.data_ptr(), D, None, -1,
+                                               energy_dev.data_ptr(), stream))
+
+    def hills(step):
+        x = xs_dev[step % n_sets]
+        if world == 1:
+            edm.check(L.edm_bias_add_hills_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, seed, step, stream))
+        else:
+            edm.check(L.edm_bias_select_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, est_total, seed, step,
+                                            rank * n_atoms, stream))
+            edm.check(L.edm_bias_hills_pack_dev(bias.h, block.data_ptr(), HILL_CAP, stream))
+            dist.all_gather_into_tensor(gathered, block)
+            edm.check(L.edm_bias_hills_commit_dev(bias.h, gathered.data_ptr(), world, HILL_CAP, est_total, stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    step_no = 0
+    for _ in range(max(args.warmup, 3)):
+        forces(step_no)
+        hills(step_no)
+        step_no += 1
+    barrier()
+    launches0 = edm.launch_count()
+    info0 = bias.round_info()
+    clocks.mark()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        forces(step_no)
+        ev[k][1].record()
+        hills(step_no)
+        ev[k][2].record()
+        step_no += 1
+    barrier()
+    launches = edm.launch_count() - launches0
+    info1 = bias.round_info()
+    k1_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    round_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    total_ms = float(sum(k1_ms) + sum(round_ms))
+
+    # ---- e2e through the host-buffer C ABI: update_forces + add_hills on pinned host arrays
+    def step_e2e(step):
+        xh = xs_host[step % n_sets]
+        e = C.c_double(0)
+        edm.check(L.edm_bias_update_forces(bias.h, n_atoms, xh.data_ptr(), D, f_host.data_ptr(), D, None, -1, C.byref(e)))
+        edm.check(L.edm_bias_add_hills(bias.h, n_atoms, xh.data_ptr(), D, None, None, -1, seed, step))
+        return e.value
+
+    e2e_ms = None
+    if world == 1:
+        step_e2e(step_no)
+        step_no += 1
+        torch.cuda.synchronize()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            step_e2e(step_no)
+            step_no += 1
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    clk = clocks.stop()
+
+    stats = torch.tensor([total_ms, float(np.mean(k1_ms)), float(np.mean(round_ms)), float(launches)],
+                         dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        total_ms, k1, rnd = float(mx[0]), float(mx[1]), float(mx[2])
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        launches_all = float(sm[3])
+    else:
+        k1, rnd, launches_all = float(stats[1]), float(stats[2]), float(launches)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        evals = float(n_atoms) * world * args.steps
+        grid_bytes = n_pts * (1 + D) * 8
+        alg = 24 * D * n_atoms + min(n_atoms * (2 ** D) * (1 + D) * 8, grid_bytes)   # SURVEY 8(d), per launch
+        achieved = alg / (k1 * 1e-3) / 1e9
+        out = {
+            "metric": "CV bias+force evals/sec", "value": evals / (total_ms * 1e-3), "unit": "evals/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "atoms_total": n_atoms * world, "atoms_per_gpu": n_atoms,
+                       "grid_points": n_pts, "grid_bytes_in_hbm": n_pts * (2 if D == 1 else 4) * 8, "hill_density": 250,
+                       "l2": "flushed between timed steps (512 MiB memset outside the CUDA-event pairs)",
+                       "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
+            "step_breakdown_ms": {"update_forces": k1, "hill_round": rnd},
+            "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],
+                      "rounds_in_order": info1["in_order"] - info0["in_order"]},
+            "roofline": {"bound": "hbm", "kernel": "forces_kernel<%d>" % D, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": k1, "algorithmic_bytes_per_launch": alg,
+                         "note": "kernel_ms spans forces_kernel + the 1-CTA energy sum (CUDA events on the launch stream)"},
+            "gpu_launches": int(launches_all),
+            "clocks": clk,
+        }
+        if e2e_ms is not None:
+            out["e2e"] = {"value": n_atoms / (e2e_ms * 1e-3), "unit": "evals/s",
+                          "h2d_bytes_per_step": 3 * n_atoms * D * 8, "d2h_bytes_per_step": n_atoms * D * 8 + 8,
+                          "ms_per_step": e2e_ms}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -445,6 +630,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2_pair_rdf",
+                    choices=["c2_pair_rdf", "c5_pair_rdf_backlog"] + sorted(COORD_WORKLOADS),
+                    help="c2_pair_rdf is the benchmark (BASELINE.json configs[1]); the others are the remaining configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -454,7 +642,10 @@ def main():
     else:
         if world != args.gpus and world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
-        run_gpu(args, rank, local_rank, world)
+        if args.workload in COORD_WORKLOADS:
+            run_coord(args, rank, local_rank, world)
+        else:
+            run_gpu(args, rank, local_rank, world)
 
 
 if __name__ == "__main__":

@@ -112,42 +112,58 @@ struct RoundParams {
   long accepted_cap, log_cap;
 };
 
-// One hill, deposited by the whole CTA with plain read-modify-writes (one hill at a time, so no
-// two threads touch the same point unless a periodic window revisits it; then fp64 atomics, whose
-// operands are equal, keep the result order-independent).  Returns add_value's integral to all.
+// One hill's window spread over the CTA.  kPassStore: plain read-modify-writes (one hill at a time,
+// so no two threads touch the same point unless a periodic window revisits it; then fp64 atomics,
+// whose operands are equal, keep the result order-independent).  kPassAtomic: fp64 REDs, for hills of
+// one round deposited concurrently.  kPassIntegrate: no writes, only add_value's integral.  The
+// window-point -> thread mapping and the reduction tree are the same in every mode, so the integral
+// comes out bit-identical whichever pass computed it.  Every thread receives the integral.
+enum { kPassIntegrate = 0, kPassStore = 1, kPassAtomic = 2 };
+
+template <int DIM, int MODE>
+__device__ double cta_window_pass(const GridDesc& g, const double* x0, double h, double* red, bool& dirty) {
+  constexpr int W = RecW<DIM>::value;
+  HillGeom<DIM> hg;
+  dirty = false;
+  double ba = 0.0;
+  if (d_hill_prepare<DIM>(g, x0, hg)) {
+    long long total = 1;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) total *= (2 * g.minisize[d] + 1);
+    for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+      int idx[DIM];
+      long long lin;
+      if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
+      double etot, force[DIM];
+      bool cnz;
+      if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
+      double add = h * etot;
+      if (MODE != kPassIntegrate) {
+        double* r = g.rec + lin * W;
+        if (MODE == kPassAtomic || g.dup_possible) {
+          atomicAdd(r, add);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
+        } else {
+          r[0] += add;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) r[1 + d] += h * force[d];
+        }
+      }
+      ba += add * g.vol_element;
+      dirty |= cnz;
+    }
+  }
+  return block_sum(ba, red);  // contains __syncthreads: record writes are visible CTA-wide after it
+}
+
+// GaussGrid::add_value for one hill by the whole CTA, lib/gaussian_grid.h:176-372
 template <int DIM>
 __device__ double cta_deposit(const GridDesc& g, const double* x0, double h, double* red, int* sflag) {
   constexpr int W = RecW<DIM>::value;
-  HillGeom<DIM> hg;
-  if (!d_hill_prepare<DIM>(g, x0, hg)) return 0.0;
-  long long total = 1;
-#pragma unroll
-  for (int d = 0; d < DIM; d++) total *= (2 * g.minisize[d] + 1);
-  double ba = 0.0;
-  bool dirty = false;
-  for (long long w = threadIdx.x; w < total; w += blockDim.x) {
-    int idx[DIM];
-    long long lin;
-    if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
-    double etot, force[DIM];
-    bool cnz;
-    if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
-    double add = h * etot;
-    double* r = g.rec + lin * W;
-    if (g.dup_possible) {
-      atomicAdd(r, add);
-#pragma unroll
-      for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
-    } else {
-      r[0] += add;
-#pragma unroll
-      for (int d = 0; d < DIM; d++) r[1 + d] += h * force[d];
-    }
-    ba += add * g.vol_element;
-    dirty |= cnz;
-  }
   if (threadIdx.x == 0) *sflag = 0;
-  double tot = block_sum(ba, red);  // contains __syncthreads: record writes are visible CTA-wide after it
+  bool dirty;
+  double tot = cta_window_pass<DIM, kPassStore>(g, x0, h, red, dirty);
   if (dirty) *sflag = 1;
   __syncthreads();
   if (*sflag) {  // duplicate_boundary, lib/gaussian_grid.h:365-368
@@ -156,6 +172,27 @@ __device__ double cta_deposit(const GridDesc& g, const double* x0, double h, dou
   }
   __syncthreads();
   return tot;
+}
+
+// cv_hist_->add_value(position, v), lib/grid.h:370-385 (T21)
+template <int DIM, bool ATOMIC>
+__device__ __forceinline__ void d_hist_bump(const GridDesc& hist, const double* pos, double v) {
+  if (!hist.rec) return;
+  long long lin = 0, pstride = 1;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    double xd = pos[d];
+    if (!hist.periodic[d] && (xd < hist.min[d] || xd >= hist.upper[d])) return;
+    if (hist.periodic[d]) xd = d_wrap(xd, hist.min[d], hist.len[d]);
+    long long idx = (long long)floor(__ddiv_rn(__dsub_rn(xd, hist.min[d]), hist.dx[d]));
+    idx = idx < 0 ? 0 : (idx > hist.n[d] - 1 ? hist.n[d] - 1 : idx);
+    lin += idx * pstride;
+    pstride *= hist.n[d];
+  }
+  if (ATOMIC)
+    atomicAdd(&hist.rec[lin * hist.rec_w], v);  // +-1.0 adds are exact: the order does not matter
+  else
+    hist.rec[lin * hist.rec_w] += v;
 }
 
 // output_hill, lib/edm_bias.cpp:586-612 (thread 0 only)
@@ -174,22 +211,8 @@ __device__ void log_event(BiasDev* st, const GridDesc& hist, edm_hill_event_t* l
   } else {
     st->log_dropped++;
   }
-  // histogram bump, lib/grid.h:370-385 on cv_hist_ (T21)
   double v = (type == 'b' || type == 'h' || type == 'n') ? 1.0 : ((type == 'u' || type == 'v') ? -1.0 : 0.0);
-  if (v != 0.0 && hist.rec) {
-    bool inside = true;
-    long long lin = 0, pstride = 1;
-    for (int d = 0; d < DIM; d++) {
-      double xd = pos[d];
-      if (!hist.periodic[d] && (xd < hist.min[d] || xd >= hist.upper[d])) inside = false;
-      if (hist.periodic[d]) xd = d_wrap(xd, hist.min[d], hist.len[d]);
-      long long idx = (long long)floor(__ddiv_rn(__dsub_rn(xd, hist.min[d]), hist.dx[d]));
-      idx = idx < 0 ? 0 : (idx > hist.n[d] - 1 ? hist.n[d] - 1 : idx);
-      lin += idx * pstride;
-      pstride *= hist.n[d];
-    }
-    if (inside) hist.rec[lin * hist.rec_w] += v;
-  }
+  if (v != 0.0) d_hist_bump<DIM, false>(hist, pos, v);
 }
 
 // Orders the accepted candidates by key (= candidate order).  Keys are unique.  Rank sort for
@@ -248,7 +271,13 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ double s_h;
   __shared__ int s_go;
   __shared__ double s_prefactor;
-  if (st->round_mode == 2) return;  // the parallel round below already committed this round
+  if (st->round_mode == 2) {  // the parallel round below already committed this round
+    if (threadIdx.x == 0) {
+      st->n_accepted_last = st->n_accepted;
+      st->n_accepted = 0;  // the next selection starts a fresh candidate list
+    }
+    return;
+  }
   const int W1 = DIM + 1;
   const bool t0 = threadIdx.x == 0;
   const double bps = prm.bias_per_step;
@@ -394,28 +423,112 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   if (t0) {
     st->cum_bias += st->temp_hill_cum;
     st->steps++;
+    st->rounds_in_order++;
+    st->n_accepted_last = st->n_accepted;
+    st->n_accepted = 0;  // the next selection starts a fresh candidate list
   }
 }
 
-// ------------------------------------------------------------------ K4: the parallel hill round (1-D)
+// ------------------------------------------------------------------ K4: the parallel hill round
 //
-// Without local well-tempering a hill's height does not depend on the bias the earlier hills of the
-// round left behind, so the round splits into: plan (order the candidates, scale the heights) ->
-// owner-computes deposit staged into scratch with every hill's integral -> decide (the limiter's
-// running sum, in candidate order) -> commit.  If the backlog is not empty or the running sum
-// reaches bias_per_step the round is left untouched and the sequential kernel above runs instead,
+// A round whose backlog is empty and whose running sum stays below bias_per_step deposits every
+// accepted hill in full, so it splits into: plan (order the candidates, scale the heights) ->
+// every hill's integral, all hills at once -> decide (the limiter's running sum, in candidate
+// order) -> deposit, all hills at once.  If the backlog is not empty or the sum reaches
+// bias_per_step, nothing has been written and the sequential kernel above runs the round instead,
 // so the limiter/undo/backlog semantics never have to be re-expressed here.
+//
+// Local well-tempering (T15) makes hill k's height read the bias left by hills < k of the round.
+// The plan resolves that exactly without depositing: the corner records of k's interpolation cell
+// are patched with h_j * term_j(corner) for every earlier hill j whose window reaches a corner, in
+// order j (the adds a sequential deposit would have made to those records), and k's height is
+// interpolated from the patched corners.  Hills with no such predecessor are scaled in parallel;
+// the others follow in order in one warp (a handful per round in 2-D/3-D, where windows are small
+// against the grid).
+//
+// 1-D: the deposit is the owner-computes kernel staged into scratch (edm_grid.cu) and committed
+// after the decision; 2-D/3-D: one CTA per hill, integrals first, fp64 REDs after the decision.
 
-__global__ void __launch_bounds__(512) round_plan_kernel(GridDesc target, RoundParams prm, int n_max, BiasDev* st,
-                                                         HillAccepted* acc, HillAccepted* acc_tmp,
-                                                         double* __restrict__ centres, double* __restrict__ heights) {
+template <int DIM> struct PlanHill {
+  HillGeom<DIM> hg;
+  int ok;            // d_hill_prepare succeeded: the hill deposits something
+  int valid;         // the centre lies inside the grid: get_value interpolates (else 0)
+  int ndep;          // earlier hills of the round whose window can reach a corner
+  int lo[DIM], up[DIM];
+  double X0[DIM];
+  double hb;         // height before the local tempering factor and the density division
+  double rec[1 << DIM][RecW<DIM>::value];
+};
+
+// can hill j's window (centre cell xi, half-width minisize) write grid index i of dim d?
+// mirrors d_window_index (lib/gaussian_grid.h:229-268)
+__device__ __forceinline__ bool d_window_reaches(const GridDesc& g, int d, int xi, int i) {
+  const int m = g.minisize[d];
+  int off = i - xi;
+  if (!g.periodic[d]) return off >= -m && off <= m;
+  const int n = g.n[d];
+  off %= n;
+  if (off < 0) off += n;                 // off in [0, n): i = xi + off (mod n)
+  if (off <= m) return true;             // reached from above the centre (xi + off may wrap once or more)
+  return off - n >= -m && xi + off - n >= -n;  // from below: the reference adds n once only
+}
+
+template <int DIM>
+__device__ __forceinline__ bool d_hill_near(const GridDesc& g, const PlanHill<DIM>& pj, const PlanHill<DIM>& pk) {
+  if (!pj.ok) return false;
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (!d_window_reaches(g, d, pj.hg.xi[d], pk.lo[d]) && !d_window_reaches(g, d, pj.hg.xi[d], pk.up[d])) return false;
+  return true;
+}
+
+template <int DIM>
+__device__ __forceinline__ double d_local_height(const GridDesc& bias, const RoundParams& prm, const double* X0,
+                                                 const double (*rec)[RecW<DIM>::value], bool valid, double hb) {
+  double v = 0.0;
+  if (valid) {
+    if (bias.b_interp && bias.b_deriv) {
+      double der[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) der[d] = 0.0;
+      v = d_interp_cell<DIM>(bias, X0, der, [&](int c, double* r) {
+#pragma unroll
+        for (int m = 0; m < RecW<DIM>::value; m++) r[m] = rec[c][m];
+      });
+    } else {
+      v = rec[0][0];
+    }
+  }
+  double h = hb * exp(-v / ((prm.bias_factor - 1) * prm.boltzmann_factor));
+  if (prm.hill_density < 0)
+    h /= (double)(int)prm.est_hill_count;
+  else
+    h /= prm.hill_density;
+  return fmin(h, 1.0 * prm.bias_per_step);  // BIAS_CLAMP, lib/edm_bias.h:14
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc target, RoundParams prm, int n_max,
+                                                         BiasDev* st, HillAccepted* acc, HillAccepted* acc_tmp,
+                                                         double* __restrict__ centres, double* heights,
+                                                         PlanHill<DIM>* plan, int4* __restrict__ cells) {
+  constexpr int W = RecW<DIM>::value;
+  constexpr int NC = 1 << DIM;
   __shared__ double s_prefactor;
   __shared__ int s_mode;
+  __shared__ double s_contrib[32][NC * W];
+  __shared__ double s_rec[NC][W];
+  const bool local = prm.b_tempering && prm.global_tempering < 0;
   if (threadIdx.x == 0) {
-    s_mode = (st->left == 0 && st->right == 0 && !st->accepted_overflow && st->n_accepted <= n_max) ? 1 : 0;
-    st->round_mode = s_mode;
+    int mode = (st->left == 0 && st->right == 0 && !st->accepted_overflow && st->n_accepted <= n_max) ? 1 : 0;
+    if (DIM > 1 && bias.dup_possible) mode = 0;    // concurrent hills would revisit points of their own window
+    if (local && bias.n_dup > 0) mode = 0;         // duplicate_boundary rewrites records between hills
+    s_mode = mode;
+    st->round_mode = mode;
+    st->ticket = 0;
+    st->round_epoch++;
     double pf = prm.hill_prefactor;
-    if (prm.global_tempering > 0) {
+    if (prm.global_tempering > 0) {  // T15: threshold tempering, lib/edm_bias.cpp:419-426
       double avg = st->cum_bias / prm.total_volume;
       if (avg >= prm.global_tempering)
         pf *= exp(-(avg - prm.global_tempering) / (prm.global_tempering * (prm.bias_factor - 1) * prm.boltzmann_factor));
@@ -431,20 +544,198 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc target, RoundP
   if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
   cta_sort_accepted(acc, acc_tmp, nacc);
   for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
-    double pos[1] = {acc[k].x[0]};
+    double pos[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      pos[d] = acc[k].x[d];
+      centres[(long)k * DIM + d] = pos[d];
+    }
     double h = s_prefactor;
-    if (prm.b_targeting) h *= exp(d_get_value<1>(target, pos) - prm.expected_target);
-    if (prm.hill_density < 0)
-      h /= (double)(int)prm.est_hill_count;
-    else
-      h /= prm.hill_density;
-    h = fmin(h, 1.0 * prm.bias_per_step);
-    centres[k] = pos[0];
-    heights[k] = h;
+    if (prm.b_targeting) h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
+    if (DIM > 1 && !local) {  // centre cells for the deposit's overlap test
+      HillGeom<DIM> hg;
+      bool ok = d_hill_prepare<DIM>(bias, pos, hg);
+      cells[k] = make_int4(hg.xi[0], hg.xi[DIM > 1 ? 1 : 0], hg.xi[DIM > 2 ? 2 : 0], ok ? 1 : 0);
+    }
+    if (!local) {
+      if (prm.hill_density < 0)
+        h /= (double)(int)prm.est_hill_count;
+      else
+        h /= prm.hill_density;
+      heights[k] = fmin(h, 1.0 * prm.bias_per_step);
+    } else {
+      PlanHill<DIM>& p = plan[k];
+      p.hb = h;
+      p.ok = d_hill_prepare<DIM>(bias, pos, p.hg) ? 1 : 0;
+      if (DIM > 1)
+        cells[k] = make_int4(p.hg.xi[0], p.hg.xi[DIM > 1 ? 1 : 0], p.hg.xi[DIM > 2 ? 2 : 0], p.ok);
+      CellLoc<DIM> L;
+      p.valid = d_locate<DIM>(bias, pos, L) ? 1 : 0;
+      if (p.valid) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          p.lo[d] = L.idx[d];
+          p.up[d] = (bias.periodic[d] && L.idx[d] == bias.n[d] - 1) ? 0 : L.idx[d] + 1;
+          p.X0[d] = L.X0[d];
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) RecLoad<W>::ld(bias.rec + (L.base + d_corner_shift<DIM>(L, c)) * W, p.rec[c]);
+      }
+    }
   }
   if (threadIdx.x == 0) st->n_fast = nacc;
+  if (!local) return;
+  __syncthreads();
+
+  // hills nobody earlier can reach: heights from the start-of-round records, all at once
+  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+    PlanHill<DIM>& p = plan[k];
+    int ndep = 0;
+    if (p.valid)
+      for (int j = 0; j < k; j++) ndep += d_hill_near<DIM>(bias, plan[j], p) ? 1 : 0;
+    p.ndep = ndep;
+    if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+
+  // the others in candidate order: patch the corner records with every earlier reaching hill
+  const int lane = threadIdx.x;
+  for (int k = 0; k < nacc; k++) {
+    const PlanHill<DIM>& p = plan[k];
+    if (p.ndep == 0) continue;
+    double accv = 0.0;
+    if (lane < NC * W) accv = p.rec[lane / W][lane % W];
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int j = j0 + lane;
+      bool near = j < k && d_hill_near<DIM>(bias, plan[j], p);
+      if (near) {
+        const double hj = heights[j];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          int idx[DIM];
+          bool reach = true;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            idx[d] = ((c >> d) & 1) ? p.up[d] : p.lo[d];
+            reach = reach && d_window_reaches(bias, d, plan[j].hg.xi[d], idx[d]);
+          }
+          double etot = 0.0, force[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) force[d] = 0.0;
+          bool cnz;
+          if (reach && !d_hill_term<DIM>(bias, plan[j].hg, idx, etot, force, cnz)) {
+            etot = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) force[d] = 0.0;
+          }
+          s_contrib[lane][c * W] = hj * etot;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) s_contrib[lane][c * W + 1 + d] = hj * force[d];
+          if (W > DIM + 1) s_contrib[lane][c * W + W - 1] = 0.0;
+        }
+      }
+      __syncwarp();
+      unsigned m = __ballot_sync(0xffffffffu, near);
+      while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        if (lane < NC * W) accv += s_contrib[src][lane];
+      }
+      __syncwarp();
+    }
+    if (lane < NC * W) s_rec[lane / W][lane % W] = accv;
+    __syncwarp();
+    if (lane == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, s_rec, true, p.hb);
+    __threadfence_block();
+    __syncwarp();
+  }
 }
 
+// add_value's integral of every planned hill, one CTA per hill (2-D/3-D)
+template <int DIM>
+__global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, const BiasDev* st,
+                                                              const double* __restrict__ centres,
+                                                              const double* __restrict__ heights,
+                                                              double* __restrict__ ba) {
+  __shared__ double red[33];
+  if (st->round_mode != 1) return;
+  const int n = st->n_fast;
+  for (int k = blockIdx.x; k < n; k += gridDim.x) {
+    double pos[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) pos[d] = centres[(long)k * DIM + d];
+    bool dirty;
+    double tot = cta_window_pass<DIM, kPassIntegrate>(bias, pos, heights[k], red, dirty);
+    if (threadIdx.x == 0) ba[k] = tot;
+  }
+}
+
+// The deposit itself once the decision fell (round_mode == 2), 2-D/3-D.  CTAs take hills by ticket,
+// in candidate order; before depositing, hill k waits for every earlier hill whose window can overlap
+// its own.  A hill only ever waits for lower tickets, which running CTAs hold, so the wait cannot
+// deadlock whatever the residency; every grid point receives its adds in candidate order — the
+// result is bit-identical to the in-order kernel and the same on every replica.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int DIM>
+__device__ __forceinline__ bool d_windows_overlap(const GridDesc& g, const int4& a, const int4& b) {
+  if (!a.w || !b.w) return false;
+  const int ca[3] = {a.x, a.y, a.z}, cb[3] = {b.x, b.y, b.z};
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    int dist = ca[d] - cb[d];
+    dist = dist < 0 ? -dist : dist;
+    if (g.periodic[d]) {
+      dist %= g.n[d];
+      dist = min(dist, g.n[d] - dist);
+    }
+    if (dist > 2 * g.minisize[d]) return false;
+  }
+  return true;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasDev* st,
+                                                            const double* __restrict__ centres,
+                                                            const double* __restrict__ heights,
+                                                            const int4* __restrict__ cells, int* flags) {
+  __shared__ double red[33];
+  __shared__ int s_k;
+  if (st->round_mode != 2) return;
+  const int n = st->n_fast;
+  const int epoch = st->round_epoch;
+  while (true) {
+    if (threadIdx.x == 0) s_k = atomicAdd(&st->ticket, 1);
+    __syncthreads();
+    const int k = s_k;
+    if (k >= n) break;
+    const int4 ck = cells[k];
+    for (int j = threadIdx.x; j < k; j += blockDim.x)
+      if (d_windows_overlap<DIM>(bias, cells[j], ck))
+        while (ld_acquire_gpu(&st->hill_done[j]) != epoch) {
+        }
+    __syncthreads();
+    double pos[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) pos[d] = centres[(long)k * DIM + d];
+    bool dirty;
+    cta_window_pass<DIM, kPassAtomic>(bias, pos, heights[k], red, dirty);
+    if (dirty) flags[0] = 1;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(&st->hill_done[k], epoch);
+  }
+}
+
+template <int DIM>
 __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundParams prm, BiasDev* st,
                                                            const double* __restrict__ centres,
                                                            const double* __restrict__ heights,
@@ -483,20 +774,16 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
     e.steps = steps;
     e.type = 'h';
     e.hills_added = k + 1;
-    e.pos[0] = centres[k];
-    e.pos[1] = 0.0;
-    e.pos[2] = 0.0;
+    double pos[DIM];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (d < DIM) pos[d] = centres[(long)k * DIM + d];
+      e.pos[d] = d < DIM ? pos[d] : 0.0;
+    }
     e.height = heights[k];
     e.bias_added = ba[k];
     e.cum_over_vol = cov;
-    if (hist.rec) {  // cv_hist_ bump: +1.0 adds are exact, so the atomic order does not matter
-      double xd = centres[k];
-      bool inside = !(!hist.periodic[0] && (xd < hist.min[0] || xd >= hist.upper[0]));
-      if (hist.periodic[0]) xd = d_wrap(xd, hist.min[0], hist.len[0]);
-      long long idx = (long long)floor(__ddiv_rn(__dsub_rn(xd, hist.min[0]), hist.dx[0]));
-      idx = idx < 0 ? 0 : (idx > hist.n[0] - 1 ? hist.n[0] - 1 : idx);
-      if (inside) atomicAdd(&hist.rec[idx * hist.rec_w], 1.0);
-    }
+    d_hist_bump<DIM, true>(hist, pos, 1.0);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -504,6 +791,7 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
     st->cum_bias += st->temp_hill_cum;
     st->steps++;
     st->round_mode = 2;
+    st->rounds_parallel++;
   }
 }
 
@@ -592,6 +880,51 @@ int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st) {
   return EDM_OK;
 }
 
+template <int DIM>
+static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& hist, const GridDesc& target,
+                            bool fast, cudaStream_t st) {
+  HillAccepted* tmp = b->d_accepted + b->accepted_cap;
+  const GridDesc& bias = b->bias->d;
+  if (fast) {
+    const long cap = b->accepted_cap;
+    // the plan is sized for the usual few hundred hills; larger rounds take the sequential path
+    const long n_max = cap < EDM_ROUND_MAX ? cap : EDM_ROUND_MAX;
+    const size_t b_dbl = (size_t)(DIM + 2) * cap * sizeof(double);
+    const size_t b_plan = ((size_t)n_max * sizeof(PlanHill<DIM>) + 15) / 16 * 16;
+    EDM_TRY(b->fast.reserve(b_dbl + b_plan + (size_t)n_max * sizeof(int4)));
+    double* centres = b->fast.as<double>();
+    double* heights = centres + (size_t)DIM * cap;
+    double* ba = heights + cap;
+    PlanHill<DIM>* plan = reinterpret_cast<PlanHill<DIM>*>(b->fast.as<char>() + b_dbl);
+    int4* cells = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan);
+    round_plan_kernel<DIM><<<1, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres,
+                                               heights, plan, cells);
+    if (DIM == 1 && deposit1d_eligible(b->bias)) {
+      EDM_TRY(deposit1d_stage(b->bias, centres, heights, ba, &b->d_state->n_fast, n_max, st));
+      round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
+      EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
+      count_launches(2);
+    } else {
+      const int blocks = (int)(n_max < 148 * 4 ? n_max : 148 * 4);
+      round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
+      round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
+      round_deposit_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
+      count_launches(4);
+      if (bias.n_dup) {
+        EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
+        count_launches(1);
+      }
+    }
+  } else {
+    reset_mode_kernel<<<1, 1, 0, st>>>(b->d_state);
+    count_launches(1);
+  }
+  count_launches(1);
+  hill_round_kernel<DIM><<<1, 512, 0, st>>>(bias, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log);
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
 // launches the hill round over whatever sits in the accepted buffer
 int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
   RoundParams rp = round_params(b, est);
@@ -599,35 +932,18 @@ int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
   memset(&none, 0, sizeof(none));
   const GridDesc& hist = b->hist ? b->hist->d : none;
   const GridDesc& target = b->target ? b->target->d : none;
-  HillAccepted* tmp = b->d_accepted + b->accepted_cap;
   const bool local_tempering = b->prm.b_tempering && b->prm.global_tempering < 0;
   static int allow_fast = -1;
   if (allow_fast < 0) allow_fast = getenv("EDM_NO_FAST_ROUND") ? 0 : 1;
-  if (allow_fast && b->prm.dim == 1 && !local_tempering && deposit1d_eligible(b->bias)) {
-    const long cap = b->accepted_cap;
-    EDM_TRY(b->fast.reserve(3 * (size_t)cap * sizeof(double)));
-    double* centres = b->fast.as<double>();
-    double* heights = centres + cap;
-    double* ba = heights + cap;
-    // the deposit grid is sized for the usual few hundred hills; larger rounds take the sequential path
-    const long n_max = cap < 2048 ? cap : 2048;
-    round_plan_kernel<<<1, 512, 0, st>>>(target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres, heights);
-    EDM_TRY(deposit1d_stage(b->bias, centres, heights, ba, &b->d_state->n_fast, n_max, st));
-    round_decide_kernel<<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
-    EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
-    count_launches(2);
-  } else {
-    reset_mode_kernel<<<1, 1, 0, st>>>(b->d_state);
-    count_launches(1);
-  }
-  count_launches(1);
+  bool fast = allow_fast != 0;
+  // 1-D windows are a sizeable fraction of the grid: with local tempering nearly every hill depends on
+  // its predecessors and the in-order kernel is the better fit
+  if (b->prm.dim == 1 && (local_tempering || !deposit1d_eligible(b->bias))) fast = false;
   switch (b->prm.dim) {
-    case 1: hill_round_kernel<1><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
-    case 2: hill_round_kernel<2><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
-    default: hill_round_kernel<3><<<1, 512, 0, st>>>(b->bias->d, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log); break;
+    case 1: return launch_round_dim<1>(b, rp, hist, target, fast, st);
+    case 2: return launch_round_dim<2>(b, rp, hist, target, fast, st);
+    default: return launch_round_dim<3>(b, rp, hist, target, fast, st);
   }
-  EDM_CUDA(cudaGetLastError());
-  return EDM_OK;
 }
 
 int edm_bias_check_round(edm_bias* b) {
@@ -727,7 +1043,7 @@ int edm_bias_state(edm_bias_t* b, edm_bias_state_t* out) {
   out->skipped = hdr.skip;
   out->backlog_left = (long)hdr.left;
   out->backlog_right = (long)hdr.right;
-  out->n_accepted = hdr.n_accepted;
+  out->n_accepted = hdr.n_accepted_last;
   out->log_dropped = hdr.log_dropped;
   return EDM_OK;
 }
@@ -933,6 +1249,16 @@ int edm_bias_post_add_hill(edm_bias_t* b) {
   EDM_TRY(edm_bias_launch_round(b, b->round_est, 0));
   EDM_CUDA(cudaDeviceSynchronize());
   return edm_bias_check_round(b);
+}
+
+int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* in_order) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  if (parallel) *parallel = hdr.rounds_parallel;
+  if (in_order) *in_order = hdr.rounds_in_order;
+  return EDM_OK;
 }
 
 int edm_bias_set_profiling(edm_bias_t* b, int on) {

@@ -114,31 +114,34 @@ template <> struct RecLoad<4> {
 };
 
 // Grid::get_value_deriv (lib/grid.h:390-446) behind GaussGrid::get_value_deriv
-// (lib/gaussian_grid.h:118-138), with interp<DIM> (lib/grid.h:52-139) restructured:
-//   tabf*C_d = tabf*a(X) + s*tabder_d*b(X)*dx   and   tabf*D_d = tabf*a'(X)*s/dx + tabder_d*c(X)
-// in 1-D (no division), one reciprocal of tabf per corner in 2-D/3-D.
+// (lib/gaussian_grid.h:118-138), in two pieces so the hill round can interpolate from corner
+// records it has patched itself: d_locate finds the cell, d_interp_cell blends its 2^DIM corners.
+
+template <int DIM> struct CellLoc {
+  long long base;         // linear index of the cell's low corner
+  long long stride[DIM];  // linear step to the upper neighbour in each dim (wraps at a periodic edge)
+  int idx[DIM];           // the low corner's grid index
+  double X0[DIM];         // fractional position inside the cell
+};
+
+// in_bounds / remap / in_grid, then get_index + multi2one (lib/gaussian_grid.h:128-135,
+// lib/grid.h:264-273, 315-325, 428-433).  False: the reference returns 0 for this point.
 template <int DIM>
-__device__ __forceinline__ double d_eval_point(const GridDesc& g, const double* xin, double* der, bool interp) {
-  constexpr int W = RecW<DIM>::value;
+__device__ __forceinline__ bool d_locate(const GridDesc& g, const double* xin, CellLoc<DIM>& L) {
   double x[DIM];
 #pragma unroll
-  for (int d = 0; d < DIM; d++) {
-    x[d] = xin[d];
-    der[d] = 0.0;
-  }
+  for (int d = 0; d < DIM; d++) x[d] = xin[d];
   if (g.is_gauss) {
     if (!d_in_bounds<DIM>(g, x)) {
       d_remap<DIM>(g, x);
-      if (!d_in_bounds<DIM>(g, x)) return 0.0;
+      if (!d_in_bounds<DIM>(g, x)) return false;
     }
   }
 #pragma unroll
   for (int d = 0; d < DIM; d++)
-    if (!g.periodic[d] && (x[d] < g.min[d] || x[d] >= g.upper[d])) return 0.0;  // in_grid (T4)
+    if (!g.periodic[d] && (x[d] < g.min[d] || x[d] >= g.upper[d])) return false;  // in_grid (T4)
 
   long long base = 0, pstride = 1;
-  long long stride[DIM];
-  double X0[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
     double xi = x[d];
@@ -149,27 +152,36 @@ __device__ __forceinline__ double d_eval_point(const GridDesc& g, const double* 
     long long hi = g.periodic[d] ? nd - 1 : nd - 2;
     idx = idx < 0 ? 0 : (idx > hi ? hi : idx);  // rounding can land one past the last cell; clamp
     double where = __dsub_rn(t, __dmul_rn((double)idx, g.dx[d]));
-    X0[d] = where * g.inv_dx[d];
-    stride[d] = (g.periodic[d] && idx == nd - 1) ? pstride * (1 - nd) : pstride;  // lib/grid.h:432-433
+    L.X0[d] = where * g.inv_dx[d];
+    L.idx[d] = (int)idx;
+    L.stride[d] = (g.periodic[d] && idx == nd - 1) ? pstride * (1 - nd) : pstride;  // lib/grid.h:432-433
     base += idx * pstride;
     pstride *= nd;
   }
-  if (!interp) {  // lib/grid.h:438-443
-    double r[W];
-    RecLoad<W>::ld(g.rec + base * W, r);
+  L.base = base;
+  return true;
+}
+
+template <int DIM> __device__ __forceinline__ long long d_corner_shift(const CellLoc<DIM>& L, int c) {
+  long long shift = 0;
 #pragma unroll
-    for (int d = 0; d < DIM; d++) der[d] = r[1 + d];
-    return r[0];
-  }
+  for (int d = 0; d < DIM; d++)
+    if ((c >> d) & 1) shift += L.stride[d];
+  return shift;
+}
+
+// interp<DIM> (lib/grid.h:52-139) restructured:
+//   tabf*C_d = tabf*a(X) + s*tabder_d*b(X)*dx   and   tabf*D_d = tabf*a'(X)*s/dx + tabder_d*c(X)
+// in 1-D (no division), one reciprocal of tabf per corner in 2-D/3-D.  load(c, r) fills r with the
+// record {V, dV/dx...} of corner c (bit d of c set = upper neighbour in dim d).
+template <int DIM, typename Load>
+__device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double* X0, double* der, Load load) {
+  constexpr int W = RecW<DIM>::value;
   double f = 0.0;
 #pragma unroll
   for (int c = 0; c < (1 << DIM); c++) {
-    long long shift = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; d++)
-      if ((c >> d) & 1) shift += stride[d];
     double r[W];
-    RecLoad<W>::ld(g.rec + (base + shift) * W, r);
+    load(c, r);
     double tabf = r[0];
     bool nz = !(fabs(tabf) < kInterpZero);  // T6
     if (DIM == 1) {
@@ -212,6 +224,25 @@ __device__ __forceinline__ double d_eval_point(const GridDesc& g, const double* 
     }
   }
   return f;
+}
+
+template <int DIM>
+__device__ __forceinline__ double d_eval_point(const GridDesc& g, const double* xin, double* der, bool interp) {
+  constexpr int W = RecW<DIM>::value;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) der[d] = 0.0;
+  CellLoc<DIM> L;
+  if (!d_locate<DIM>(g, xin, L)) return 0.0;
+  if (!interp) {  // lib/grid.h:438-443
+    double r[W];
+    RecLoad<W>::ld(g.rec + L.base * W, r);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) der[d] = r[1 + d];
+    return r[0];
+  }
+  return d_interp_cell<DIM>(g, L.X0, der, [&](int c, double* r) {
+    RecLoad<W>::ld(g.rec + (L.base + d_corner_shift<DIM>(L, c)) * W, r);
+  });
 }
 
 // Grid::get_value (lib/grid.h:343-365) behind GaussGrid::get_value (lib/gaussian_grid.h:99-116)

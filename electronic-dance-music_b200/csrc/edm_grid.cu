@@ -663,6 +663,13 @@ int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st)
   return EDM_OK;
 }
 
+int edm_grid_dup_boundary_if(edm_grid* g, const int* gate, int want, cudaStream_t st) {
+  if (!g->d.n_dup) return EDM_OK;
+  dup_boundary_kernel<<<1, 64, 0, st>>>(g->d, g->d_flags, gate, want);
+  EDM_CUDA(cudaGetLastError());
+  return EDM_OK;
+}
+
 }  // namespace edm
 
 // ------------------------------------------------------------------ C ABI: grids

@@ -41,6 +41,8 @@ bool deposit1d_eligible(const edm_grid* g);
 int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, double* ba, const int* n_dev,
                     long n_max, cudaStream_t st);
 int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st);
+// duplicate_boundary (lib/gaussian_grid.h:571-630) after a batch of hills, only if *gate == want
+int edm_grid_dup_boundary_if(edm_grid* g, const int* gate, int want, cudaStream_t st);
 void count_launches(int n);
 
 // Device scratch that grows on demand and is reused across calls (no allocation on the steady
@@ -73,6 +75,8 @@ struct HillAccepted {  // one selected candidate
   double x[3];
 };
 
+#define EDM_ROUND_MAX 2048  // hills one parallel round plans; larger rounds run in order
+
 struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/edm_bias.h:130,161-178
   double cum_bias;
   double temp_hill_cum;
@@ -87,8 +91,13 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int backlog_full;
   int round_mode;  // 0: sequential round, 1: parallel round planned, 2: parallel round committed
   int n_fast;      // hills planned by the parallel round
+  int n_accepted_last;  // candidates the last finished round consumed
+  int rounds_parallel, rounds_in_order;  // how the rounds so far ran (edm_bias_round_info)
+  int ticket;      // next hill a CTA of the parallel deposit takes
+  int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   unsigned long long n_pairs;
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
+  int hill_done[EDM_ROUND_MAX];          // parallel deposit: hill k finished in round hill_done[k]
 };
 
 struct edm_bias {

@@ -198,11 +198,45 @@ BIAS_CASES = {
              "bias_sigma 0.25 0.25",
         T=300.0, kB=0.0019872, sub=([0.0, 0.0], [8.0, 8.0]), periodic=[1, 1], skin=[0.0, 0.0], n=4000, lo=0.0, hi=8.0,
         steps=4),
+    "c3_2d_local_tempering_sparse": dict(  # windows small against the grid: most hills independent, a few chained
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 250\ndimension 2\nbox_low 0 0\nbox_high 16 16\nbias_spacing 0.03125 0.03125\n"
+             "bias_sigma 0.0625 0.0625",
+        T=300.0, kB=0.0019872, sub=([0.0, 0.0], [16.0, 16.0]), periodic=[1, 1], skin=[0.0, 0.0], n=20000, lo=-2.0,
+        hi=18.0, steps=4),
+    "2d_mcgdp_walls_threshold_tempering": dict(  # non-periodic walls: McGDP hills, out-of-bounds candidates
+        text="tempering 1\nglobal_tempering 0.00001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 150\ndimension 2\nbox_low 0 0\nbox_high 4 4\nbias_spacing 0.03125 0.03125\n"
+             "bias_sigma 0.125 0.125",
+        T=300.0, kB=0.0019872, sub=([0.0, 0.0], [4.0, 4.0]), periodic=[0, 0], skin=[0.0, 0.0], n=6000, lo=-0.5,
+        hi=4.5, steps=4),
+    "2d_limiter_cuts_the_round": dict(  # bias_per_step reached inside a round: in-order kernel takes over
+        text="tempering 0\nhill_prefactor 0.02\nbias_per_step 0.012\n"
+             "hill_density 200\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\n"
+             "bias_sigma 0.25 0.25",
+        T=1.0, kB=1.0, sub=([0.0, 0.0], [8.0, 8.0]), periodic=[1, 1], skin=[0.0, 0.0], n=5000, lo=0.0, hi=8.0,
+        steps=5),
+    "c4_3d_density": dict(
+        text="tempering 0\nhill_prefactor 0.02\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
+             "bias_spacing 0.125 0.125 0.125\nbias_sigma 0.25 0.25 0.25\nhill_density 120\nbias_per_step 1000",
+        T=1.0, kB=1.0, sub=([0.0] * 3, [8.0] * 3), periodic=[1, 1, 1], skin=[0.0] * 3, n=8000, lo=-1.0, hi=9.0, steps=3),
+    "3d_local_tempering_mixed_walls": dict(
+        text="tempering 1\nglobal_tempering -1\nbias_factor 8\nhill_prefactor 0.05\nbias_per_step 1000\n"
+             "dimension 3\nbox_low 0 0 0\nbox_high 4 4 4\nbias_spacing 0.125 0.125 0.125\n"
+             "bias_sigma 0.25 0.25 0.25\nhill_density 80",
+        T=300.0, kB=0.0019872, sub=([0.0] * 3, [4.0] * 3), periodic=[1, 0, 1], skin=[0.0] * 3, n=3000, lo=0.0, hi=4.0,
+        steps=3),
     "3d_all_candidates_deposit": dict(
         text="tempering 0\nhill_prefactor 1.0\nbias_per_step 0.4\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
              "bias_spacing 0.25 0.25 0.25\nbias_sigma 0.5 0.5 0.5",
         T=1.0, kB=1.0, sub=([0.0] * 3, [8.0] * 3), periodic=[1, 1, 1], skin=[0.0] * 3, n=40, lo=0.0, hi=8.0, steps=4),
 }
+
+
+# rounds that must have run as parallel rounds (the others: backlog / limiter / 1-D local tempering)
+PARALLEL_ROUND_CASES = {"c1_sanity_density": 1, "c2_rdf_threshold_tempering": 6, "2d_local_well_tempering": 4,
+                        "c3_2d_local_tempering_sparse": 4, "2d_mcgdp_walls_threshold_tempering": 4,
+                        "c4_3d_density": 3, "3d_local_tempering_mixed_walls": 3}
 
 
 def run_bias_case(edm, port, tmp_path, name, masked=False):
@@ -269,6 +303,10 @@ def test_bias_round_parity(edm, port, tmp_path, name):
     bd, bo = run_bias_case(edm, port, tmp_path, name)
     log = compare_bias(bd, bo)
     assert len(log) > 0
+    info = bd.round_info()
+    assert info["parallel"] + info["in_order"] == BIAS_CASES[name]["steps"]
+    if name in PARALLEL_ROUND_CASES:   # the all-hills-at-once round really ran (and fell back where it must)
+        assert info["parallel"] >= PARALLEL_ROUND_CASES[name], info
 
 
 def test_bias_backlog_exercised(edm, port, tmp_path):
