@@ -559,10 +559,11 @@ def run_coord(args, rank, local_rank, world):
 
     # ---- e2e through the host-buffer C ABI: update_forces + add_hills on pinned host arrays
     def step_e2e(step):
-        xh = xs_host[step % n_sets]
+        dp = C.POINTER(C.c_double)
+        xh = C.cast(xs_host[step % n_sets].data_ptr(), dp)
         e = C.c_double(0)
-        edm.check(L.edm_bias_update_forces(bias.h, n_atoms, xh.data_ptr(), D, f_host.data_ptr(), D, None, -1, C.byref(e)))
-        edm.check(L.edm_bias_add_hills(bias.h, n_atoms, xh.data_ptr(), D, None, None, -1, seed, step))
+        edm.check(L.edm_bias_update_forces(bias.h, n_atoms, xh, D, C.cast(f_host.data_ptr(), dp), D, None, -1, C.byref(e)))
+        edm.check(L.edm_bias_add_hills(bias.h, n_atoms, xh, D, None, None, -1, seed, step))
         return e.value
 
     e2e_ms = None
@@ -606,6 +607,7 @@ def run_coord(args, rank, local_rank, world):
                        "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
             "step_breakdown_ms": {"update_forces": k1, "hill_round": rnd},
             "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],
+                      "rounds_split": info1["split"] - info0["split"],
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},
             "roofline": {"bound": "hbm", "kernel": "forces_kernel<%d>" % D, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -195,24 +195,33 @@ __device__ __forceinline__ void d_hist_bump(const GridDesc& hist, const double* 
     hist.rec[lin * hist.rec_w] += v;
 }
 
+// The scalars of BiasDev a round reads and writes, held in shared memory while the in-order kernel
+// runs: thread 0 walks the round's state machine on this copy (a dependent global load per field
+// per hill was most of the kernel's time) and writes it back once at the end.
+struct RoundState {
+  double cum_bias, temp_hill_cum;
+  long long steps, left, right;
+  int hills_added, log_n, log_dropped, backlog_full, skip;
+};
+
 // output_hill, lib/edm_bias.cpp:586-612 (thread 0 only)
 template <int DIM>
-__device__ void log_event(BiasDev* st, const GridDesc& hist, edm_hill_event_t* log, long log_cap, const double* pos,
+__device__ void log_event(RoundState& rs, const GridDesc& hist, edm_hill_event_t* log, long log_cap, const double* pos,
                           double height, double bias_added, int type, double total_volume) {
-  if (st->log_n < log_cap) {
-    edm_hill_event_t& e = log[st->log_n++];
-    e.steps = st->steps;
+  if (rs.log_n < log_cap) {
+    edm_hill_event_t& e = log[rs.log_n++];
+    e.steps = rs.steps;
     e.type = type;
-    e.hills_added = st->hills_added;
+    e.hills_added = rs.hills_added;
     for (int d = 0; d < 3; d++) e.pos[d] = d < DIM ? pos[d] : 0.0;
     e.height = height;
     e.bias_added = bias_added;
-    e.cum_over_vol = st->cum_bias / total_volume;
+    e.cum_over_vol = rs.cum_bias / total_volume;
   } else {
-    st->log_dropped++;
+    rs.log_dropped++;
   }
   double v = (type == 'b' || type == 'h' || type == 'n') ? 1.0 : ((type == 'u' || type == 'v') ? -1.0 : 0.0);
-  if (v != 0.0) d_hist_bump<DIM, false>(hist, pos, v);
+  if (v != 0.0) d_hist_bump<DIM, true>(hist, pos, v);  // a RED: nothing waits for the old count
 }
 
 // Orders the accepted candidates by key (= candidate order).  Keys are unique.  Rank sort for
@@ -261,6 +270,10 @@ __device__ void cta_sort_accepted(HillAccepted* a, HillAccepted* tmp, int n) {
 // sequence; the work inside each step (a hill's window, the sort) is spread over its threads.
 // Sequential on purpose: with local well-tempering hill k's height reads the bias left by hills
 // < k, and the limiter is a running sum with an undo ("Hard parts").
+// round_mode on entry: 0 = the whole round is this kernel's; 2 = the parallel round committed it;
+// 3 = the parallel round committed entries [0, n_fast) of its list (n_plan_b backlog slots, then the
+// candidates) — every one a plain full deposit — and this kernel resumes at entry n_fast, the first
+// at which the running sum reaches bias_per_step.
 template <int DIM>
 __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc hist, GridDesc target,
                                                           RoundParams prm, BiasDev* st, HillAccepted* acc,
@@ -271,7 +284,9 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ double s_h;
   __shared__ int s_go;
   __shared__ double s_prefactor;
-  if (st->round_mode == 2) {  // the parallel round below already committed this round
+  __shared__ RoundState rs;
+  const int mode = st->round_mode;
+  if (mode == 2) {  // the parallel round already committed this round
     if (threadIdx.x == 0) {
       st->n_accepted_last = st->n_accepted;
       st->n_accepted = 0;  // the next selection starts a fresh candidate list
@@ -284,26 +299,34 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
 
   // ---- pre_add_hill
   if (t0) {
+    rs.cum_bias = st->cum_bias;
+    rs.steps = st->steps;
+    rs.left = st->left;
+    rs.right = st->right;
+    rs.log_n = st->log_n;
+    rs.log_dropped = st->log_dropped;
+    rs.backlog_full = st->backlog_full;
+    rs.temp_hill_cum = 0.0;
+    rs.hills_added = mode == 3 ? st->hills_added : 0;
+    rs.skip = 0;
     double pf = prm.hill_prefactor;
     if (prm.global_tempering > 0) {  // T15: threshold tempering
-      double avg = st->cum_bias / prm.total_volume;
+      double avg = rs.cum_bias / prm.total_volume;
       if (avg >= prm.global_tempering)
         pf *= exp(-(avg - prm.global_tempering) /
                   (prm.global_tempering * (prm.bias_factor - 1) * prm.boltzmann_factor));
     }
     s_prefactor = pf;
-    st->temp_hill_cum = 0.0;
-    st->hills_added = 0;
   }
   __syncthreads();
 
-  // ---- flush_bias_buffer(bias_per_step)
-  double drained = 0.0;  // meaningful on thread 0
+  // ---- flush_bias_buffer(bias_per_step); in mode 3 the first n_fast slots are already drained
+  double drained = mode == 3 ? st->temp_hill_cum : 0.0;  // meaningful on thread 0
   while (true) {
     if (t0) {
-      s_go = (st->left < st->right) ? 1 : 0;
+      s_go = (rs.left < rs.right) ? 1 : 0;
       if (s_go) {
-        const double* slot = &st->overflow[st->left * W1];
+        const double* slot = &st->overflow[rs.left * W1];
         for (int d = 0; d < DIM; d++) s_pos[d] = slot[d];
         s_h = slot[DIM];
       }
@@ -315,13 +338,13 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
     double h = s_h;
     double temp = cta_deposit<DIM>(bias, pos, h, red, &sflag);
     if (t0) {
-      st->hills_added++;
+      rs.hills_added++;
       drained += temp;
-      log_event<DIM>(st, hist, log, prm.log_cap, pos, h, temp, 'b', prm.total_volume);
+      log_event<DIM>(rs, hist, log, prm.log_cap, pos, h, temp, 'b', prm.total_volume);
       s_go = 0;
       if (drained > bps) {
         double hh = fmax(bps - drained, -h);  // T20
-        st->overflow[st->left * W1 + DIM] = -hh;
+        st->overflow[rs.left * W1 + DIM] = -hh;
         s_h = hh;
         s_go = 1;
       }
@@ -331,31 +354,37 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
       double hh = s_h;
       double t2 = cta_deposit<DIM>(bias, pos, hh, red, &sflag);
       if (t0) {
-        log_event<DIM>(st, hist, log, prm.log_cap, pos, hh, t2, 'v', prm.total_volume);
-        st->hills_added++;
+        log_event<DIM>(rs, hist, log, prm.log_cap, pos, hh, t2, 'v', prm.total_volume);
+        rs.hills_added++;
         drained += t2;
       }
       break;  // uniform: s_go is shared
     }
-    if (t0) st->left++;
+    if (t0) rs.left++;
     __syncthreads();
   }
   __syncthreads();
   if (t0) {
-    if (st->left == st->right) st->left = st->right = 0;
-    st->temp_hill_cum += drained;
-    st->skip = (st->left == 0 && st->right == 0) ? 0 : 1;  // T18
+    if (rs.left == rs.right) rs.left = rs.right = 0;
+    rs.temp_hill_cum += drained;
+    rs.skip = (rs.left == 0 && rs.right == 0) ? 0 : 1;  // T18
   }
   __syncthreads();
 
   // ---- add_hill for every accepted candidate, in candidate order
   int nacc = st->n_accepted;
   if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
-  if (!st->skip && nacc > 0) {
-    cta_sort_accepted(acc, acc_tmp, nacc);
-    for (int k = 0; k < nacc; k++) {
+  int k_first = mode == 3 ? st->n_fast - st->n_plan_b : 0;  // planned entries: backlog slots, then candidates
+  if (k_first < 0) k_first = 0;
+  if (!rs.skip && nacc > k_first) {
+    if (mode == 0) cta_sort_accepted(acc, acc_tmp, nacc);  // mode 3: the plan already ordered them
+    double nxt[DIM];
+    for (int d = 0; d < DIM; d++) nxt[d] = acc[k_first].x[d];
+    for (int k = k_first; k < nacc; k++) {
       double pos[DIM];
-      for (int d = 0; d < DIM; d++) pos[d] = acc[k].x[d];
+      for (int d = 0; d < DIM; d++) pos[d] = nxt[d];
+      if (k + 1 < nacc)  // the next centre travels while this hill is worked on
+        for (int d = 0; d < DIM; d++) nxt[d] = acc[k + 1].x[d];
       if (t0) {
         double this_h = s_prefactor;
         if (prm.b_targeting) this_h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
           this_h /= prm.hill_density;
         this_h = fmin(this_h, 1.0 * bps);  // BIAS_CLAMP, lib/edm_bias.h:14
         s_h = this_h;
-        s_go = (st->temp_hill_cum < bps) ? 1 : 0;
+        s_go = (rs.temp_hill_cum < bps) ? 1 : 0;
       }
       __syncthreads();
       double this_h = s_h;
@@ -375,12 +404,12 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
       if (s_go) {
         double ba = cta_deposit<DIM>(bias, pos, this_h, red, &sflag);
         if (t0) {
-          st->temp_hill_cum += ba;
-          st->hills_added++;
-          log_event<DIM>(st, hist, log, prm.log_cap, pos, this_h, ba, 'h', prm.total_volume);
+          rs.temp_hill_cum += ba;
+          rs.hills_added++;
+          log_event<DIM>(rs, hist, log, prm.log_cap, pos, this_h, ba, 'h', prm.total_volume);
           s_go = 0;
-          if (st->temp_hill_cum > bps) {
-            s_h = fmax(bps - st->temp_hill_cum, -this_h);  // T20
+          if (rs.temp_hill_cum > bps) {
+            s_h = fmax(bps - rs.temp_hill_cum, -this_h);  // T20
             s_go = 1;
           }
         }
@@ -389,30 +418,30 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
           double temp_h = s_h;
           double ba2 = cta_deposit<DIM>(bias, pos, temp_h, red, &sflag);
           if (t0) {
-            st->hills_added++;
-            log_event<DIM>(st, hist, log, prm.log_cap, pos, temp_h, ba2, 'u', prm.total_volume);
-            st->temp_hill_cum += ba2;
+            rs.hills_added++;
+            log_event<DIM>(rs, hist, log, prm.log_cap, pos, temp_h, ba2, 'u', prm.total_volume);
+            rs.temp_hill_cum += ba2;
             buffer_flag = 1;
             this_h = -temp_h;
           }
         }
       } else if (t0) {
-        log_event<DIM>(st, hist, log, prm.log_cap, pos, 0.0, 0.0, 'h', prm.total_volume);
+        log_event<DIM>(rs, hist, log, prm.log_cap, pos, 0.0, 0.0, 'h', prm.total_volume);
         buffer_flag = 1;
       }
       if (t0 && buffer_flag) {  // lib/edm_bias.cpp:498-523 incl. the off-by-one push (T19)
-        if (st->right == EDM_BUFFER_SLOTS) {
-          if (st->left == 0) {
-            st->backlog_full = 1;  // the reference aborts here
+        if (rs.right == EDM_BUFFER_SLOTS) {
+          if (rs.left == 0) {
+            rs.backlog_full = 1;  // the reference aborts here
           } else {
-            st->left--;
-            for (int d = 0; d < DIM; d++) st->overflow[st->left * W1 + d] = pos[d];
-            st->overflow[st->left * W1 + DIM] = this_h;
+            rs.left--;
+            for (int d = 0; d < DIM; d++) st->overflow[rs.left * W1 + d] = pos[d];
+            st->overflow[rs.left * W1 + DIM] = this_h;
           }
         } else {
-          st->right++;
-          for (int d = 0; d < DIM; d++) st->overflow[st->right * W1 + d] = pos[d];
-          st->overflow[st->right * W1 + DIM] = this_h;
+          rs.right++;
+          for (int d = 0; d < DIM; d++) st->overflow[rs.right * W1 + d] = pos[d];
+          st->overflow[rs.right * W1 + DIM] = this_h;
         }
       }
       __syncthreads();
@@ -421,9 +450,20 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __syncthreads();
   // ---- post_add_hill (serial build: no exchange), update_height (T22)
   if (t0) {
-    st->cum_bias += st->temp_hill_cum;
-    st->steps++;
-    st->rounds_in_order++;
+    st->cum_bias = rs.cum_bias + rs.temp_hill_cum;
+    st->temp_hill_cum = rs.temp_hill_cum;
+    st->steps = rs.steps + 1;
+    st->left = rs.left;
+    st->right = rs.right;
+    st->hills_added = rs.hills_added;
+    st->skip = rs.skip;
+    st->log_n = rs.log_n;
+    st->log_dropped = rs.log_dropped;
+    st->backlog_full = rs.backlog_full;
+    if (mode == 3)
+      st->rounds_split++;
+    else
+      st->rounds_in_order++;
     st->n_accepted_last = st->n_accepted;
     st->n_accepted = 0;  // the next selection starts a fresh candidate list
   }
@@ -431,12 +471,14 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
 
 // ------------------------------------------------------------------ K4: the parallel hill round
 //
-// A round whose backlog is empty and whose running sum stays below bias_per_step deposits every
-// accepted hill in full, so it splits into: plan (order the candidates, scale the heights) ->
-// every hill's integral, all hills at once -> decide (the limiter's running sum, in candidate
-// order) -> deposit, all hills at once.  If the backlog is not empty or the sum reaches
-// bias_per_step, nothing has been written and the sequential kernel above runs the round instead,
-// so the limiter/undo/backlog semantics never have to be re-expressed here.
+// A round is a list of deposits in a fixed order: the backlog slots flush_bias_buffer drains first,
+// then the accepted candidates.  As long as the running sum stays below bias_per_step every entry is
+// a plain full deposit whose height is known up front, so the round splits into: plan (order the
+// candidates, scale the heights) -> every entry's integral, all at once -> decide (the running sum,
+// in list order: how long is the plain prefix?) -> deposit the prefix, all at once.  The first entry
+// at which the sum reaches bias_per_step — the undo hill, the push to the backlog, the skipped rest —
+// is left to the in-order kernel above, which resumes exactly there (round_mode 3), so the
+// limiter/undo/backlog semantics are never re-expressed here.
 //
 // Local well-tempering (T15) makes hill k's height read the bias left by hills < k of the round.
 // The plan resolves that exactly without depositing: the corner records of k's interpolation cell
@@ -518,9 +560,16 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   __shared__ int s_mode;
   __shared__ double s_contrib[32][NC * W];
   __shared__ double s_rec[NC][W];
+  __shared__ int s_nb;
   const bool local = prm.b_tempering && prm.global_tempering < 0;
+  const int W1 = DIM + 1;
   if (threadIdx.x == 0) {
-    int mode = (st->left == 0 && st->right == 0 && !st->accepted_overflow && st->n_accepted <= n_max) ? 1 : 0;
+    // the planned list: the backlog slots [left, right) first (flush_bias_buffer drains them before
+    // any new hill, lib/edm_bias.cpp:432), then the accepted candidates
+    const long long nb = st->right - st->left;
+    int mode = (!st->accepted_overflow && nb + st->n_accepted <= n_max) ? 1 : 0;
+    s_nb = (int)nb;
+    st->n_plan_b = (int)nb;
     if (DIM > 1 && bias.dup_possible) mode = 0;    // concurrent hills would revisit points of their own window
     if (local && bias.n_dup > 0) mode = 0;         // duplicate_boundary rewrites records between hills
     s_mode = mode;
@@ -543,15 +592,23 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   int nacc = st->n_accepted;
   if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
   cta_sort_accepted(acc, acc_tmp, nacc);
-  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+  const int nb = s_nb;
+  const int nall = nb + nacc;
+  const long long left = st->left;
+  for (int k = threadIdx.x; k < nall; k += blockDim.x) {
     double pos[DIM];
+    const bool slot = k < nb;  // a backlog slot: its height is what the slot holds
+    const double* src = slot ? &st->overflow[(left + k) * W1] : acc[k - nb].x;
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
-      pos[d] = acc[k].x[d];
+      pos[d] = src[d];
       centres[(long)k * DIM + d] = pos[d];
     }
     double h = s_prefactor;
-    if (prm.b_targeting) h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
+    if (slot)
+      heights[k] = src[DIM];
+    else if (prm.b_targeting)
+      h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
     if (DIM > 1 && !local) {  // centre cells for the deposit's overlap test
       HillGeom<DIM> hg;
       bool ok = d_hill_prepare<DIM>(bias, pos, hg);
@@ -562,7 +619,7 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
         h /= (double)(int)prm.est_hill_count;
       else
         h /= prm.hill_density;
-      heights[k] = fmin(h, 1.0 * prm.bias_per_step);
+      if (!slot) heights[k] = fmin(h, 1.0 * prm.bias_per_step);
     } else {
       PlanHill<DIM>& p = plan[k];
       p.hb = h;
@@ -583,12 +640,12 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       }
     }
   }
-  if (threadIdx.x == 0) st->n_fast = nacc;
+  if (threadIdx.x == 0) st->n_fast = nall;
   if (!local) return;
   __syncthreads();
 
   // hills nobody earlier can reach: heights from the start-of-round records, all at once
-  for (int k = threadIdx.x; k < nacc; k += blockDim.x) {
+  for (int k = nb + threadIdx.x; k < nall; k += blockDim.x) {
     PlanHill<DIM>& p = plan[k];
     int ndep = 0;
     if (p.valid)
@@ -601,7 +658,7 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
 
   // the others in candidate order: patch the corner records with every earlier reaching hill
   const int lane = threadIdx.x;
-  for (int k = 0; k < nacc; k++) {
+  for (int k = nb; k < nall; k++) {
     const PlanHill<DIM>& p = plan[k];
     if (p.ndep == 0) continue;
     double accv = 0.0;
@@ -671,7 +728,7 @@ __global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, con
   }
 }
 
-// The deposit itself once the decision fell (round_mode == 2), 2-D/3-D.  CTAs take hills by ticket,
+// The deposit itself once the decision fell (round_mode 2 or 3: hills [0, n_fast)), 2-D/3-D.  CTAs take hills by ticket,
 // in candidate order; before depositing, hill k waits for every earlier hill whose window can overlap
 // its own.  A hill only ever waits for lower tickets, which running CTAs hold, so the wait cannot
 // deadlock whatever the residency; every grid point receives its adds in candidate order — the
@@ -709,7 +766,7 @@ __global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasD
                                                             const int4* __restrict__ cells, int* flags) {
   __shared__ double red[33];
   __shared__ int s_k;
-  if (st->round_mode != 2) return;
+  if (st->round_mode < 2) return;
   const int n = st->n_fast;
   const int epoch = st->round_epoch;
   while (true) {
@@ -740,39 +797,63 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
                                                            const double* __restrict__ centres,
                                                            const double* __restrict__ heights,
                                                            const double* __restrict__ ba, edm_hill_event_t* log) {
-  __shared__ int s_ok, s_mode;
+  __shared__ int s_take, s_mode, s_nb;
   if (threadIdx.x == 0) s_mode = st->round_mode;
   __syncthreads();
   if (s_mode != 1) return;
   const int n = st->n_fast;
   if (threadIdx.x == 0) {
-    // the limiter's running sum, lib/edm_bias.cpp:465-474, in candidate order
+    // Entries [0, take) of the planned list are plain full deposits.  Backlog slots first
+    // (flush_bias_buffer, lib/edm_bias.cpp:313-380): a slot is plain unless the drained sum exceeds
+    // bias_per_step after it.  Then, only if the backlog emptied (T18), the new hills (the limiter's
+    // running sum, lib/edm_bias.cpp:465-474): plain while the sum stays below bias_per_step before
+    // and after the hill.  The first entry that is not plain, and everything behind it, is the
+    // in-order kernel's.
+    const int nb = st->n_plan_b;
     double cum = 0.0;
-    int ok = 1;
-    for (int k = 0; k < n; k++) {
-      if (!(cum < prm.bias_per_step)) ok = 0;
-      cum += ba[k];
-      if (!(cum < prm.bias_per_step)) ok = 0;
+    int take = 0;
+    bool drained_all = true;
+    for (; take < nb; take++) {
+      const double next = cum + ba[take];
+      if (next > prm.bias_per_step) {
+        drained_all = false;
+        break;
+      }
+      cum = next;
     }
-    if (st->log_n + n > prm.log_cap) ok = 0;
-    s_ok = ok;
-    if (ok) {
+    if (drained_all)
+      for (; take < n; take++) {
+        const double next = cum + ba[take];
+        if (!(cum < prm.bias_per_step) || !(next < prm.bias_per_step)) break;
+        cum = next;
+      }
+    if (st->log_n + take > prm.log_cap) take = 0;
+    s_take = take;
+    s_nb = nb;
+    if (take > 0) {
       st->temp_hill_cum = cum;
-      st->hills_added = n;
+      st->hills_added = take;
       st->skip = 0;
+      st->n_fast = take;
+      if (take >= nb)
+        st->left = st->right = 0;
+      else
+        st->left += take;
     } else {
       st->round_mode = 0;
+      st->n_fast = 0;
     }
   }
   __syncthreads();
-  if (!s_ok) return;
+  const int take = s_take;
+  if (take == 0) return;
   const double cov = st->cum_bias / prm.total_volume;
   const int base = st->log_n;
   const long long steps = st->steps;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  for (int k = threadIdx.x; k < take; k += blockDim.x) {
     edm_hill_event_t& e = log[base + k];
     e.steps = steps;
-    e.type = 'h';
+    e.type = k < s_nb ? 'b' : 'h';
     e.hills_added = k + 1;
     double pos[DIM];
 #pragma unroll
@@ -787,11 +868,15 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    st->log_n = base + n;
-    st->cum_bias += st->temp_hill_cum;
-    st->steps++;
-    st->round_mode = 2;
-    st->rounds_parallel++;
+    st->log_n = base + take;
+    if (take == n) {  // post_add_hill; otherwise the in-order kernel finishes the round
+      st->cum_bias += st->temp_hill_cum;
+      st->steps++;
+      st->round_mode = 2;
+      st->rounds_parallel++;
+    } else {
+      st->round_mode = 3;
+    }
   }
 }
 
@@ -899,17 +984,18 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     int4* cells = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan);
     round_plan_kernel<DIM><<<1, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres,
                                                heights, plan, cells);
+    const int blocks = (int)(n_max < 148 * 4 ? n_max : 148 * 4);
+    round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
+    round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
+    count_launches(3);
     if (DIM == 1 && deposit1d_eligible(b->bias)) {
-      EDM_TRY(deposit1d_stage(b->bias, centres, heights, ba, &b->d_state->n_fast, n_max, st));
-      round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
+      // owner-computes deposit of hills [0, n_fast): staged from the stored values, written back if the
+      // round was committed (n_fast = 0 stages the stored values themselves)
+      EDM_TRY(deposit1d_stage(b->bias, centres, heights, nullptr, &b->d_state->n_fast, n_max, st));
       EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
-      count_launches(2);
     } else {
-      const int blocks = (int)(n_max < 148 * 4 ? n_max : 148 * 4);
-      round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
-      round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
       round_deposit_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
-      count_launches(4);
+      count_launches(1);
       if (bias.n_dup) {
         EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
         count_launches(1);
@@ -1251,12 +1337,13 @@ int edm_bias_post_add_hill(edm_bias_t* b) {
   return edm_bias_check_round(b);
 }
 
-int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* in_order) {
+int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* split, long long* in_order) {
   EDM_REQUIRE(b != nullptr, "NULL argument");
   EDM_TRY(ensure_device(b->device));
   BiasDev hdr;
   EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
   if (parallel) *parallel = hdr.rounds_parallel;
+  if (split) *split = hdr.rounds_split;
   if (in_order) *in_order = hdr.rounds_in_order;
   return EDM_OK;
 }

@@ -340,7 +340,7 @@ template <int DIM> __global__ void remap_kernel(GridDesc g, double* x) {
 
 // duplicate_boundary, lib/gaussian_grid.h:571-630 (T13: values only)
 __global__ void dup_boundary_kernel(GridDesc g, int* flags, const int* __restrict__ gate, int want) {
-  if (gate && *gate != want) return;
+  if (gate && *gate < want) return;
   if (flags[0] == 0) return;
   for (int k = threadIdx.x; k < g.n_dup; k += blockDim.x)
     g.rec[g.dup_pairs[2 * k] * g.rec_w] = g.rec[g.dup_pairs[2 * k + 1] * g.rec_w];
@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
 
 __global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* __restrict__ partial,
                                         const int* __restrict__ flag, int want) {
-  if (flag && *flag != want) return;
+  if (flag && *flag < want) return;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.n[0]) return;
   double v = 0.0, dv = 0.0;
@@ -635,7 +635,7 @@ int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, d
   Hill1D* hl = reinterpret_cast<Hill1D*>(basep);
   double* partial = reinterpret_cast<double*>(basep + b_h);
   double* slots = reinterpret_cast<double*>(basep + b_h + b_p);
-  EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
+  if (ba) EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
   deposit1d_prepare_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(d, n_max, n_dev, centres, heights, hl);
   long chunk = (n_max + 31) / 32 * 32;
   dim3 grid((nwarps + 3) / 4, 1);
@@ -643,9 +643,9 @@ int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, d
     deposit1d_owner_kernel<true><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
   else
     deposit1d_owner_kernel<false><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
-  deposit1d_ba_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(n_max, n_dev, nslot, slots, ba);
+  if (ba) deposit1d_ba_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(n_max, n_dev, nslot, slots, ba);
   g->stage_partial = partial;
-  count_launches(3);
+  count_launches(ba ? 3 : 2);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }

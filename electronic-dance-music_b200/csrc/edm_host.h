@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int ensure_device(int device);
 // 1-D owner-computes deposit split in two so a caller can decide between them (edm_grid.cu):
 // stage = prepare + accumulate into scratch (+ per-hill integrals), commit = write the grid back
-// only if *flag == want.  n is read from *n_dev (clamped to n_max) when n_dev is not NULL.
+// only if *flag >= want.  n is read from *n_dev (clamped to n_max) when n_dev is not NULL.
 bool deposit1d_eligible(const edm_grid* g);
 int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, double* ba, const int* n_dev,
                     long n_max, cudaStream_t st);
@@ -89,10 +89,11 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int log_n;
   int log_dropped;
   int backlog_full;
-  int round_mode;  // 0: sequential round, 1: parallel round planned, 2: parallel round committed
-  int n_fast;      // hills planned by the parallel round
+  int round_mode;  // 0: in-order round, 1: parallel round planned, 2: committed in full, 3: committed hills [0, n_fast)
+  int n_fast;      // entries planned, then committed, by the parallel round
+  int n_plan_b;    // how many of the planned entries are backlog slots (they come first)
   int n_accepted_last;  // candidates the last finished round consumed
-  int rounds_parallel, rounds_in_order;  // how the rounds so far ran (edm_bias_round_info)
+  int rounds_parallel, rounds_split, rounds_in_order;  // how the rounds so far ran (edm_bias_round_info)
   int ticket;      // next hill a CTA of the parallel deposit takes
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   unsigned long long n_pairs;

@@ -107,7 +107,7 @@ EXPORTS = {
     "edm_bias_profile_ms": (C.c_int, [vp, c_dp]),
     "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
     "edm_pair_search_info": (C.c_int, [vp, c_ip, c_dp, C.POINTER(C.c_longlong)]),
-    "edm_bias_round_info": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "edm_bias_round_info": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "edm_bias_hills_commit_dev": (C.c_int, [vp, vp, C.c_int, C.c_long, C.c_longlong, vp]),
 }
 
@@ -376,9 +376,9 @@ class Bias:
         return dict(bricks=tuple(bd), density_scale=sc.value, fallbacks=fb.value)
 
     def round_info(self):
-        a, b = C.c_longlong(0), C.c_longlong(0)
-        check(self.L.edm_bias_round_info(self.h, C.byref(a), C.byref(b)))
-        return dict(parallel=a.value, in_order=b.value)
+        a, m, b = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        check(self.L.edm_bias_round_info(self.h, C.byref(a), C.byref(m), C.byref(b)))
+        return dict(parallel=a.value, split=m.value, in_order=b.value)
 
     def pair_step_list(self, x, f, nlocal, ilist, first, jlist, do_hills=False, est=0, runiform=None, seed=0, step=0,
                        types=None, itype=0, jtype=0):

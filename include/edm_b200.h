@@ -238,11 +238,12 @@ int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms);
  * kernel (both 0 when the generic search ran). */
 int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms);
 
-/* How the hill rounds so far ran: `parallel` rounds planned, integrated and deposited all hills at
- * once; `in_order` rounds walked pre_add_hill / add_hill / post_add_hill hill by hill (backlog not
- * empty, bias_per_step reached inside the round, or a 1-D grid with local tempering).  Same results
- * either way.  Outputs may be NULL. */
-int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* in_order);
+/* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
+ * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,
+ * the rest of the round hill by hill.  `in_order`: pre_add_hill / add_hill / post_add_hill walked
+ * hill by hill (backlog not empty, or a 1-D grid with local tempering).  Same results either way.
+ * Outputs may be NULL. */
+int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* split, long long* in_order);
 
 #ifdef __cplusplus
 }

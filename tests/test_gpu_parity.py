@@ -234,7 +234,8 @@ BIAS_CASES = {
 
 
 # rounds that must have run as parallel rounds (the others: backlog / limiter / 1-D local tempering)
-PARALLEL_ROUND_CASES = {"c1_sanity_density": 1, "c2_rdf_threshold_tempering": 6, "2d_local_well_tempering": 4,
+PARALLEL_ROUND_CASES = {"c1_sanity_density": 6, "c5_rdf_tight_limiter_backlog": 10, "2d_limiter_cuts_the_round": 4,
+                         "c2_rdf_threshold_tempering": 6, "2d_local_well_tempering": 4,
                         "c3_2d_local_tempering_sparse": 4, "2d_mcgdp_walls_threshold_tempering": 4,
                         "c4_3d_density": 3, "3d_local_tempering_mixed_walls": 3}
 
@@ -304,9 +305,9 @@ def test_bias_round_parity(edm, port, tmp_path, name):
     log = compare_bias(bd, bo)
     assert len(log) > 0
     info = bd.round_info()
-    assert info["parallel"] + info["in_order"] == BIAS_CASES[name]["steps"]
+    assert info["parallel"] + info["split"] + info["in_order"] == BIAS_CASES[name]["steps"]
     if name in PARALLEL_ROUND_CASES:   # the all-hills-at-once round really ran (and fell back where it must)
-        assert info["parallel"] >= PARALLEL_ROUND_CASES[name], info
+        assert info["parallel"] + info["split"] >= PARALLEL_ROUND_CASES[name], info
 
 
 def test_bias_backlog_exercised(edm, port, tmp_path):
