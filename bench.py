@@ -557,13 +557,13 @@ def run_coord(args, rank, local_rank, world):
     round_ms = [e[1].elapsed_time(e[2]) for e in ev]
     total_ms = float(sum(k1_ms) + sum(round_ms))
 
-    # ---- e2e through the host-buffer C ABI: update_forces + add_hills on pinned host arrays
+    # ---- e2e through the host-buffer C ABI: edm_bias_step_coords (update_forces + add_hills) on pinned host arrays
     def step_e2e(step):
         dp = C.POINTER(C.c_double)
         xh = C.cast(xs_host[step % n_sets].data_ptr(), dp)
         e = C.c_double(0)
-        edm.check(L.edm_bias_update_forces(bias.h, n_atoms, xh, D, C.cast(f_host.data_ptr(), dp), D, None, -1, C.byref(e)))
-        edm.check(L.edm_bias_add_hills(bias.h, n_atoms, xh, D, None, None, -1, seed, step))
+        edm.check(L.edm_bias_step_coords(bias.h, n_atoms, xh, D, C.cast(f_host.data_ptr(), dp), D, None, -1, 1, None,
+                                         seed, step, C.byref(e)))
         return e.value
 
     e2e_ms = None
@@ -618,7 +618,7 @@ def run_coord(args, rank, local_rank, world):
         }
         if e2e_ms is not None:
             out["e2e"] = {"value": n_atoms / (e2e_ms * 1e-3), "unit": "evals/s",
-                          "h2d_bytes_per_step": 3 * n_atoms * D * 8, "d2h_bytes_per_step": n_atoms * D * 8 + 8,
+                          "h2d_bytes_per_step": 2 * n_atoms * D * 8, "d2h_bytes_per_step": n_atoms * D * 8 + 8,
                           "ms_per_step": e2e_ms}
         print(json.dumps(out))
     if world > 1:

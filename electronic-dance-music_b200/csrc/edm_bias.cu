@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ int sflag;
   __shared__ double s_pos[3];
   __shared__ double s_h;
-  __shared__ int s_go;
+  __shared__ int s_go, s_tail;
   __shared__ double s_prefactor;
   __shared__ RoundState rs;
   const int mode = st->round_mode;
@@ -397,8 +397,46 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
         this_h = fmin(this_h, 1.0 * bps);  // BIAS_CLAMP, lib/edm_bias.h:14
         s_h = this_h;
         s_go = (rs.temp_hill_cum < bps) ? 1 : 0;
+        // Once the sum has reached bias_per_step it cannot change any more: every remaining hill is
+        // logged with height 0 and pushed whole (lib/edm_bias.cpp:492-523).  If they all fit to the
+        // right of the backlog and into the log, the CTA does them at once.
+        s_tail = (!s_go && rs.right + (nacc - k) <= EDM_BUFFER_SLOTS && rs.log_n + (nacc - k) <= prm.log_cap) ? 1 : 0;
       }
       __syncthreads();
+      if (s_tail) {
+        const double cov = rs.cum_bias / prm.total_volume;
+        for (int i = k + threadIdx.x; i < nacc; i += blockDim.x) {
+          double p[DIM];
+          for (int d = 0; d < DIM; d++) p[d] = acc[i].x[d];
+          double hh = s_prefactor;
+          if (prm.b_targeting) hh *= exp(d_get_value<DIM>(target, p) - prm.expected_target);
+          if (prm.b_tempering && prm.global_tempering < 0)
+            hh *= exp(-d_get_value<DIM>(bias, p) / ((prm.bias_factor - 1) * prm.boltzmann_factor));
+          if (prm.hill_density < 0)
+            hh /= (double)(int)prm.est_hill_count;
+          else
+            hh /= prm.hill_density;
+          hh = fmin(hh, 1.0 * bps);
+          edm_hill_event_t& e = log[rs.log_n + (i - k)];
+          e.steps = rs.steps;
+          e.type = 'h';
+          e.hills_added = rs.hills_added;
+          for (int d = 0; d < 3; d++) e.pos[d] = d < DIM ? p[d] : 0.0;
+          e.height = 0.0;
+          e.bias_added = 0.0;
+          e.cum_over_vol = cov;
+          d_hist_bump<DIM, true>(hist, p, 1.0);
+          double* slot = &st->overflow[(rs.right + 1 + (i - k)) * W1];  // T19: the index moves before the write
+          for (int d = 0; d < DIM; d++) slot[d] = p[d];
+          slot[DIM] = hh;
+        }
+        __syncthreads();
+        if (t0) {
+          rs.log_n += nacc - k;
+          rs.right += nacc - k;
+        }
+        break;
+      }
       double this_h = s_h;
       int buffer_flag = 0;  // thread 0
       if (s_go) {
@@ -495,7 +533,6 @@ template <int DIM> struct PlanHill {
   HillGeom<DIM> hg;
   int ok;            // d_hill_prepare succeeded: the hill deposits something
   int valid;         // the centre lies inside the grid: get_value interpolates (else 0)
-  int ndep;          // earlier hills of the round whose window can reach a corner
   int lo[DIM], up[DIM];
   double X0[DIM];
   double hb;         // height before the local tempering factor and the density division
@@ -515,13 +552,28 @@ __device__ __forceinline__ bool d_window_reaches(const GridDesc& g, int d, int x
   return off - n >= -m && xi + off - n >= -n;  // from below: the reference adds n once only
 }
 
+// Cheap superset of "hill j's window can write a corner of hill k's interpolation cell", for the
+// O(n^2) scan: cj = hill j's centre cell (periodic dims folded into [0, n)) and ok flag, lo = the low
+// corner of k's cell.  A window reaches at most minisize cells from its centre and the upper corner
+// is one cell further; the exact per-corner test (d_window_reaches) follows for the survivors.
 template <int DIM>
-__device__ __forceinline__ bool d_hill_near(const GridDesc& g, const PlanHill<DIM>& pj, const PlanHill<DIM>& pk) {
-  if (!pj.ok) return false;
+__device__ __forceinline__ bool d_hill_near(const GridDesc& g, const int4& cj, const int* lo) {
+  if (!cj.w) return false;
+  const int xi[3] = {cj.x, cj.y, cj.z};
 #pragma unroll
-  for (int d = 0; d < DIM; d++)
-    if (!d_window_reaches(g, d, pj.hg.xi[d], pk.lo[d]) && !d_window_reaches(g, d, pj.hg.xi[d], pk.up[d])) return false;
+  for (int d = 0; d < DIM; d++) {
+    int dist = xi[d] - lo[d];
+    dist = dist < 0 ? -dist : dist;
+    if (g.periodic[d]) dist = min(dist, g.n[d] - dist);
+    if (dist > g.minisize[d] + 1) return false;
+  }
   return true;
+}
+
+__device__ __forceinline__ int d_fold(int i, int n, bool periodic) {
+  if (!periodic) return i;
+  i %= n;
+  return i < 0 ? i + n : i;
 }
 
 template <int DIM>
@@ -561,6 +613,8 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   __shared__ double s_contrib[32][NC * W];
   __shared__ double s_rec[NC][W];
   __shared__ int s_nb;
+  __shared__ int4 s_cells[EDM_ROUND_MAX];          // centre cell + ok of every planned entry
+  __shared__ unsigned short s_ndep[EDM_ROUND_MAX]; // earlier entries that can reach entry k's corners
   const bool local = prm.b_tempering && prm.global_tempering < 0;
   const int W1 = DIM + 1;
   if (threadIdx.x == 0) {
@@ -624,8 +678,11 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       PlanHill<DIM>& p = plan[k];
       p.hb = h;
       p.ok = d_hill_prepare<DIM>(bias, pos, p.hg) ? 1 : 0;
-      if (DIM > 1)
-        cells[k] = make_int4(p.hg.xi[0], p.hg.xi[DIM > 1 ? 1 : 0], p.hg.xi[DIM > 2 ? 2 : 0], p.ok);
+      const int4 c = make_int4(p.hg.xi[0], p.hg.xi[DIM > 1 ? 1 : 0], p.hg.xi[DIM > 2 ? 2 : 0], p.ok);
+      if (DIM > 1) cells[k] = c;
+      s_cells[k] = make_int4(d_fold(c.x, bias.n[0], bias.periodic[0] != 0),
+                             d_fold(c.y, bias.n[DIM > 1 ? 1 : 0], bias.periodic[DIM > 1 ? 1 : 0] != 0),
+                             d_fold(c.z, bias.n[DIM > 2 ? 2 : 0], bias.periodic[DIM > 2 ? 2 : 0] != 0), p.ok);
       CellLoc<DIM> L;
       p.valid = d_locate<DIM>(bias, pos, L) ? 1 : 0;
       if (p.valid) {
@@ -648,9 +705,13 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   for (int k = nb + threadIdx.x; k < nall; k += blockDim.x) {
     PlanHill<DIM>& p = plan[k];
     int ndep = 0;
-    if (p.valid)
-      for (int j = 0; j < k; j++) ndep += d_hill_near<DIM>(bias, plan[j], p) ? 1 : 0;
-    p.ndep = ndep;
+    if (p.valid) {
+      int lo[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) lo[d] = p.lo[d];
+      for (int j = 0; j < k; j++) ndep += d_hill_near<DIM>(bias, s_cells[j], lo) ? 1 : 0;
+    }
+    s_ndep[k] = (unsigned short)ndep;
     if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
   }
   __syncthreads();
@@ -659,13 +720,19 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   // the others in candidate order: patch the corner records with every earlier reaching hill
   const int lane = threadIdx.x;
   for (int k = nb; k < nall; k++) {
+    if (s_ndep[k] == 0) continue;
     const PlanHill<DIM>& p = plan[k];
-    if (p.ndep == 0) continue;
+    int lo[DIM], up[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      lo[d] = p.lo[d];
+      up[d] = p.up[d];
+    }
     double accv = 0.0;
     if (lane < NC * W) accv = p.rec[lane / W][lane % W];
     for (int j0 = 0; j0 < k; j0 += 32) {
       const int j = j0 + lane;
-      bool near = j < k && d_hill_near<DIM>(bias, plan[j], p);
+      bool near = j < k && d_hill_near<DIM>(bias, s_cells[j], lo);
       if (near) {
         const double hj = heights[j];
 #pragma unroll
@@ -674,7 +741,7 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
           bool reach = true;
 #pragma unroll
           for (int d = 0; d < DIM; d++) {
-            idx[d] = ((c >> d) & 1) ? p.up[d] : p.lo[d];
+            idx[d] = ((c >> d) & 1) ? up[d] : lo[d];
             reach = reach && d_window_reaches(bias, d, plan[j].hg.xi[d], idx[d]);
           }
           double etot = 0.0, force[DIM];
@@ -802,6 +869,9 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
   __syncthreads();
   if (s_mode != 1) return;
   const int n = st->n_fast;
+  __shared__ double s_ba[EDM_ROUND_MAX];  // the scan below is one thread's: keep its operands next to it
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s_ba[k] = ba[k];
+  __syncthreads();
   if (threadIdx.x == 0) {
     // Entries [0, take) of the planned list are plain full deposits.  Backlog slots first
     // (flush_bias_buffer, lib/edm_bias.cpp:313-380): a slot is plain unless the drained sum exceeds
@@ -810,23 +880,29 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
     // and after the hill.  The first entry that is not plain, and everything behind it, is the
     // in-order kernel's.
     const int nb = st->n_plan_b;
+    const double bps = prm.bias_per_step;
     double cum = 0.0;
     int take = 0;
-    bool drained_all = true;
-    for (; take < nb; take++) {
-      const double next = cum + ba[take];
-      if (next > prm.bias_per_step) {
-        drained_all = false;
-        break;
+    bool stop = false;
+    while (!stop && take < n) {  // eight entries at a time: the loads and tests overlap, the sum stays serial
+      const int cnt = n - take < 8 ? n - take : 8;
+      double c[9];
+      c[0] = cum;
+#pragma unroll
+      for (int i = 0; i < 8; i++) c[i + 1] = c[i] + (i < cnt ? s_ba[take + i] : 0.0);
+      int first = cnt;
+#pragma unroll
+      for (int i = 7; i >= 0; i--) {
+        const bool slot = take + i < nb;
+        const bool plain = slot ? !(c[i + 1] > bps) : (c[i] < bps && c[i + 1] < bps);
+        if (i < cnt && !plain) first = i;
       }
-      cum = next;
+#pragma unroll
+      for (int i = 0; i <= 8; i++)
+        if (i == first) cum = c[i];
+      take += first;
+      stop = first < cnt;
     }
-    if (drained_all)
-      for (; take < n; take++) {
-        const double next = cum + ba[take];
-        if (!(cum < prm.bias_per_step) || !(next < prm.bias_per_step)) break;
-        cum = next;
-      }
     if (st->log_n + take > prm.log_cap) take = 0;
     s_take = take;
     s_nb = nb;
@@ -862,7 +938,7 @@ __global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundP
       e.pos[d] = d < DIM ? pos[d] : 0.0;
     }
     e.height = heights[k];
-    e.bias_added = ba[k];
+    e.bias_added = s_ba[k];
     e.cum_over_vol = cov;
     d_hist_bump<DIM, true>(hist, pos, 1.0);
   }
@@ -1113,6 +1189,14 @@ int edm_bias_destroy(edm_bias_t* b) {
   if (b->st_copy) cudaStreamDestroy(b->st_copy);
   if (b->ev_f_up) cudaEventDestroy(b->ev_f_up);
   if (b->ev_f_final) cudaEventDestroy(b->ev_f_final);
+  if (b->st_up) {
+    cudaStreamDestroy(b->st_up);
+    for (int c = 0; c < edm_bias::kMaxChunks; c++) {
+      cudaEventDestroy(b->ev_chunk_up[c]);
+      cudaEventDestroy(b->ev_chunk_done[c]);
+    }
+    cudaFree(b->d_chunk_energy);
+  }
   delete b;
   return EDM_OK;
 }
@@ -1208,31 +1292,102 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
   return EDM_OK;
 }
 
+// Host-buffer coordinate step: update_forces and, if asked, the hill round over the same atoms, with
+// one upload of the coordinates.  The atoms go through in chunks on three streams so the two PCIe
+// directions and the kernels overlap (pinned host buffers make the copies truly asynchronous;
+// pageable ones still work, staged by the driver):
+//   up:    x0 f0 | x1 f1 | x2 f2 ...
+//   main:        | K1(0) select(0) | K1(1) select(1) ...            | hill round
+//   down:                          | f0 | f1 ...
+static int coords_pipeline(edm_bias* b, long n, const double* x, long xs, double* f, long fs, const int* mask,
+                           int apply_mask, int do_hills, const double* runiform, uint64_t seed, uint64_t step,
+                           double* energy) {
+  if (energy) *energy = 0.0;
+  if (!b->st_main) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
+  }
+  if (!b->st_up) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_up, cudaStreamNonBlocking));
+    for (int c = 0; c < edm_bias::kMaxChunks; c++) {
+      EDM_CUDA(cudaEventCreateWithFlags(&b->ev_chunk_up[c], cudaEventDisableTiming));
+      EDM_CUDA(cudaEventCreateWithFlags(&b->ev_chunk_done[c], cudaEventDisableTiming));
+    }
+    EDM_CUDA(cudaMalloc(&b->d_chunk_energy, edm_bias::kMaxChunks * sizeof(double)));
+  }
+  EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
+  if (do_hills) {
+    if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+    EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
+  }
+  if (n > 0) {
+    const size_t bx = (size_t)n * xs * sizeof(double), bf = (size_t)n * fs * sizeof(double);
+    EDM_TRY(b->io.reserve(bx));
+    EDM_TRY(b->io2.reserve(bf));
+    if (apply_mask >= 0) EDM_TRY(b->io3.reserve((size_t)n * sizeof(int)));
+    if (do_hills && runiform) EDM_TRY(b->io4.reserve((size_t)n * sizeof(double)));
+    double* dx = b->io.as<double>();
+    double* df = b->io2.as<double>();
+    int* dm = apply_mask >= 0 ? b->io3.as<int>() : nullptr;
+    double* du = (do_hills && runiform) ? b->io4.as<double>() : nullptr;
+    long chunk = (n + edm_bias::kMaxChunks - 1) / edm_bias::kMaxChunks;
+    if (chunk < (1L << 18)) chunk = 1L << 18;  // enough atoms per launch to fill the GPU
+    const int nchunks = (int)((n + chunk - 1) / chunk);
+    for (int c = 0; c < nchunks; c++) {
+      const long o = (long)c * chunk, cnt = (n - o < chunk) ? n - o : chunk;
+      EDM_CUDA(cudaMemcpyAsync(dx + o * xs, x + o * xs, (size_t)cnt * xs * sizeof(double), cudaMemcpyHostToDevice, b->st_up));
+      EDM_CUDA(cudaMemcpyAsync(df + o * fs, f + o * fs, (size_t)cnt * fs * sizeof(double), cudaMemcpyHostToDevice, b->st_up));
+      if (dm) EDM_CUDA(cudaMemcpyAsync(dm + o, mask + o, (size_t)cnt * sizeof(int), cudaMemcpyHostToDevice, b->st_up));
+      if (du) EDM_CUDA(cudaMemcpyAsync(du + o, runiform + o, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, b->st_up));
+      EDM_CUDA(cudaEventRecord(b->ev_chunk_up[c], b->st_up));
+      EDM_CUDA(cudaStreamWaitEvent(b->st_main, b->ev_chunk_up[c], 0));
+      EDM_TRY(edm_bias_update_forces_dev(b, cnt, dx + o * xs, xs, df + o * fs, fs, dm ? dm + o : nullptr, apply_mask,
+                                         b->d_chunk_energy + c, b->st_main));
+      // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17); candidate keys = atom indices
+      if (do_hills)
+        EDM_TRY(select_launch(b, cnt, dx + o * xs, xs, du ? du + o : nullptr, dm ? dm + o : nullptr, apply_mask, n, seed,
+                              step, (uint64_t)o, b->st_main));
+      EDM_CUDA(cudaEventRecord(b->ev_chunk_done[c], b->st_main));
+      EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_chunk_done[c], 0));
+      EDM_CUDA(cudaMemcpyAsync(f + o * fs, df + o * fs, (size_t)cnt * fs * sizeof(double), cudaMemcpyDeviceToHost, b->st_copy));
+    }
+    if (do_hills) EDM_TRY(edm_bias_launch_round(b, n, b->st_main));
+    double e[edm_bias::kMaxChunks];
+    EDM_CUDA(cudaMemcpyAsync(e, b->d_chunk_energy, nchunks * sizeof(double), cudaMemcpyDeviceToHost, b->st_main));
+    EDM_CUDA(cudaStreamSynchronize(b->st_main));
+    double tot = 0.0;
+    for (int c = 0; c < nchunks; c++) tot += e[c];  // chunk order: run-to-run deterministic
+    if (energy) *energy = tot;
+    EDM_CUDA(cudaStreamSynchronize(b->st_copy));
+  } else if (do_hills) {
+    EDM_TRY(edm_bias_launch_round(b, n, b->st_main));
+    EDM_CUDA(cudaStreamSynchronize(b->st_main));
+  }
+  return do_hills ? edm_bias_check_round(b) : EDM_OK;
+}
+
 int edm_bias_update_forces(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
                            const int* mask, int apply_mask, double* energy) {
-  EDM_REQUIRE(b && (n == 0 || (x && f)), "NULL argument");
+  EDM_REQUIRE(b && (n <= 0 || (x && f)), "NULL argument");
+  EDM_REQUIRE(apply_mask < 0 || mask || n <= 0, "apply_mask >= 0 needs a mask");
+  EDM_REQUIRE(n <= 0 || (xstride >= b->prm.dim && fstride >= b->prm.dim), "stride < dim");
   EDM_TRY(ensure_device(b->device));
   if (energy) *energy = 0.0;
   if (n <= 0) return EDM_OK;
-  size_t bx = (size_t)n * xstride * sizeof(double), bf = (size_t)n * fstride * sizeof(double);
-  EDM_TRY(b->io.reserve(bx));
-  EDM_TRY(b->io2.reserve(bf));
-  const int* dmask = nullptr;
-  if (apply_mask >= 0) {
-    EDM_REQUIRE(mask != nullptr, "apply_mask >= 0 needs a mask");
-    EDM_TRY(b->io3.reserve((size_t)n * sizeof(int)));
-    EDM_CUDA(cudaMemcpyAsync(b->io3.p, mask, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, 0));
-    dmask = b->io3.as<int>();
-  }
-  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
-  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bf, cudaMemcpyHostToDevice, 0));
-  EDM_TRY(edm_bias_update_forces_dev(b, n, b->io.as<double>(), xstride, b->io2.as<double>(), fstride, dmask, apply_mask,
-                                     b->d_scalar, nullptr));
-  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bf, cudaMemcpyDeviceToHost, 0));
-  double e = 0;
-  EDM_CUDA(cudaMemcpy(&e, b->d_scalar, sizeof(double), cudaMemcpyDeviceToHost));
-  if (energy) *energy = e;
-  return EDM_OK;
+  return coords_pipeline(b, n, x, xstride, f, fstride, mask, apply_mask, 0, nullptr, 0, 0, energy);
+}
+
+int edm_bias_step_coords(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                         const int* mask, int apply_mask, int do_hills, const double* runiform, uint64_t seed,
+                         uint64_t step, double* energy) {
+  EDM_REQUIRE(b && (n <= 0 || (x && f)), "NULL argument");
+  EDM_REQUIRE(apply_mask < 0 || mask || n <= 0, "apply_mask >= 0 needs a mask");
+  EDM_REQUIRE(n <= 0 || (xstride >= b->prm.dim && fstride >= b->prm.dim), "stride < dim");
+  EDM_TRY(ensure_device(b->device));
+  return coords_pipeline(b, n < 0 ? 0 : n, x, xstride, f, fstride, mask, apply_mask, do_hills, runiform, seed, step,
+                         energy);
 }
 
 // ------------------------------------------------------------------ add_hills

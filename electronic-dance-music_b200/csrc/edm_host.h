@@ -131,5 +131,10 @@ struct edm_bias {
   int profiling = 0;
   cudaStream_t st_main = nullptr, st_copy = nullptr;  // host-buffer pair step: kernels / overlapped copies
   cudaEvent_t ev_f_up = nullptr, ev_f_final = nullptr;
+  // host-buffer coordinate step: chunks pipelined over upload / kernels / download
+  static constexpr int kMaxChunks = 16;
+  cudaStream_t st_up = nullptr;
+  cudaEvent_t ev_chunk_up[kMaxChunks] = {}, ev_chunk_done[kMaxChunks] = {};
+  double* d_chunk_energy = nullptr;
   cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };

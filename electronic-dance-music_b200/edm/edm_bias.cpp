@@ -256,6 +256,27 @@ double EDMBias::update_forces(int nlocal, const double* const* positions, double
   return energy;
 }
 
+double EDMBias::update_forces_add_hills(int nlocal, const double* const* positions, double** forces,
+                                        const double* runiform, int apply_mask, int do_hills) {
+  if (b_outofbounds_ || nlocal <= 0) return 0.0;
+  long xs, fs;
+  const double* x = pack_rows(nlocal, positions, (int)dim_, scratch_x_, &xs);
+  double* f = const_cast<double*>(pack_rows(nlocal, forces, (int)dim_, scratch_f_, &fs));
+  const bool gathered = (f == scratch_f_.data());
+  double energy = 0;
+  edm_check(edm_bias_step_coords(dev_, nlocal, x, xs, f, fs, mask_, apply_mask, do_hills, runiform, 0,
+                                 (unsigned long long)steps_, &energy),
+            "edm_bias.cpp:update_forces_add_hills");
+  if (gathered)
+    for (int i = 0; i < nlocal; i++)
+      for (unsigned j = 0; j < dim_; j++) forces[i][j] = f[(size_t)i * dim_ + j];
+  if (do_hills) {
+    drain_hill_log();
+    refresh_state();
+  }
+  return energy;
+}
+
 double EDMBias::update_force(const double* positions, double* forces) const {
   if (b_outofbounds_) return 0.0;
   double energy = 0;

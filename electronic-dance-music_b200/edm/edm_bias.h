@@ -65,6 +65,11 @@ class EDMBias {
   double pair_step(long natoms, const double* x, double* f, const int* type, int itype, int jtype,
                    const double box[3], double cutoff, int do_hills, long long est_hill_count,
                    unsigned long long seed, unsigned long long step, long long* ncalls);
+  // fix edm's whole post_force (lammps/fix_edm.cpp:134-162) as one call: update_forces and, if
+  // do_hills, add_hills over the same atoms; the coordinates cross PCIe once and the atoms stream
+  // through the GPU in chunks.  Same results as update_forces(...) followed by add_hills(...).
+  double update_forces_add_hills(int nlocal, const double* const* positions, double** forces,
+                                 const double* runiform, int apply_mask, int do_hills);
   edm_bias_t* device_bias() const { return dev_; }
   // after a hill round launched directly through the C ABI: HILLS lines, cum_bias_, host mirrors
   void after_device_round() {

@@ -1,6 +1,6 @@
 // fix edm — coordinate collective variables, B200 build.
-// Reference entry point: lammps/fix_edm.cpp:134-162 (post_force).  The per-step work is two calls
-// into EDM::EDMBias, each of which is one batched launch sequence on the GPU.
+// Reference entry point: lammps/fix_edm.cpp:134-162 (post_force).  The per-step work is one call
+// into EDM::EDMBias: the force update and the hill round share one pipelined pass over the atoms.
 #include "fix_edm.h"
 
 #include <cstdlib>
@@ -71,15 +71,17 @@ void FixEDM::min_setup(int vflag) { post_force(vflag); }
 void FixEDM::post_force(int) {
   const int n = atom->nlocal;
   bias->set_mask(atom->mask);
-  edm_energy = bias->update_forces(n, atom->x, atom->f, groupbit);
-  if (stride > 0 && update->ntimestep % stride == 0) {
+  const int do_hills = (stride > 0 && update->ntimestep % stride == 0) ? 1 : 0;
+  if (do_hills) {
     if (random_capacity < n) {  // one uniform per local atom, drawn in atom order (fix_edm.cpp:149-151)
       random_numbers = (double*)realloc(random_numbers, sizeof(double) * (size_t)atom->nmax);
       random_capacity = atom->nmax;
     }
     for (int i = 0; i < n; i++) random_numbers[i] = random->uniform();
-    bias->add_hills(n, atom->x, random_numbers, groupbit);
   }
+  // update_forces, then add_hills on the same coordinates (fix_edm.cpp:140, 153): one upload, one
+  // pipelined pass over the atoms
+  edm_energy = bias->update_forces_add_hills(n, atom->x, atom->f, random_numbers, groupbit, do_hills);
   if (write_stride > 0 && update->ntimestep % write_stride == 0) {
     bias->write_bias(bias_file);
     bias->write_histogram();

@@ -83,6 +83,8 @@ EXPORTS = {
     "edm_bias_backlog_set": (C.c_int, [vp, C.c_long, C.c_long, c_dp]),
     "edm_bias_log_read": (C.c_int, [vp, vp, C.c_long, c_lp]),
     "edm_bias_update_forces": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, C.c_long, c_ip, C.c_int, c_dp]),
+    "edm_bias_step_coords": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, C.c_long, c_ip, C.c_int, C.c_int, c_dp,
+                                       C.c_uint64, C.c_uint64, c_dp]),
     "edm_bias_update_forces_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, vp, vp]),
     "edm_bias_add_hills": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_ip, C.c_int, C.c_uint64, C.c_uint64]),
     "edm_bias_add_hills_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, vp, C.c_int, C.c_uint64, C.c_uint64, vp]),
@@ -339,6 +341,17 @@ class Bias:
         m = _i(mask) if mask is not None else None
         check(self.L.edm_bias_update_forces(self.h, x.shape[0], _dp(x), x.shape[1], _dp(f), f.shape[1],
                                             _ip(m) if m is not None else None, int(apply_mask), C.byref(e)))
+        return e.value
+
+    def step_coords(self, x, f, runiform=None, mask=None, apply_mask=-1, do_hills=True, seed=0, step=0):
+        """update_forces + add_hills over the same atoms in one pipelined call (fix edm's post_force)."""
+        assert x.flags.c_contiguous and f.flags.c_contiguous and f.dtype == np.float64 and x.dtype == np.float64
+        e = C.c_double(0)
+        u = _d(runiform) if runiform is not None else None
+        m = _i(mask) if mask is not None else None
+        check(self.L.edm_bias_step_coords(self.h, x.shape[0], _dp(x), x.shape[1], _dp(f), f.shape[1],
+                                          _ip(m) if m is not None else None, int(apply_mask), 1 if do_hills else 0,
+                                          _dp(u) if u is not None else None, seed, step, C.byref(e)))
         return e.value
 
     def add_hills(self, x, runiform=None, mask=None, apply_mask=-1, seed=0, step=0):

@@ -476,6 +476,52 @@ static void notebook_vector() {  // python-example/EDM.ipynb:103
   REQUIRE(fabs(-force[0] - (-0.6144025830861709)) < 1e-10 * 0.6144025830861709);
 }
 
+// update_forces_add_hills (fix edm's post_force as one call) against update_forces + add_hills on a
+// second bias fed the same LAMMPS-style rows: identical hills, forces and energies.
+static void fused_step_matches_two_calls() {
+  write_file("fused_host.edm",
+             "tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 60\n"
+             "dimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\nbias_sigma 0.25 0.25\n"
+             "hills_filename HILLS_FUSED\n");
+  double low[] = {0, 0, 0}, high[] = {8, 8, 0}, skin[] = {0, 0, 0};
+  int p[] = {1, 1, 0};
+  EDMBias a("fused_host.edm"), b("fused_host.edm");
+  a.setup(300, 0.0019872);
+  b.setup(300, 0.0019872);
+  a.subdivide(low, high, low, high, p, skin);
+  b.subdivide(low, high, low, high, p, skin);
+  const int n = 5000;
+  std::vector<double> xs(3 * n), fa(3 * n), fb(3 * n), u(n);
+  std::vector<double*> xr(n), far(n), fbr(n);
+  std::vector<int> mask(n);
+  for (int i = 0; i < n; i++) {
+    xr[i] = &xs[3 * i];
+    far[i] = &fa[3 * i];
+    fbr[i] = &fb[3 * i];
+  }
+  for (int step = 0; step < 3; step++) {
+    for (int i = 0; i < n; i++) {
+      for (int d = 0; d < 3; d++) xs[3 * i + d] = 8.0 * rand() / RAND_MAX;
+      fa[3 * i] = fa[3 * i + 1] = fb[3 * i] = fb[3 * i + 1] = 0.0;
+      u[i] = (double)rand() / RAND_MAX;
+      mask[i] = rand() % 4;
+    }
+    a.set_mask(&mask[0]);
+    b.set_mask(&mask[0]);
+    double ea = a.update_forces_add_hills(n, &xr[0], &far[0], &u[0], 2, 1);
+    double eb = b.update_forces(n, &xr[0], &fbr[0], 2);
+    b.add_hills(n, &xr[0], &u[0], 2);
+    REQUIRE(fabs(ea - eb) <= 1e-12 * fabs(eb));
+    bool same = true;
+    for (int i = 0; i < 3 * n; i++) same = same && fa[i] == fb[i];
+    REQUIRE(same);
+    REQUIRE(a.cum_bias_ == b.cum_bias_);
+  }
+  REQUIRE(a.cum_bias_ > 0);
+  double x[] = {4.0, 4.0};
+  REQUIRE(a.bias_->get_value(x) == b.bias_->get_value(x));
+}
+
 int main(int argc, char** argv) {
   g_src = argc > 1 ? argv[1] : "-";
   g_filter = argc > 2 ? argv[2] : NULL;
@@ -497,6 +543,7 @@ int main(int argc, char** argv) {
   if (wanted("edm_bias_reader")) edm_bias_reader();
   if (wanted("edm_sanity")) edm_sanity();
   if (wanted("notebook_vector")) notebook_vector();
+  if (wanted("fused_step_matches_two_calls")) fused_step_matches_two_calls();
   printf("%d checks, %d failed\n", g_checks, g_failed);
   return g_failed ? 1 : 0;
 }

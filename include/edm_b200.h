@@ -158,6 +158,15 @@ int edm_bias_update_forces(edm_bias_t* b, long n, const double* x, long xstride,
 int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
                                const int* mask, int apply_mask, double* energy, void* stream);
 
+/* FixEDM::post_force, lammps/fix_edm.cpp:134-162, as ONE call on host buffers: update_forces over every
+ * atom and, if do_hills (ntimestep % stride == 0, fix_edm.cpp:142), add_hills over the same atoms.  The
+ * coordinates are uploaded once and the atoms stream through in chunks, so both PCIe directions and
+ * the kernels overlap.  Same results as edm_bias_update_forces followed by edm_bias_add_hills.
+ * runiform may be NULL (uniforms = edm_uniform(seed, step, i)); energy may be NULL. */
+int edm_bias_step_coords(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                         const int* mask, int apply_mask, int do_hills, const double* runiform, uint64_t seed,
+                         uint64_t step, double* energy);
+
 /* EDMBias::add_hills, lib/edm_bias.cpp:401-411 (= pre_add_hill(n); add_hill per masked atom;
  * post_add_hill()).  runiform may be NULL: uniforms then come from edm_uniform(seed, step, i). */
 int edm_bias_add_hills(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,

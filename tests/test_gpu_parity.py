@@ -240,7 +240,7 @@ PARALLEL_ROUND_CASES = {"c1_sanity_density": 6, "c5_rdf_tight_limiter_backlog": 
                         "c4_3d_density": 3, "3d_local_tempering_mixed_walls": 3}
 
 
-def run_bias_case(edm, port, tmp_path, name, masked=False):
+def run_bias_case(edm, port, tmp_path, name, masked=False, fused=False):
     cfg = BIAS_CASES[name]
     f = write_edm(tmp_path, name + ".edm", cfg["text"])
     sublo, subhi = cfg["sub"]
@@ -262,12 +262,16 @@ def run_bias_case(edm, port, tmp_path, name, masked=False):
         fd = np.zeros((n, 3))
         am = 2 if masked else -1
         eo = bo.update_forces(x, fo, am)
-        ed = bd.update_forces(x, fd, mask, am)
+        if fused:   # fix edm's post_force as one pipelined call
+            ed = bd.step_coords(x, fd, u, mask, am)
+        else:
+            ed = bd.update_forces(x, fd, mask, am)
         if step > 0:
             assert abs(ed - eo) <= RTOL * abs(eo), "energy step %d: %r vs %r" % (step, ed, eo)
             assert_close(fd, fo, "forces step %d" % step)
         bo.add_hills(x, u, am)
-        bd.add_hills(x, u, mask, am)
+        if not fused:
+            bd.add_hills(x, u, mask, am)
     return bd, bo
 
 
@@ -321,6 +325,36 @@ def test_bias_backlog_exercised(edm, port, tmp_path):
 
 def test_bias_masked_atoms(edm, port, tmp_path):
     bd, bo = run_bias_case(edm, port, tmp_path, "c2_rdf_threshold_tempering", masked=True)
+    compare_bias(bd, bo)
+
+
+@pytest.mark.parametrize("name", ["c1_sanity_density", "c3_2d_local_tempering_sparse", "c5_rdf_tight_limiter_backlog"])
+def test_fused_coordinate_step_parity(edm, port, tmp_path, name):
+    """edm_bias_step_coords (update_forces + add_hills, one upload, chunked pipeline) against the oracle."""
+    bd, bo = run_bias_case(edm, port, tmp_path, name, masked=(name == "c1_sanity_density"), fused=True)
+    compare_bias(bd, bo)
+
+
+def test_fused_coordinate_step_many_chunks(edm, port, tmp_path):
+    """Enough atoms for several pipeline chunks; candidate order and energy must not depend on chunking."""
+    cfg = BIAS_CASES["c1_sanity_density"]
+    f = write_edm(tmp_path, "chunks.edm", cfg["text"])
+    bo = port.Bias("port", f)
+    bo.setup(1.0, 1.0)
+    bo.subdivide([0.0], [10.0], [0.0], [10.0], [1], [0.0])
+    bd = edm.bias_from_edm(f, 1.0, 1.0, [0.0], [10.0], [0.0], [10.0], [1], [0.0])
+    rng = np.random.default_rng(11)
+    n = 3 * (1 << 18) + 12345
+    for step in range(3):
+        x = np.ascontiguousarray(rng.uniform(-1.0, 11.0, size=(n, 1)))
+        u = rng.uniform(0, 1, n)
+        fo, fd = np.zeros((n, 1)), np.zeros((n, 1))
+        eo = bo.update_forces(x, fo, -1)
+        ed = bd.step_coords(x, fd, u)
+        if step:
+            assert abs(ed - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "forces step %d" % step)
+        bo.add_hills(x, u, -1)
     compare_bias(bd, bo)
 
 
