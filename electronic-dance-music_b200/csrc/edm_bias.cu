@@ -129,7 +129,7 @@ __device__ double cta_window_pass(const GridDesc& g, const double* x0, double h,
   if (d_hill_prepare<DIM>(g, x0, hg)) {
     long long total = 1;
 #pragma unroll
-    for (int d = 0; d < DIM; d++) total *= (2 * g.minisize[d] + 1);
+    for (int d = 0; d < DIM; d++) total *= (2 * g.supp[d] + 1);
     for (long long w = threadIdx.x; w < total; w += blockDim.x) {
       int idx[DIM];
       long long lin;

@@ -46,6 +46,7 @@ struct GridDesc {
   double bmin[3], bmax[3], blen[3];
   int bper[3];
   int minisize[3];
+  int supp[3];  // cells from the centre cell beyond which the support test dp^2 < 8 always fails (<= minisize)
   const double* ptab[3];
   const long long* dup_pairs;  // (outer, bound) linear indices of duplicate_boundary, lib/gaussian_grid.h:571-630
   int n_dup;
@@ -333,7 +334,8 @@ __device__ __forceinline__ bool d_hill_term(const GridDesc& g, const HillGeom<DI
   return true;
 }
 
-// Maps window offset w (dim 0 fastest over 2*minisize+1 per dim) to a wrapped grid index,
+// Maps window offset w (dim 0 fastest over 2*supp+1 per dim: the part of the reference's
+// 2*minisize+1 window that can pass the support test) to a wrapped grid index,
 // lib/gaussian_grid.h:229-268.  False when the point falls off a non-periodic grid.
 template <int DIM>
 __device__ __forceinline__ bool d_window_index(const GridDesc& g, const HillGeom<DIM>& hg, long long w, int* idx,
@@ -342,7 +344,7 @@ __device__ __forceinline__ bool d_window_index(const GridDesc& g, const HillGeom
   long long pstride = 1;
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
-    int span = 2 * g.minisize[d] + 1;
+    int span = 2 * g.supp[d] + 1;
     int off;
     if (d < DIM - 1) {
       off = (int)(w % span);
@@ -350,7 +352,7 @@ __device__ __forceinline__ bool d_window_index(const GridDesc& g, const HillGeom
     } else {
       off = (int)w;
     }
-    int i = off - g.minisize[d] + hg.xi[d];
+    int i = off - g.supp[d] + hg.xi[d];
     if (i >= g.n[d]) {
       if (!g.periodic[d]) return false;
       i %= g.n[d];

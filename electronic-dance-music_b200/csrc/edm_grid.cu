@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) deposit_hills_kernel(GridDesc g, long n, 
   __shared__ double red[33];
   long long total = 1;
 #pragma unroll
-  for (int d = 0; d < DIM; d++) total *= (2 * g.minisize[d] + 1);
+  for (int d = 0; d < DIM; d++) total *= (2 * g.supp[d] + 1);
   for (long hill = blockIdx.x; hill < n; hill += gridDim.x) {
     HillGeom<DIM> hg;
     double x0[DIM];
@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
   const long h1 = (h0 + chunk < n) ? h0 + chunk : n;
   const int npts = g.n[0];
   const int m = g.minisize[0];
+  const int ms = g.supp[0];  // hills further than this from the warp's 32 points cannot reach them
   const int p0 = w * 32;
   const int p = p0 + lane;
   const bool have = p < npts;
@@ -488,9 +489,9 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
         if (GPER) {
           int d = (p0 - xi) % npts;
           if (d < 0) d += npts;
-          ov = all_overlap || (d <= m) || (d >= npts - m - 31);
+          ov = all_overlap || (d <= ms) || (d >= npts - ms - 31);
         } else {
-          ov = (xi - m <= p0 + 31) && (xi + m >= p0);
+          ov = (xi - ms <= p0 + 31) && (xi + ms >= p0);
         }
       }
     }
@@ -782,6 +783,15 @@ int edm_gauss_create(edm_grid_t** out, int device, int dim, const double* mn, co
     double dist = sqrt(2 * kGaussSupport) * d.sigma[i];
     d.minisize[i] = host_int_floor(dist / d.dx[i]);
     if (d.periodic[i] && 2 * d.minisize[i] + 1 > d.n[i]) d.dup_possible = 1;
+  }
+  // The window is 5.66 sigma wide each way but only points with sum dp^2 < 8 receive anything
+  // (lib/gaussian_grid.h:299): |xx - x| < sqrt(8) sigma~ in every dim.  A point more than `supp`
+  // cells from the centre cell lies at least (supp - 1) dx > sqrt(8) sigma~ away, so loops may stop
+  // at supp and still visit every point the reference changes.  Not when a periodic window revisits
+  // points (each revisit adds again).
+  for (int i = 0; i < dim; i++) {
+    int s = host_int_floor(sqrt(kGaussSupport) * d.sigma[i] / d.dx[i]) + 2;
+    d.supp[i] = (d.dup_possible || s > d.minisize[i]) ? d.minisize[i] : s;
   }
   // the ctor calls set_boundary with the un-extended box (lib/gaussian_grid.h:78, T9)
   int rc = build_boundary(g, mn, mx, periodic);
