@@ -90,7 +90,87 @@ def main():
         assert len(ld) == len(lo) and np.array_equal(ld["type"], lo["type"]) and np.array_equal(ld["pos"], lo["pos"])
         assert b.backlog()[:2] == bo.backlog()[:2]
         print("MULTI_GPU_CHECK_OK world=%d events=%d" % (world, len(ld)))
+    coord_check(tmp, rank, world, local)
     dist.destroy_process_group()
+
+
+COORD_TEXT = ("tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+              "hill_density 200\ndimension 2\nbox_low 0 0\nbox_high 16 16\nbias_spacing 0.03125 0.03125\n"
+              "bias_sigma 0.0625 0.0625\n")
+
+
+def coord_check(tmp, rank, world, local):
+    """fix edm sharded: every rank owns a block of atoms (2-D coordinate CV, local well-tempering), selects
+    with the job-wide est_hill_count and atom-index counters, and commits the all-gathered hills; checked
+    against a single-rank oracle run on the rank-major concatenation."""
+    d = os.path.join(tmp, "c%d" % rank)
+    os.makedirs(d, exist_ok=True)
+    f = os.path.join(d, "c.edm")
+    open(f, "w").write(COORD_TEXT + "hills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (d, d))
+    L = edm.lib()
+    b = edm.bias_from_edm(f, 300.0, 0.0019872, [0, 0], [16, 16], [0, 0], [16, 16], [1, 1], [0.0, 0.0], device=local)
+    n, cap, steps = 20000, 1024, 4
+    blk_n = L.edm_hill_block_doubles(2, cap)
+    block = torch.zeros(blk_n, dtype=torch.float64, device="cuda")
+    gathered = torch.zeros(blk_n * world, dtype=torch.float64, device="cuda")
+    fdev = torch.zeros((n, 2), dtype=torch.float64, device="cuda")
+    edev = torch.zeros(1, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    xs, us, es, fs = [], [], [], []
+    for step in range(steps):
+        rng = np.random.default_rng([77, rank, step])
+        x = np.ascontiguousarray(rng.uniform(-1, 17, size=(n, 2)))
+        u = rng.uniform(0, 1, n)
+        xs.append(x)
+        us.append(u)
+        xd, ud = torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda()
+        fdev.zero_()
+        edm.check(L.edm_bias_update_forces_dev(b.h, n, xd.data_ptr(), 2, fdev.data_ptr(), 2, None, -1, edev.data_ptr(), st))
+        es.append(float(edev.item()))
+        fs.append(fdev.cpu().numpy().copy())
+        edm.check(L.edm_bias_select_dev(b.h, n, xd.data_ptr(), 2, ud.data_ptr(), None, -1, n * world, 0, step,
+                                        rank * n, st))
+        edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, st))
+        dist.all_gather_into_tensor(gathered, block)
+        edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, n * world, st))
+    torch.cuda.synchronize()
+    v, dv = b.bias_grid.get_arrays()
+    mine = torch.from_numpy(np.concatenate([v, dv.ravel()])).cuda()
+    ref = mine.clone()
+    dist.broadcast(ref, 0)
+    flags = torch.tensor([1 if torch.equal(mine, ref) else 0], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    assert int(flags.item()) == 1, "2-D replicas differ across ranks"
+    allx, allu, alle, allf = [None] * world, [None] * world, [None] * world, [None] * world
+    dist.all_gather_object(allx, xs)
+    dist.all_gather_object(allu, us)
+    dist.all_gather_object(alle, es)
+    dist.all_gather_object(allf, fs)
+    if rank == 0:
+        fo = os.path.join(tmp, "oc.edm")
+        open(fo, "w").write(COORD_TEXT + "hills_filename %s/HC\nhistogram_filename %s/GC\n" % (tmp, tmp))
+        bo = pyoracle.Bias("port", fo)
+        bo.setup(300.0, 0.0019872)
+        bo.subdivide([0, 0], [16, 16], [0, 0], [16, 16], [1, 1], [0.0, 0.0])
+        for step in range(steps):
+            x = np.ascontiguousarray(np.concatenate([allx[r][step] for r in range(world)]))
+            u = np.concatenate([allu[r][step] for r in range(world)])
+            x3 = np.zeros((x.shape[0], 3))
+            x3[:, :2] = x
+            fo3 = np.zeros_like(x3)
+            eo = bo.update_forces(x3, fo3, -1)
+            ed = sum(alle[r][step] for r in range(world))
+            fd = np.concatenate([allf[r][step] for r in range(world)])
+            if step:
+                assert abs(ed - eo) <= 1e-10 * abs(eo), (ed, eo)
+                assert np.abs(fd - fo3[:, :2]).max() <= 1e-10 * np.abs(fo3).max()
+            bo.add_hills(x3, u, -1)
+        vo, do = bo.gauss.get_arrays()
+        assert np.abs(v - vo).max() <= 1e-10 * np.abs(vo).max(), np.abs(v - vo).max() / np.abs(vo).max()
+        ld, lo = b.log(), bo.log()
+        assert len(ld) == len(lo) and np.array_equal(ld["pos"], lo["pos"])
+        assert np.abs(ld["height"] - lo["height"]).max() <= 1e-10 * np.abs(lo["height"]).max()
+        print("MULTI_GPU_COORD_CHECK_OK world=%d events=%d rounds=%s" % (world, len(ld), b.round_info()))
 
 
 if __name__ == "__main__":

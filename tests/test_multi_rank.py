@@ -121,3 +121,4 @@ def test_two_gpu_replicas_match_single_rank_oracle(tmp_path):
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
     assert "MULTI_GPU_CHECK_OK" in r.stdout
+    assert "MULTI_GPU_COORD_CHECK_OK" in r.stdout
