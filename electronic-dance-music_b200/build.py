@@ -60,7 +60,7 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
-HOST_SRCS = ["edm.cpp", "grid.cpp", "gaussian_grid.cpp", "edm_bias.cpp"]
+HOST_SRCS = ["edm.cpp", "grid.cpp", "gaussian_grid.cpp", "edm_bias.cpp", "edm_bias_py.cpp"]
 HOST_LIB = os.path.join(LIBDIR, "libedm.so")
 HOST_TEST = os.path.join(LIBDIR, "edm_host_test")
 CXX = "/usr/bin/g++"

@@ -514,8 +514,10 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
           mult = (o >= -m && o <= m) ? 1 : 0;
         }
       }
+      // Straight-line body: lanes outside the window or the support add an exact 0.0 (the divergence
+      // bookkeeping of a nested if cost more issue slots than the arithmetic it skipped).
       double term_ba = 0.0;
-      if (mult > 0) {
+      {
         double v = __dsub_rn(xx, hl.x);
         if (GPER) v = __dsub_rn(v, __dmul_rn(d_round(__ddiv_rn(v, len)), len));
         // reciprocal first; the exactly rounded quotient only where it could change the support test
@@ -525,37 +527,36 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
           dp = __ddiv_rn(v, sigma);
           dp2 = __dmul_rn(dp, dp);
         }
-        if (dp2 < kGaussSupport) {
-          const double E = exp(-dp2);
-          const double t5 = -2.0 * dp * inv_sigma;
-          double etot, F;
-          if (wall) {  // McGDP + zero-force terms, lib/gaussian_grid.h:310-337
-            double corr = (hl.t1 - E) * uL + (hl.t3 - E) * uU;
-            F = t5 * E + (hl.t1 - E) * t6 - t5 * E * uL + (hl.t3 - E) * t7 - t5 * E * uU;
-            F = (F * Z - Zd * (E + corr)) * invZ2;
-            corr *= invZ;
-            etot = E * invZ + corr;
-            dirty |= (corr * corr > 0.0);
-          } else if (!bper) {  // interior of a non-periodic boundary: the correction terms vanish
-            etot = E * invZ;
-            F = E * (t5 * invZ - ZdinvZ2);
-          } else {  // periodic boundary, lib/gaussian_grid.h:340,352
-            etot = E * invZ;
-            F = t5 * etot;
-          }
-          const double add = hl.h * etot;
-          const double addd = hl.h * F;
-          if (GPER) {
-            for (int k = 0; k < mult; k++) {
-              acc_v += add;
-              acc_d += addd;
-              term_ba += add * vol;
-            }
-          } else {
+        const bool in = mult > 0 && dp2 < kGaussSupport;
+        const double E = d_exp_support(in ? -dp2 : 0.0);
+        const double t5 = -2.0 * dp * inv_sigma;
+        double etot, F;
+        if (wall) {  // McGDP + zero-force terms, lib/gaussian_grid.h:310-337
+          double corr = (hl.t1 - E) * uL + (hl.t3 - E) * uU;
+          F = t5 * E + (hl.t1 - E) * t6 - t5 * E * uL + (hl.t3 - E) * t7 - t5 * E * uU;
+          F = (F * Z - Zd * (E + corr)) * invZ2;
+          corr *= invZ;
+          etot = E * invZ + corr;
+          dirty |= in && (corr * corr > 0.0);
+        } else if (!bper) {  // interior of a non-periodic boundary: the correction terms vanish
+          etot = E * invZ;
+          F = E * (t5 * invZ - ZdinvZ2);
+        } else {  // periodic boundary, lib/gaussian_grid.h:340,352
+          etot = E * invZ;
+          F = t5 * etot;
+        }
+        const double add = in ? hl.h * etot : 0.0;
+        const double addd = in ? hl.h * F : 0.0;
+        if (GPER) {
+          for (int k = 0; k < mult; k++) {
             acc_v += add;
             acc_d += addd;
-            term_ba = add * vol;
+            term_ba += add * vol;
           }
+        } else {
+          acc_v += add;
+          acc_d += addd;
+          term_ba = add * vol;
         }
       }
       const double tot = warp_sum(term_ba);

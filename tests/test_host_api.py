@@ -114,3 +114,32 @@ def test_restated_reference_unit_tests_on_gpu(host_test_binary, tmp_path):
     print(r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:]
     assert " 0 failed" in r.stdout
+
+
+@pytest.mark.gpu
+def test_python_api_reproduces_the_notebook_vector(host_test_binary, tmp_path, monkeypatch):
+    """edm.EDMBias (python/edm/__init__.py) on the B200 engine: python-example/EDM.ipynb:86-103."""
+    import sys
+    sys.path.insert(0, os.path.join(PKG, "python"))
+    from edm_b200.compat import EDMBias
+    monkeypatch.chdir(tmp_path)   # HILLS / HIST files open relative to the working directory
+    f = tmp_path / "input.edm"
+    f.write_text("tempering 0\nhill_prefactor 1.0\ndimension 1\nbox_low 0.0\nbox_high 1.0\nbias_spacing 0.01\n"
+                 "bias_sigma 0.5\n")
+    bias = EDMBias(str(f), 1, 1)
+    bias.set_box([0], [10], [0])
+    bias.pre_add_hill(1)
+    bias.add_hill_r([0.25], 0.0)
+    bias.post_add_hill()
+    e, der = bias.get_force([0.24])
+    assert abs(e - 1.1002417338159258) <= 1e-10 * 1.1002417338159258
+    assert abs(der[0] - (-0.6144025830861709)) <= 1e-10 * 0.6144025830861709
+    bias.add_hill([0.5])                       # the wrapper's own convenience method
+    e2, _ = bias.get_force([0.24])
+    assert e2 > e
+    bias.write_bias(str(tmp_path / "BIAS"))
+    bias.write_histogram()
+    bias.clear_histogram()
+    assert (tmp_path / "BIAS").exists()
+    with pytest.raises(ValueError):
+        bias.get_force([0.1, 0.2])
