@@ -42,8 +42,8 @@ DEPOSIT_BATCH = 1 << 20      # hills in the batched-deposit throughput measureme
 HILL_CAP = 4096              # records per rank in the exchange block
 ALG_BYTES_PER_ATOM = 76      # 24 B x + 48 B f read-modify-write + 4 B type, per atom per step
 # dram__bytes_read.sum + dram__bytes_write.sum of one block_eval_kernel launch on this workload
-NCU_TRAFFIC_BYTES = 188_917_504
-NCU_TRAFFIC_SOURCE = "profiles/r01_d_block_pair_ncu_selected.txt (ncu --set full, one launch)"
+NCU_TRAFFIC_BYTES = 188_613_376
+NCU_TRAFFIC_SOURCE = "profiles/r01_i_block_eval_ncu_selected.txt (ncu --set full, one launch: 180.32 MB read + 8.29 MB written)"
 
 
 # The other BASELINE.json configs (parity-test cases first; measurable on request with --workload).
@@ -427,7 +427,9 @@ def run_gpu(args, rank, local_rank, world):
                        "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
-                      "in_situ_hill_events": int(hills_timed), "rounds": bias.round_info(),
+                      "in_situ_hill_events": int(hills_timed),
+                      "in_situ_hills_per_s": (st1["steps"] - st0["steps"]) * 250.0 / (total_ms * 1e-3) if total_ms else None,
+                      "rounds": bias.round_info(),
                       "backlog": list(bias.backlog()[:2])},
             "roofline": {"bound": "hbm", "kernel": "block_eval_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
@@ -450,13 +452,14 @@ def run_gpu(args, rank, local_rank, world):
             sample = 2_600_000 * cores
             r = sample_pair_distances(crng, sample)
             rate, t, _ = cpu_pair_rate(kind, edm_file, r, warm, cores, 2)
+            rate1, _, _ = cpu_pair_rate(kind, edm_file, r[:2_600_000], warm, 1, 2)
             hills = cpu_hill_rate(kind, 20000, crng)
             out["cpu_baseline"] = {
                 "value": rate, "unit": "evals/s", "cores": cores, "kind": kind_name,
                 "sample": "%d pair distances x2 through EDMBias::update_force on %d single-rank instances (one per "
                           "core, full grid replica each); hills/s: 20000 GaussGrid::add_value calls on one core"
                           % (sample, cores),
-                "hills_per_s_1core": hills}
+                "evals_per_s_1core": rate1, "hills_per_s_1core": hills}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
