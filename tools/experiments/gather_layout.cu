@@ -11,7 +11,8 @@ __device__ __forceinline__ void ld32(const double* p, double* o) {
   o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
 }
 
-template <int DIM, bool CELL>
+// LAYOUT 0: point records; 1: cell records; 2: pair records {rec[p], rec[p+1]} (64 B, aligned) per point
+template <int DIM, int CELL>
 __global__ void __launch_bounds__(256, 3) gather(const double* __restrict__ rec, long n0, long n1, long n2, long n,
                                                  const double* __restrict__ x, double* __restrict__ f) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,7 +21,18 @@ __global__ void __launch_bounds__(256, 3) gather(const double* __restrict__ rec,
   for (int d = 0; d < DIM; d++) { xi[d] = x[i * DIM + d]; fo[d] = f[i * DIM + d]; }
   long c0 = (long)xi[0], c1 = (long)xi[1], c2 = DIM == 3 ? (long)xi[2] : 0;
   double acc[4] = {0, 0, 0, 0};
-  if (CELL) {
+  if (CELL == 2) {
+    for (int c = 0; c < (1 << (DIM - 1)); c++) {
+      long a1 = c1 + (c & 1), a2 = c2 + ((c >> 1) & 1);
+      if (a1 == n1) a1 = 0;
+      if (DIM == 3 && a2 == n2) a2 = 0;
+      const double* p = rec + ((a2 * n1 + a1) * n0 + c0) * 8;
+      double r[4], q[4];
+      ld32(p, r);
+      ld32(p + 4, q);
+      for (int k = 0; k < 4; k++) acc[k] += r[k] * (2 * c + 1) + q[k] * (2 * c + 2);
+    }
+  } else if (CELL == 1) {
     const double* p = rec + ((c2 * n1 + c1) * n0 + c0) * (4L << DIM);
     for (int c = 0; c < (1 << DIM); c++) {
       double r[4];
@@ -55,7 +67,7 @@ __global__ void rnd(double* x, long n, int dim, double s0, double s1, double s2)
   }
 }
 
-template <int DIM, bool CELL> float run(const double* rec, long n0, long n1, long n2, long n, const double* x, double* f, void* flush) {
+template <int DIM, int CELL> float run(const double* rec, long n0, long n1, long n2, long n, const double* x, double* f, void* flush) {
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   float best = 1e9;
@@ -79,8 +91,9 @@ int main() {
     cudaMalloc(&pt, n0 * n1 * 32); cudaMalloc(&cell, n0 * n1 * 128); cudaMalloc(&x, n * 16); cudaMalloc(&f, n * 16);
     fill<<<1184, 256>>>(pt, n0 * n1 * 4); fill<<<1184, 256>>>(cell, n0 * n1 * 16); cudaMemset(f, 0, n * 16);
     rnd<<<(unsigned)((n + 255) / 256), 256>>>(x, n, 2, 4096, 4096, 1);
-    printf("2-D 4096^2, 1e7 points: point records %.3f ms, cell records %.3f ms\n", run<2, false>(pt, n0, n1, 1, n, x, f, flush),
-           run<2, true>(cell, n0, n1, 1, n, x, f, flush));
+    printf("2-D 4096^2, 1e7 points: point records %.3f ms, cell records %.3f ms, pair records %.3f ms\n",
+           run<2, 0>(pt, n0, n1, 1, n, x, f, flush), run<2, 1>(cell, n0, n1, 1, n, x, f, flush),
+           run<2, 2>(cell, n0, n1, 1, n, x, f, flush));
     cudaFree(pt); cudaFree(cell); cudaFree(x); cudaFree(f);
   }
   {  // C4: 3-D 512^3, 1e7 points
@@ -91,8 +104,9 @@ int main() {
     cudaMalloc(&x, n * 24); cudaMalloc(&f, n * 24);
     fill<<<1184, 256>>>(pt, n0 * n1 * n2 * 4); fill<<<1184, 256>>>(cell, n0 * n1 * n2 * 32); cudaMemset(f, 0, n * 24);
     rnd<<<(unsigned)((n + 255) / 256), 256>>>(x, n, 3, 512, 512, 512);
-    printf("3-D 512^3, 1e7 points: point records %.3f ms, cell records %.3f ms\n", run<3, false>(pt, n0, n1, n2, n, x, f, flush),
-           run<3, true>(cell, n0, n1, n2, n, x, f, flush));
+    printf("3-D 512^3, 1e7 points: point records %.3f ms, cell records %.3f ms, pair records %.3f ms\n",
+           run<3, 0>(pt, n0, n1, n2, n, x, f, flush), run<3, 1>(cell, n0, n1, n2, n, x, f, flush),
+           run<3, 2>(cell, n0, n1, n2, n, x, f, flush));
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
