@@ -1,0 +1,140 @@
+"""Edge cases of the hill round and the batched calls on the GPU, against the oracle: empty and
+fully masked inputs, candidates outside a walled boundary, rounds larger than the parallel plan,
+a backlog that fills up (the reference aborts there), rounds that deposit nothing."""
+import numpy as np
+import pytest
+
+from test_gpu_parity import BIAS_CASES, RTOL, assert_close, compare_bias, write_edm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def edm():
+    import edm_b200
+    if edm_b200.device_count() == 0:
+        pytest.fail("no CUDA device visible: the GPU tests cannot fall back to the CPU")
+    return edm_b200
+
+
+def make_both(edm, port, tmp_path, name, text, T, kB, lo, hi, periodic):
+    f = write_edm(tmp_path, name + ".edm", text)
+    D = len(lo)
+    bo = port.Bias("port", f)
+    bo.setup(T, kB)
+    bo.subdivide(lo, hi, lo, hi, periodic, [0.0] * D)
+    bd = edm.bias_from_edm(f, T, kB, lo, hi, lo, hi, periodic, [0.0] * D)
+    return bd, bo
+
+
+def test_empty_and_fully_masked_rounds(edm, port, tmp_path):
+    """n = 0 and "no atom in the group" still run pre_add_hill / post_add_hill: steps advance, nothing is deposited."""
+    cfg = BIAS_CASES["c2_rdf_threshold_tempering"]
+    bd, bo = make_both(edm, port, tmp_path, "empty", cfg["text"], cfg["T"], cfg["kB"], [1.68], [5.0], [0])
+    rng = np.random.default_rng(3)
+    x = np.ascontiguousarray(rng.uniform(0.5, 5.5, size=(5000, 3)))
+    u = rng.uniform(0, 1, 5000)
+    mask = np.ones(5000, np.int32)            # bit 0 only: group bit 2 selects nobody
+    for step in range(4):
+        fo, fd = np.zeros((5000, 3)), np.zeros((5000, 3))
+        if step == 1:                          # empty call
+            e0, f0 = np.zeros((0, 3)), np.zeros((0, 3))
+            assert bd.update_forces(e0, f0) == 0.0
+            bo.add_hills(e0, np.zeros(0), -1)
+            bd.add_hills(e0, np.zeros(0))
+        elif step == 2:                        # everybody masked out
+            bo.set_mask(mask)
+            assert bo.update_forces(x, fo, 2) == bd.update_forces(x, fd, mask, 2) == 0.0
+            assert not fd.any()
+            bo.add_hills(x, u, 2)
+            bd.add_hills(x, u, mask, 2)
+        else:
+            eo = bo.update_forces(x, fo, -1)
+            ed = bd.step_coords(x, fd, u)
+            if step:
+                assert abs(ed - eo) <= RTOL * abs(eo)
+                assert_close(fd, fo, "forces")
+            bo.add_hills(x, u, -1)
+    compare_bias(bd, bo)
+    assert bd.state()["steps"] == 4
+
+
+def test_every_candidate_outside_the_walls(edm, port, tmp_path):
+    """Centres outside a non-periodic boundary are accepted, logged and deposit nothing (T10)."""
+    text = ("tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 50\ndimension 2\nbox_low 0 0\n"
+            "box_high 4 4\nbias_spacing 0.0625 0.0625\nbias_sigma 0.125 0.125")
+    bd, bo = make_both(edm, port, tmp_path, "outside", text, 1.0, 1.0, [0.0, 0.0], [4.0, 4.0], [0, 0])
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        x = np.ascontiguousarray(rng.uniform(4.5, 6.0, size=(2000, 3)))
+        if step == 2:
+            x[::7, :2] = rng.uniform(0.0, 4.0, size=(x[::7].shape[0], 2))   # now a few land inside
+        u = rng.uniform(0, 1, 2000)
+        fo, fd = np.zeros((2000, 3)), np.zeros((2000, 3))
+        bo.update_forces(x, fo, -1)
+        bd.update_forces(x, fd)
+        assert_close(fd, fo, "forces")
+        bo.add_hills(x, u, -1)
+        bd.add_hills(x, u)
+    log = compare_bias(bd, bo)
+    assert (log["bias_added"] == 0).sum() > 0 and (log["bias_added"] > 0).sum() > 0
+
+
+def test_round_larger_than_the_parallel_plan(edm, port, tmp_path):
+    """hill_density < 0: every candidate deposits.  6 000 hills in one round exceed the plan's capacity
+    (in-order kernel, bitonic ordering of the accepted list) and 1 500 fit it."""
+    text = ("tempering 0\nhill_prefactor 0.5\nbias_per_step 1000\ndimension 1\nbox_low 0\nbox_high 10\n"
+            "bias_spacing 0.01\nbias_sigma 0.05")
+    bd, bo = make_both(edm, port, tmp_path, "big", text, 1.0, 1.0, [0.0], [10.0], [1])
+    rng = np.random.default_rng(9)
+    for n in (6000, 1500):
+        x = np.ascontiguousarray(rng.uniform(-1, 11, size=(n, 1)))
+        u = rng.uniform(0, 1, n)
+        bo.add_hills(x, u, -1)
+        bd.add_hills(x, u)
+    log = compare_bias(bd, bo)
+    assert len(log) == 7500
+    info = bd.round_info()
+    assert info["in_order"] == 1 and info["parallel"] == 1, info
+
+
+def test_backlog_overflow_is_reported(edm, port, tmp_path):
+    """More buffered hills than BIAS_BUFFER_SIZE: the reference aborts (lib/edm_bias.cpp:503-507); the C ABI
+    returns EDM_ERR_BACKLOG_FULL and the C++ mirror turns that into edm_error."""
+    text = ("tempering 0\nhill_prefactor 1.0\nbias_per_step 0.0001\ndimension 1\nbox_low 0\nbox_high 10\n"
+            "bias_spacing 0.01\nbias_sigma 0.05")
+    f = write_edm(tmp_path, "full.edm", text)
+    bd = edm.bias_from_edm(f, 1.0, 1.0, [0.0], [10.0], [0.0], [10.0], [1], [0.0])
+    rng = np.random.default_rng(1)
+    # the first hill fits under bias_per_step, the second overshoots and is pushed, then one push per hill:
+    # 2 050 candidates are one more than the deque takes
+    x = np.ascontiguousarray(rng.uniform(0, 10, size=(2050, 1)))
+    with pytest.raises(edm.EdmError) as err:
+        bd.add_hills(x, rng.uniform(0, 1, 2050))
+    assert "overflow buffer is full" in str(err.value)
+
+
+def test_backlog_fills_to_the_brim_without_overflow(edm, port, tmp_path):
+    """Exactly as many pushes as the deque takes (the parallel tail push must stop at the same slot)."""
+    text = ("tempering 0\nhill_prefactor 1.0\nbias_per_step 0.0001\ndimension 1\nbox_low 0\nbox_high 10\n"
+            "bias_spacing 0.01\nbias_sigma 0.05")
+    bd, bo = make_both(edm, port, tmp_path, "brim", text, 1.0, 1.0, [0.0], [10.0], [1])
+    rng = np.random.default_rng(2)
+    for n in (2049, 400, 300):     # 2 048 pushes fill the deque exactly; later rounds are skipped while it drains
+        x = np.ascontiguousarray(rng.uniform(0, 10, size=(n, 1)))
+        u = rng.uniform(0, 1, n)
+        bo.add_hills(x, u, -1)
+        bd.add_hills(x, u)
+    compare_bias(bd, bo)
+    assert bd.backlog()[1] == 2048
+
+
+def test_deposit_empty_and_single(edm, port):
+    gd = edm.GaussGrid(2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    go = port.GaussGrid("port", 2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    assert len(gd.add_values(np.zeros((0, 2)), np.zeros(0))) == 0
+    c = np.array([[3.99, 0.01]])
+    bd = gd.add_values(c, np.array([0.5]))
+    bo = go.add_values(c, np.array([0.5]))
+    assert_close(bd, bo, "bias_added")
+    assert_close(gd.get_arrays()[0], go.get_arrays()[0], "grid")

@@ -32,6 +32,18 @@ __global__ void __launch_bounds__(256, 3) gather(const double* __restrict__ rec,
       ld32(p + 4, q);
       for (int k = 0; k < 4; k++) acc[k] += r[k] * (2 * c + 1) + q[k] * (2 * c + 2);
     }
+  } else if (CELL == 3) {  // point records in 4x4x4 tiles (2 KB each), tiles in linear order
+    for (int c = 0; c < (1 << DIM); c++) {
+      long a0 = c0 + (c & 1), a1 = c1 + ((c >> 1) & 1), a2 = c2 + ((c >> 2) & 1);
+      if (a0 == n0) a0 = 0;
+      if (a1 == n1) a1 = 0;
+      if (DIM == 3 && a2 == n2) a2 = 0;
+      const long tile = ((a2 >> 2) * (n1 >> 2) + (a1 >> 2)) * (n0 >> 2) + (a0 >> 2);
+      const long in = ((a2 & 3) * 4 + (a1 & 3)) * 4 + (a0 & 3);
+      double r[4];
+      ld32(rec + (tile * 64 + in) * 4, r);
+      for (int k = 0; k < 4; k++) acc[k] += r[k] * (c + 1);
+    }
   } else if (CELL == 1) {
     const double* p = rec + ((c2 * n1 + c1) * n0 + c0) * (4L << DIM);
     for (int c = 0; c < (1 << DIM); c++) {
@@ -104,9 +116,12 @@ int main() {
     cudaMalloc(&x, n * 24); cudaMalloc(&f, n * 24);
     fill<<<1184, 256>>>(pt, n0 * n1 * n2 * 4); fill<<<1184, 256>>>(cell, n0 * n1 * n2 * 32); cudaMemset(f, 0, n * 24);
     rnd<<<(unsigned)((n + 255) / 256), 256>>>(x, n, 3, 512, 512, 512);
-    printf("3-D 512^3, 1e7 points: point records %.3f ms, cell records %.3f ms, pair records %.3f ms\n",
+    printf("3-D 512^3, 1e7 points: point records %.3f ms, cell records %.3f ms, pair records %.3f ms, 4x4x4-tiled point records %.3f ms\n",
            run<3, 0>(pt, n0, n1, n2, n, x, f, flush), run<3, 1>(cell, n0, n1, n2, n, x, f, flush),
-           run<3, 2>(cell, n0, n1, n2, n, x, f, flush));
+           run<3, 2>(cell, n0, n1, n2, n, x, f, flush), run<3, 3>(pt, n0, n1, n2, n, x, f, flush));
+    rnd<<<(unsigned)((n + 255) / 256), 256>>>(x, n, 3, 512, 512, 512);
+    printf("   1.25e6 points (one of 8 GPUs): point %.3f ms, tiled %.3f ms\n", run<3, 0>(pt, n0, n1, n2, n / 8, x, f, flush),
+           run<3, 3>(pt, n0, n1, n2, n / 8, x, f, flush));
   }
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
