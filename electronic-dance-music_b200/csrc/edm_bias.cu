@@ -112,58 +112,13 @@ struct RoundParams {
   long accepted_cap, log_cap;
 };
 
-// One hill's window spread over the CTA.  kPassStore: plain read-modify-writes (one hill at a time,
-// so no two threads touch the same point unless a periodic window revisits it; then fp64 atomics,
-// whose operands are equal, keep the result order-independent).  kPassAtomic: fp64 REDs, for hills of
-// one round deposited concurrently.  kPassIntegrate: no writes, only add_value's integral.  The
-// window-point -> thread mapping and the reduction tree are the same in every mode, so the integral
-// comes out bit-identical whichever pass computed it.  Every thread receives the integral.
-enum { kPassIntegrate = 0, kPassStore = 1, kPassAtomic = 2 };
-
-template <int DIM, int MODE>
-__device__ double cta_window_pass(const GridDesc& g, const double* x0, double h, double* red, bool& dirty) {
-  constexpr int W = RecW<DIM>::value;
-  HillGeom<DIM> hg;
-  dirty = false;
-  double ba = 0.0;
-  if (d_hill_prepare<DIM>(g, x0, hg)) {
-    long long total = 1;
-#pragma unroll
-    for (int d = 0; d < DIM; d++) total *= (2 * g.supp[d] + 1);
-    for (long long w = threadIdx.x; w < total; w += blockDim.x) {
-      int idx[DIM];
-      long long lin;
-      if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
-      double etot, force[DIM];
-      bool cnz;
-      if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
-      double add = h * etot;
-      if (MODE != kPassIntegrate) {
-        double* r = g.rec + lin * W;
-        if (MODE == kPassAtomic || g.dup_possible) {
-          atomicAdd(r, add);
-#pragma unroll
-          for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
-        } else {
-          r[0] += add;
-#pragma unroll
-          for (int d = 0; d < DIM; d++) r[1 + d] += h * force[d];
-        }
-      }
-      ba += add * g.vol_element;
-      dirty |= cnz;
-    }
-  }
-  return block_sum(ba, red);  // contains __syncthreads: record writes are visible CTA-wide after it
-}
-
 // GaussGrid::add_value for one hill by the whole CTA, lib/gaussian_grid.h:176-372
 template <int DIM>
-__device__ double cta_deposit(const GridDesc& g, const double* x0, double h, double* red, int* sflag) {
+__device__ double cta_deposit(const GridDesc& g, const double* x0, double h, double* red, int* sflag, AxisEntry* axis) {
   constexpr int W = RecW<DIM>::value;
   if (threadIdx.x == 0) *sflag = 0;
   bool dirty;
-  double tot = cta_window_pass<DIM, kPassStore>(g, x0, h, red, dirty);
+  double tot = cta_window_pass<DIM, kPassStore>(g, x0, h, red, dirty, axis);
   if (dirty) *sflag = 1;
   __syncthreads();
   if (*sflag) {  // duplicate_boundary, lib/gaussian_grid.h:365-368
@@ -285,6 +240,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ int s_go, s_tail;
   __shared__ double s_prefactor;
   __shared__ RoundState rs;
+  __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
   const int mode = st->round_mode;
   if (mode == 2) {  // the parallel round already committed this round
     if (threadIdx.x == 0) {
@@ -336,7 +292,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
     double pos[DIM];
     for (int d = 0; d < DIM; d++) pos[d] = s_pos[d];
     double h = s_h;
-    double temp = cta_deposit<DIM>(bias, pos, h, red, &sflag);
+    double temp = cta_deposit<DIM>(bias, pos, h, red, &sflag, s_axis);
     if (t0) {
       rs.hills_added++;
       drained += temp;
@@ -352,7 +308,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
     __syncthreads();
     if (s_go) {
       double hh = s_h;
-      double t2 = cta_deposit<DIM>(bias, pos, hh, red, &sflag);
+      double t2 = cta_deposit<DIM>(bias, pos, hh, red, &sflag, s_axis);
       if (t0) {
         log_event<DIM>(rs, hist, log, prm.log_cap, pos, hh, t2, 'v', prm.total_volume);
         rs.hills_added++;
@@ -440,7 +396,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
       double this_h = s_h;
       int buffer_flag = 0;  // thread 0
       if (s_go) {
-        double ba = cta_deposit<DIM>(bias, pos, this_h, red, &sflag);
+        double ba = cta_deposit<DIM>(bias, pos, this_h, red, &sflag, s_axis);
         if (t0) {
           rs.temp_hill_cum += ba;
           rs.hills_added++;
@@ -454,7 +410,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
         __syncthreads();
         if (s_go) {
           double temp_h = s_h;
-          double ba2 = cta_deposit<DIM>(bias, pos, temp_h, red, &sflag);
+          double ba2 = cta_deposit<DIM>(bias, pos, temp_h, red, &sflag, s_axis);
           if (t0) {
             rs.hills_added++;
             log_event<DIM>(rs, hist, log, prm.log_cap, pos, temp_h, ba2, 'u', prm.total_volume);
@@ -783,6 +739,7 @@ __global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, con
                                                               const double* __restrict__ heights,
                                                               double* __restrict__ ba) {
   __shared__ double red[33];
+  __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
   if (st->round_mode != 1) return;
   const int n = st->n_fast;
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
@@ -790,7 +747,7 @@ __global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, con
 #pragma unroll
     for (int d = 0; d < DIM; d++) pos[d] = centres[(long)k * DIM + d];
     bool dirty;
-    double tot = cta_window_pass<DIM, kPassIntegrate>(bias, pos, heights[k], red, dirty);
+    double tot = cta_window_pass<DIM, kPassIntegrate>(bias, pos, heights[k], red, dirty, s_axis);
     if (threadIdx.x == 0) ba[k] = tot;
   }
 }
@@ -833,6 +790,7 @@ __global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasD
                                                             const int4* __restrict__ cells, int* flags) {
   __shared__ double red[33];
   __shared__ int s_k;
+  __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
   if (st->round_mode < 2) return;
   const int n = st->n_fast;
   const int epoch = st->round_epoch;
@@ -851,7 +809,7 @@ __global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasD
 #pragma unroll
     for (int d = 0; d < DIM; d++) pos[d] = centres[(long)k * DIM + d];
     bool dirty;
-    cta_window_pass<DIM, kPassAtomic>(bias, pos, heights[k], red, dirty);
+    cta_window_pass<DIM, kPassAtomic>(bias, pos, heights[k], red, dirty, s_axis);
     if (dirty) flags[0] = 1;
     __threadfence();
     __syncthreads();

@@ -431,6 +431,155 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return red[32];
 }
 
+// ---------------------------------------------------------------- one hill's window over a CTA
+
+// One hill's window spread over the CTA.  kPassStore: plain read-modify-writes (one hill at a time,
+// so no two threads touch the same point unless a periodic window revisits it; then fp64 atomics,
+// whose operands are equal, keep the result order-independent).  kPassAtomic: fp64 REDs, for hills
+// deposited concurrently.  kPassIntegrate: no writes, only add_value's integral.  The window-point ->
+// thread mapping and the reduction tree are the same in every mode, so the integral comes out
+// bit-identical whichever pass computed it.  Every thread receives the integral.
+//
+// When every dimension has a periodic boundary the hill is a plain product Gaussian
+// (lib/gaussian_grid.h:340-352): the CTA first tabulates, per dimension and window offset, the
+// wrapped grid index, dp^2, exp(-dp^2) and 2 dp / sigma~ (a few dozen exp instead of one per window
+// point), then every window point is three table look-ups, the support test on the same sum of
+// squares the reference forms, two multiplications and the adds.
+enum { kPassIntegrate = 0, kPassStore = 1, kPassAtomic = 2 };
+constexpr int kAxisMax = 96;  // window offsets per dimension the tables hold; wider windows take the general path
+
+struct AxisEntry {
+  double dpsq, e, t5;
+  int idx;  // wrapped grid index, -1: the reference skips this offset
+  int pad;
+};
+
+template <int DIM> __device__ __forceinline__ bool d_separable(const GridDesc& g) {
+  if (DIM == 1 || g.dup_possible) return false;
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+    if (!g.bper[d] || 2 * g.supp[d] + 1 > kAxisMax) return false;
+  return true;
+}
+
+template <int DIM, int MODE>
+__device__ __forceinline__ void d_point_add(const GridDesc& g, long long lin, double add, double h, const double* force) {
+  constexpr int W = RecW<DIM>::value;
+  if (MODE == kPassIntegrate) return;
+  double* r = g.rec + lin * W;
+  if (MODE == kPassAtomic || g.dup_possible) {
+    atomicAdd(r, add);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
+  } else {
+    r[0] += add;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) r[1 + d] += h * force[d];
+  }
+}
+
+// axis: shared memory, DIM * kAxisMax entries (only touched on the separable path)
+template <int DIM, int MODE>
+__device__ double cta_window_pass(const GridDesc& g, const double* x0, double h, double* red, bool& dirty,
+                                  AxisEntry* axis) {
+  HillGeom<DIM> hg;
+  dirty = false;
+  double ba = 0.0;
+  const bool ok = d_hill_prepare<DIM>(g, x0, hg);
+  long long total = 1;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) total *= (2 * g.supp[d] + 1);
+  if (ok && d_separable<DIM>(g)) {
+    __syncthreads();  // the tables may still be read by the previous hill's pass
+    for (int t = threadIdx.x; t < DIM * kAxisMax; t += blockDim.x) {
+      const int d = t / kAxisMax, o = t - d * kAxisMax;
+      if (o > 2 * g.supp[d]) continue;
+      AxisEntry a;
+      a.idx = -1;
+      a.dpsq = a.e = a.t5 = 0.0;
+      a.pad = 0;
+      int i = o - g.supp[d] + hg.xi[d];  // lib/gaussian_grid.h:229-268
+      bool in = true;
+      if (i >= g.n[d]) {
+        if (!g.periodic[d]) in = false;
+        i %= g.n[d];
+      }
+      if (i < 0) {
+        if (!g.periodic[d]) in = false;
+        i += g.n[d];
+        if (i < 0) in = false;
+      }
+      if (in) {
+        const double* row = g.ptab[d] + (long long)i * kPtabW;
+        double v = __dsub_rn(row[0], hg.x[d]);
+        if (g.periodic[d]) v = __dsub_rn(v, __dmul_rn(d_round(__ddiv_rn(v, g.len[d])), g.len[d]));
+        v = __ddiv_rn(v, g.sigma[d]);
+        const double sq = __dmul_rn(v, v);
+        if (row[1] != 0.0 && sq < kGaussSupport) {  // a larger square alone already fails the support test
+          a.idx = i;
+          a.dpsq = sq;
+          a.e = d_exp_support(-sq);
+          a.t5 = 2.0 * v / g.sigma[d];
+        }
+      }
+      axis[t] = a;
+    }
+    __syncthreads();
+    double inv_denom = 1.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) inv_denom *= g.sqrtpi_sigma[d];
+    inv_denom = 1.0 / inv_denom;
+    const int span0 = 2 * g.supp[0] + 1, span1 = 2 * g.supp[DIM > 1 ? 1 : 0] + 1;
+    for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+      int o[3];
+      long long q = w;
+      o[0] = (int)(q % span0);
+      q /= span0;
+      if (DIM > 2) {
+        o[1] = (int)(q % span1);
+        o[2] = (int)(q / span1);
+      } else {
+        o[1] = (int)q;
+        o[2] = 0;
+      }
+      double dp2 = 0.0, expo = inv_denom, t5[DIM];
+      long long lin = 0, pstride = 1;
+      bool in = true;
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        const AxisEntry a = axis[d * kAxisMax + o[d]];
+        in = in && a.idx >= 0;
+        dp2 = __dadd_rn(dp2, a.dpsq);
+        expo *= a.e;
+        t5[d] = a.t5;
+        lin += (long long)a.idx * pstride;
+        pstride *= g.n[d];
+      }
+      if (!in || !(dp2 < kGaussSupport)) continue;
+      double force[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) force[d] = -(t5[d] * expo);
+      const double add = h * expo;
+      d_point_add<DIM, MODE>(g, lin, add, h, force);
+      ba += add * g.vol_element;
+    }
+  } else if (ok) {
+    for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+      int idx[DIM];
+      long long lin;
+      if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
+      double etot, force[DIM];
+      bool cnz;
+      if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
+      const double add = h * etot;
+      d_point_add<DIM, MODE>(g, lin, add, h, force);
+      ba += add * g.vol_element;
+      dirty |= cnz;
+    }
+  }
+  return block_sum(ba, red);  // contains __syncthreads: record writes are visible CTA-wide after it
+}
+
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;

@@ -355,38 +355,14 @@ template <int DIM>
 __global__ void __launch_bounds__(256) deposit_hills_kernel(GridDesc g, long n, const double* __restrict__ centres,
                                                             const double* __restrict__ heights,
                                                             double* __restrict__ ba_out, int* flags) {
-  constexpr int W = RecW<DIM>::value;
   __shared__ double red[33];
-  long long total = 1;
-#pragma unroll
-  for (int d = 0; d < DIM; d++) total *= (2 * g.supp[d] + 1);
+  __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
   for (long hill = blockIdx.x; hill < n; hill += gridDim.x) {
-    HillGeom<DIM> hg;
     double x0[DIM];
 #pragma unroll
     for (int d = 0; d < DIM; d++) x0[d] = centres[hill * DIM + d];
-    double h = heights[hill];
-    bool ok = d_hill_prepare<DIM>(g, x0, hg);
-    double ba = 0.0;
-    bool dirty = false;
-    if (ok) {
-      for (long long w = threadIdx.x; w < total; w += blockDim.x) {
-        int idx[DIM];
-        long long lin;
-        if (!d_window_index<DIM>(g, hg, w, idx, lin)) continue;
-        double etot, force[DIM];
-        bool cnz;
-        if (!d_hill_term<DIM>(g, hg, idx, etot, force, cnz)) continue;
-        double add = h * etot;
-        double* r = g.rec + lin * W;
-        atomicAdd(r, add);
-        ba += add * g.vol_element;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) atomicAdd(r + 1 + d, h * force[d]);
-        dirty |= cnz;
-      }
-    }
-    double tot = block_sum(ba, red);
+    bool dirty;
+    const double tot = cta_window_pass<DIM, kPassAtomic>(g, x0, heights[hill], red, dirty, s_axis);
     if (threadIdx.x == 0 && ba_out) ba_out[hill] = tot;
     if (dirty) flags[0] = 1;
   }
