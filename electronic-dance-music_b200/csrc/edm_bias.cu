@@ -561,13 +561,15 @@ template <int DIM>
 __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc target, RoundParams prm, int n_max,
                                                          BiasDev* st, HillAccepted* acc, HillAccepted* acc_tmp,
                                                          double* __restrict__ centres, double* heights,
-                                                         PlanHill<DIM>* plan, int4* __restrict__ cells) {
+                                                         PlanHill<DIM>* plan, int4* __restrict__ cells,
+                                                         double* terms, int* term_j, int term_cap) {
   constexpr int W = RecW<DIM>::value;
   constexpr int NC = 1 << DIM;
   __shared__ double s_prefactor;
   __shared__ int s_mode;
-  __shared__ double s_contrib[32][NC * W];
   __shared__ double s_rec[NC][W];
+  __shared__ int s_off[EDM_ROUND_MAX];  // where entry k's list of reaching predecessors starts
+  __shared__ int s_total;
   __shared__ int s_nb;
   __shared__ int4 s_cells[EDM_ROUND_MAX];          // centre cell + ok of every planned entry
   __shared__ unsigned short s_ndep[EDM_ROUND_MAX]; // earlier entries that can reach entry k's corners
@@ -671,11 +673,35 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
     if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
   }
   __syncthreads();
-  if (threadIdx.x >= 32) return;
 
-  // the others in candidate order: patch the corner records with every earlier reaching hill
-  const int lane = threadIdx.x;
-  for (int k = nb; k < nall; k++) {
+  // The others.  First, all warps at once: for every such hill k, the per-unit-height terms each earlier
+  // reaching hill j adds to k's corner records, listed in order j (they do not depend on any height).
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  if (warp == 0) {  // list offsets: exclusive scan of the counts
+    int carry = 0;
+    for (int base = nb; base < nall; base += 32) {
+      const int k = base + lane;
+      const int v = k < nall ? (int)s_ndep[k] : 0;
+      int inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (k < nall) s_off[k] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) {
+      s_total = carry;
+      if (carry > term_cap) {  // more interplay than the lists hold: the in-order kernel takes the round
+        st->round_mode = 0;
+        st->n_fast = 0;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_total > term_cap) return;
+  for (int k = nb + warp; k < nall; k += nwarps) {
     if (s_ndep[k] == 0) continue;
     const PlanHill<DIM>& p = plan[k];
     int lo[DIM], up[DIM];
@@ -684,13 +710,15 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       lo[d] = p.lo[d];
       up[d] = p.up[d];
     }
-    double accv = 0.0;
-    if (lane < NC * W) accv = p.rec[lane / W][lane % W];
+    int pos = s_off[k];
     for (int j0 = 0; j0 < k; j0 += 32) {
       const int j = j0 + lane;
-      bool near = j < k && d_hill_near<DIM>(bias, s_cells[j], lo);
+      const bool near = j < k && d_hill_near<DIM>(bias, s_cells[j], lo);
+      const unsigned m = __ballot_sync(0xffffffffu, near);
       if (near) {
-        const double hj = heights[j];
+        const int slot = pos + __popc(m & ((1u << lane) - 1u));
+        term_j[slot] = j;
+        double* T = terms + (size_t)slot * (NC * W);
 #pragma unroll
         for (int c = 0; c < NC; c++) {
           int idx[DIM];
@@ -709,20 +737,32 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
 #pragma unroll
             for (int d = 0; d < DIM; d++) force[d] = 0.0;
           }
-          s_contrib[lane][c * W] = hj * etot;
+          T[c * W] = etot;
 #pragma unroll
-          for (int d = 0; d < DIM; d++) s_contrib[lane][c * W + 1 + d] = hj * force[d];
-          if (W > DIM + 1) s_contrib[lane][c * W + W - 1] = 0.0;
+          for (int d = 0; d < DIM; d++) T[c * W + 1 + d] = force[d];
+          if (W > DIM + 1) T[c * W + W - 1] = 0.0;
         }
       }
-      __syncwarp();
-      unsigned m = __ballot_sync(0xffffffffu, near);
-      while (m) {
-        int src = __ffs(m) - 1;
-        m &= m - 1;
-        if (lane < NC * W) accv += s_contrib[src][lane];
-      }
-      __syncwarp();
+      pos += __popc(m);
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+
+  // Then one warp, in candidate order: corner records + sum over the list of h_j * term (the adds a
+  // hill-by-hill deposit would have made to those records, in the same order), interpolate, scale.
+  for (int k = nb; k < nall; k++) {
+    const int cnt = s_ndep[k];
+    if (cnt == 0) continue;
+    const PlanHill<DIM>& p = plan[k];
+    double accv = 0.0;
+    if (lane < NC * W) accv = p.rec[lane / W][lane % W];
+    const int first = s_off[k];
+#pragma unroll 4
+    for (int e = 0; e < cnt; e++) {
+      const double hj = heights[term_j[first + e]];
+      const double t = lane < NC * W ? terms[(size_t)(first + e) * (NC * W) + lane] : 0.0;
+      accv += hj * t;
     }
     if (lane < NC * W) s_rec[lane / W][lane % W] = accv;
     __syncwarp();
@@ -1010,14 +1050,20 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     const long n_max = cap < EDM_ROUND_MAX ? cap : EDM_ROUND_MAX;
     const size_t b_dbl = (size_t)(DIM + 2) * cap * sizeof(double);
     const size_t b_plan = ((size_t)n_max * sizeof(PlanHill<DIM>) + 15) / 16 * 16;
-    EDM_TRY(b->fast.reserve(b_dbl + b_plan + (size_t)n_max * sizeof(int4)));
+    const size_t b_cells = (size_t)n_max * sizeof(int4);
+    // local tempering: (later hill, earlier reaching hill) pairs the plan can list
+    const int term_cap = 16384;
+    const size_t b_terms = (size_t)term_cap * (1 << DIM) * RecW<DIM>::value * sizeof(double);
+    EDM_TRY(b->fast.reserve(b_dbl + b_plan + b_cells + b_terms + (size_t)term_cap * sizeof(int)));
     double* centres = b->fast.as<double>();
     double* heights = centres + (size_t)DIM * cap;
     double* ba = heights + cap;
     PlanHill<DIM>* plan = reinterpret_cast<PlanHill<DIM>*>(b->fast.as<char>() + b_dbl);
     int4* cells = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan);
+    double* terms = reinterpret_cast<double*>(b->fast.as<char>() + b_dbl + b_plan + b_cells);
+    int* term_j = reinterpret_cast<int*>(b->fast.as<char>() + b_dbl + b_plan + b_cells + b_terms);
     round_plan_kernel<DIM><<<1, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres,
-                                               heights, plan, cells);
+                                               heights, plan, cells, terms, term_j, term_cap);
     const int blocks = (int)(n_max < 148 * 4 ? n_max : 148 * 4);
     round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
     round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);

@@ -226,6 +226,12 @@ BIAS_CASES = {
              "bias_sigma 0.25 0.25 0.25\nhill_density 80",
         T=300.0, kB=0.0019872, sub=([0.0] * 3, [4.0] * 3), periodic=[1, 0, 1], skin=[0.0] * 3, n=3000, lo=0.0, hi=4.0,
         steps=3),
+    "2d_local_tempering_too_entangled": dict(  # more (hill, earlier reaching hill) pairs than the plan lists: in order
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 700\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\n"
+             "bias_sigma 0.25 0.25",
+        T=300.0, kB=0.0019872, sub=([0.0, 0.0], [8.0, 8.0]), periodic=[1, 1], skin=[0.0, 0.0], n=20000, lo=0.0, hi=8.0,
+        steps=2),
     "3d_all_candidates_deposit": dict(
         text="tempering 0\nhill_prefactor 1.0\nbias_per_step 0.4\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
              "bias_spacing 0.25 0.25 0.25\nbias_sigma 0.5 0.5 0.5",
@@ -310,6 +316,8 @@ def test_bias_round_parity(edm, port, tmp_path, name):
     assert len(log) > 0
     info = bd.round_info()
     assert info["parallel"] + info["split"] + info["in_order"] == BIAS_CASES[name]["steps"]
+    if name == "2d_local_tempering_too_entangled":
+        assert info["in_order"] == 2, info
     if name in PARALLEL_ROUND_CASES:   # the all-hills-at-once round really ran (and fell back where it must)
         assert info["parallel"] + info["split"] >= PARALLEL_ROUND_CASES[name], info
 
