@@ -65,6 +65,8 @@ COORD_WORKLOADS = {
         T=300.0, kB=0.0019872, lo=[0.0] * 3, hi=[64.0] * 3, atoms=10_000_000, atoms_scale_with_gpus=False,
         prewarm=20000, warm_h=0.02 / 250),
 }
+C2_LOCAL_TEXT = ("tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.1\n"
+                 "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025\n")
 C5_TEXT = ("tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.0002\n"
            "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025\n")
 
@@ -266,7 +268,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = edm.lib()
     tmp = tempfile.mkdtemp()
-    edm_file = write_edm(tmp, C5_TEXT if args.workload == "c5_pair_rdf_backlog" else None)
+    edm_file = write_edm(tmp, {"c5_pair_rdf_backlog": C5_TEXT, "c2_pair_rdf_local_tempering": C2_LOCAL_TEXT}.get(args.workload))
     bias = edm.bias_from_edm(edm_file, TEMPERATURE, BOLTZ, [1.68], [5.0], [1.68], [5.0], [0], [0.0], device=local_rank)
     warm_rng = np.random.default_rng(1234 + 1)
     warm = prewarm_hills(warm_rng)          # same hills on every rank: replicas start identical
@@ -636,7 +638,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2_pair_rdf",
-                    choices=["c2_pair_rdf", "c5_pair_rdf_backlog"] + sorted(COORD_WORKLOADS),
+                    choices=["c2_pair_rdf", "c5_pair_rdf_backlog", "c2_pair_rdf_local_tempering"] + sorted(COORD_WORKLOADS),
                     help="c2_pair_rdf is the benchmark (BASELINE.json configs[1]); the others are the remaining configs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -510,7 +510,7 @@ __device__ __forceinline__ bool d_window_reaches(const GridDesc& g, int d, int x
 
 // Cheap superset of "hill j's window can write a corner of hill k's interpolation cell", for the
 // O(n^2) scan: cj = hill j's centre cell (periodic dims folded into [0, n)) and ok flag, lo = the low
-// corner of k's cell.  A window reaches at most minisize cells from its centre and the upper corner
+// corner of k's cell.  A hill adds nothing beyond supp cells from its centre and the upper corner
 // is one cell further; the exact per-corner test (d_window_reaches) follows for the survivors.
 template <int DIM>
 __device__ __forceinline__ bool d_hill_near(const GridDesc& g, const int4& cj, const int* lo) {
@@ -521,7 +521,7 @@ __device__ __forceinline__ bool d_hill_near(const GridDesc& g, const int4& cj, c
     int dist = xi[d] - lo[d];
     dist = dist < 0 ? -dist : dist;
     if (g.periodic[d]) dist = min(dist, g.n[d] - dist);
-    if (dist > g.minisize[d] + 1) return false;
+    if (dist > g.supp[d] + 1) return false;  // beyond supp cells the support test fails: nothing is added
   }
   return true;
 }
@@ -1102,9 +1102,7 @@ int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
   static int allow_fast = -1;
   if (allow_fast < 0) allow_fast = getenv("EDM_NO_FAST_ROUND") ? 0 : 1;
   bool fast = allow_fast != 0;
-  // 1-D windows are a sizeable fraction of the grid: with local tempering nearly every hill depends on
-  // its predecessors and the in-order kernel is the better fit
-  if (b->prm.dim == 1 && (local_tempering || !deposit1d_eligible(b->bias))) fast = false;
+  if (b->prm.dim == 1 && !deposit1d_eligible(b->bias)) fast = false;
   switch (b->prm.dim) {
     case 1: return launch_round_dim<1>(b, rp, hist, target, fast, st);
     case 2: return launch_round_dim<2>(b, rp, hist, target, fast, st);

@@ -240,7 +240,7 @@ BIAS_CASES = {
 
 
 # rounds that must have run as parallel rounds (the others: backlog / limiter / 1-D local tempering)
-PARALLEL_ROUND_CASES = {"c1_sanity_density": 6, "c5_rdf_tight_limiter_backlog": 10, "2d_limiter_cuts_the_round": 4,
+PARALLEL_ROUND_CASES = {"c1_sanity_density": 6, "1d_local_well_tempering": 5, "c5_rdf_tight_limiter_backlog": 10, "2d_limiter_cuts_the_round": 4,
                          "c2_rdf_threshold_tempering": 6, "2d_local_well_tempering": 4,
                         "c3_2d_local_tempering_sparse": 4, "2d_mcgdp_walls_threshold_tempering": 4,
                         "c4_3d_density": 3, "3d_local_tempering_mixed_walls": 3}
