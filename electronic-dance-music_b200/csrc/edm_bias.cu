@@ -1068,6 +1068,12 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
     round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
     count_launches(3);
+    // everything so far only read the grid; whoever else still reads it (this step's force update on
+    // another stream) must be done before the first write
+    if (b->round_after) {
+      EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
+      b->round_after = nullptr;
+    }
     if (DIM == 1 && deposit1d_eligible(b->bias)) {
       // owner-computes deposit of hills [0, n_fast): staged from the stored values, written back if the
       // round was committed (n_fast = 0 stages the stored values themselves)
@@ -1086,6 +1092,10 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     count_launches(1);
   }
   count_launches(1);
+  if (b->round_after) {  // the in-order kernel writes the grid as well
+    EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
+    b->round_after = nullptr;
+  }
   hill_round_kernel<DIM><<<1, 512, 0, st>>>(bias, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log);
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
@@ -1191,6 +1201,12 @@ int edm_bias_destroy(edm_bias_t* b) {
   if (b->st_copy) cudaStreamDestroy(b->st_copy);
   if (b->ev_f_up) cudaEventDestroy(b->ev_f_up);
   if (b->ev_f_final) cudaEventDestroy(b->ev_f_final);
+  if (b->st_side) {
+    cudaStreamDestroy(b->st_side);
+    cudaEventDestroy(b->ev_fork);
+    cudaEventDestroy(b->ev_forces);
+    cudaEventDestroy(b->ev_join);
+  }
   if (b->st_up) {
     cudaStreamDestroy(b->st_up);
     for (int c = 0; c < edm_bias::kMaxChunks; c++) {
@@ -1414,6 +1430,43 @@ int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride,
   // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
   EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, st));
   return edm_bias_launch_round(b, n, st);
+}
+
+int edm_bias_round_after(edm_bias_t* b, void* event) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  b->round_after = (cudaEvent_t)event;
+  return EDM_OK;
+}
+
+// update_forces and the hill round of one step on device buffers.  The round's selection, plan,
+// integrals and decision only read the grid, so they run on a side stream next to the force update;
+// the deposit waits for the force update (it reads the start-of-step bias), and the caller's stream
+// waits for the round.
+int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                             const int* mask, int apply_mask, int do_hills, const double* runiform, uint64_t seed,
+                             uint64_t step, double* energy, void* stream) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  if (!do_hills) return edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream);
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!b->st_side) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_side, cudaStreamNonBlocking));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_forces, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  }
+  EDM_CUDA(cudaEventRecord(b->ev_fork, st));
+  EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
+  if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream));
+  EDM_CUDA(cudaEventRecord(b->ev_forces, st));
+  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+  EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
+  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, b->st_side));
+  b->round_after = b->ev_forces;
+  EDM_TRY(edm_bias_launch_round(b, n, b->st_side));
+  EDM_CUDA(cudaEventRecord(b->ev_join, b->st_side));
+  EDM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
+  return EDM_OK;
 }
 
 int edm_bias_add_hills(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform, const int* mask,

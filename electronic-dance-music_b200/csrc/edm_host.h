@@ -136,5 +136,9 @@ struct edm_bias {
   cudaStream_t st_up = nullptr;
   cudaEvent_t ev_chunk_up[kMaxChunks] = {}, ev_chunk_done[kMaxChunks] = {};
   double* d_chunk_energy = nullptr;
+  // device-buffer coordinate step: the read-only part of the hill round runs beside the force update
+  cudaStream_t st_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_forces = nullptr, ev_join = nullptr;
+  cudaEvent_t round_after = nullptr;  // borrowed, one-shot: the next round's first grid write waits for it
   cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };

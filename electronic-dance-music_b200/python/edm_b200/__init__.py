@@ -85,6 +85,9 @@ EXPORTS = {
     "edm_bias_update_forces": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, C.c_long, c_ip, C.c_int, c_dp]),
     "edm_bias_step_coords": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, C.c_long, c_ip, C.c_int, C.c_int, c_dp,
                                        C.c_uint64, C.c_uint64, c_dp]),
+    "edm_bias_step_coords_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, C.c_int, vp,
+                                           C.c_uint64, C.c_uint64, vp, vp]),
+    "edm_bias_round_after": (C.c_int, [vp, vp]),
     "edm_bias_update_forces_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, vp, vp]),
     "edm_bias_add_hills": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_ip, C.c_int, C.c_uint64, C.c_uint64]),
     "edm_bias_add_hills_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, vp, C.c_int, C.c_uint64, C.c_uint64, vp]),

@@ -167,6 +167,13 @@ int edm_bias_step_coords(edm_bias_t* b, long n, const double* x, long xstride, d
                          const int* mask, int apply_mask, int do_hills, const double* runiform, uint64_t seed,
                          uint64_t step, double* energy);
 
+/* The same step on DEVICE buffers (energy: device pointer to one double, may be NULL).  The round's selection,
+ * plan, integrals and decision only read the grid and run on an internal stream beside the force update; the
+ * deposit waits for the force update, `stream` waits for the round.  Never synchronises the host. */
+int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
+                             const int* mask, int apply_mask, int do_hills, const double* runiform, uint64_t seed,
+                             uint64_t step, double* energy, void* stream);
+
 /* EDMBias::add_hills, lib/edm_bias.cpp:401-411 (= pre_add_hill(n); add_hill per masked atom;
  * post_add_hill()).  runiform may be NULL: uniforms then come from edm_uniform(seed, step, i). */
 int edm_bias_add_hills(edm_bias_t* b, long n, const double* x, long xstride, const double* runiform,
@@ -234,6 +241,11 @@ int edm_pair_select_cells_dev(edm_bias_t* b, long natoms, const double* x, doubl
 int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream);
 int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, long cap,
                               long long est_hill_count, void* stream);
+/* One-shot: the next hill round launched for `b` (add_hills_dev, hills_commit_dev, ...) waits for `event`
+ * (a cudaEvent_t) right before its first write to the bias grid.  Lets a caller run selection, exchange
+ * and the round's read-only kernels on a second stream while this step's force update, recorded by
+ * `event`, still reads the start-of-step bias. */
+int edm_bias_round_after(edm_bias_t* b, void* event);
 
 /* ------------------------------------------------------------------ measurement hooks (bench.py) */
 

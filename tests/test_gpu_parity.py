@@ -268,7 +268,19 @@ def run_bias_case(edm, port, tmp_path, name, masked=False, fused=False):
         fd = np.zeros((n, 3))
         am = 2 if masked else -1
         eo = bo.update_forces(x, fo, am)
-        if fused:   # fix edm's post_force as one pipelined call
+        if fused == "dev":   # device buffers: the round's read-only kernels run beside the force update
+            import ctypes as C
+            import torch
+            xt, ft, ut = torch.from_numpy(x).cuda(), torch.from_numpy(fd).cuda(), torch.from_numpy(u).cuda()
+            mt = torch.from_numpy(mask).cuda() if mask is not None else None
+            et = torch.zeros(1, dtype=torch.float64, device="cuda")
+            edm.check(edm.lib().edm_bias_step_coords_dev(bd.h, n, xt.data_ptr(), 3, ft.data_ptr(), 3,
+                                                         mt.data_ptr() if mt is not None else None, am, 1, ut.data_ptr(),
+                                                         0, step, et.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            ed = float(et.item())
+            fd[:] = ft.cpu().numpy()
+        elif fused:   # fix edm's post_force as one pipelined call
             ed = bd.step_coords(x, fd, u, mask, am)
         else:
             ed = bd.update_forces(x, fd, mask, am)
@@ -340,6 +352,14 @@ def test_bias_masked_atoms(edm, port, tmp_path):
 def test_fused_coordinate_step_parity(edm, port, tmp_path, name):
     """edm_bias_step_coords (update_forces + add_hills, one upload, chunked pipeline) against the oracle."""
     bd, bo = run_bias_case(edm, port, tmp_path, name, masked=(name == "c1_sanity_density"), fused=True)
+    compare_bias(bd, bo)
+
+
+@pytest.mark.parametrize("name", ["c1_sanity_density", "c3_2d_local_tempering_sparse", "c5_rdf_tight_limiter_backlog",
+                                  "3d_local_tempering_mixed_walls"])
+def test_fused_device_step_parity(edm, port, tmp_path, name):
+    """edm_bias_step_coords_dev: force update and hill round of one step on two streams, deposit after the forces."""
+    bd, bo = run_bias_case(edm, port, tmp_path, name, masked=(name == "c1_sanity_density"), fused="dev")
     compare_bias(bd, bo)
 
 
