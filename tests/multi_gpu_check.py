@@ -117,6 +117,8 @@ def coord_check(tmp, rank, world, local):
     edev = torch.zeros(1, dtype=torch.float64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     xs, us, es, fs = [], [], [], []
+    side = torch.cuda.Stream()
+    ev_fork, ev_k1, ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     for step in range(steps):
         rng = np.random.default_rng([77, rank, step])
         x = np.ascontiguousarray(rng.uniform(-1, 17, size=(n, 2)))
@@ -125,14 +127,25 @@ def coord_check(tmp, rank, world, local):
         us.append(u)
         xd, ud = torch.from_numpy(x).cuda(), torch.from_numpy(u).cuda()
         fdev.zero_()
+        # the application's pattern: force update on the main stream; selection, exchange and the round on a
+        # side stream, whose deposit waits (edm_bias_round_after) for the force update to finish reading
+        main = torch.cuda.current_stream()
+        ev_fork.record(main)
+        side.wait_event(ev_fork)
         edm.check(L.edm_bias_update_forces_dev(b.h, n, xd.data_ptr(), 2, fdev.data_ptr(), 2, None, -1, edev.data_ptr(), st))
+        ev_k1.record(main)
+        with torch.cuda.stream(side):
+            sst = side.cuda_stream
+            edm.check(L.edm_bias_select_dev(b.h, n, xd.data_ptr(), 2, ud.data_ptr(), None, -1, n * world, 0, step,
+                                            rank * n, sst))
+            edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, sst))
+            dist.all_gather_into_tensor(gathered, block)
+            edm.check(L.edm_bias_round_after(b.h, ev_k1.cuda_event))
+            edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, n * world, sst))
+            ev_join.record(side)
+        main.wait_event(ev_join)
         es.append(float(edev.item()))
         fs.append(fdev.cpu().numpy().copy())
-        edm.check(L.edm_bias_select_dev(b.h, n, xd.data_ptr(), 2, ud.data_ptr(), None, -1, n * world, 0, step,
-                                        rank * n, st))
-        edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, st))
-        dist.all_gather_into_tensor(gathered, block)
-        edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, n * world, st))
     torch.cuda.synchronize()
     v, dv = b.bias_grid.get_arrays()
     mine = torch.from_numpy(np.concatenate([v, dv.ravel()])).cuda()
