@@ -154,6 +154,35 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device), so the pinned host
+    buffers of the end-to-end path are first-touched on the GPU's own NUMA node.  With one process per GPU and
+    eight GPUs on two sockets, half of the host<->device copies otherwise cross the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        dev = "%s:%s" % (dom[-4:], rest)
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % dev.lower()
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 # ------------------------------------------------------------------ reference arm / CPU baseline
 
 def _cpu_worker(args):
@@ -266,6 +295,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        bind_to_gpu_numa_node(local_rank)
     L = edm.lib()
     tmp = tempfile.mkdtemp()
     edm_file = write_edm(tmp, {"c5_pair_rdf_backlog": C5_TEXT, "c2_pair_rdf_local_tempering": C2_LOCAL_TEXT}.get(args.workload))
