@@ -1195,6 +1195,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->io4.release();
   b->cells.release();
   b->fast.release();
+  b->list.release();
   b->cand.release();
   if (b->h_pair_flags) cudaFreeHost((void*)b->h_pair_flags);
   if (b->st_main) cudaStreamDestroy(b->st_main);

@@ -123,6 +123,13 @@ struct edm_bias {
   int brick_dims[3] = {0, 0, 0};       // bricks of the last pair step (0: direct search)
   long long pair_fallbacks = 0;        // steps that fell back to the direct search
   double brick_scale = 1.0;            // density inflation used to size the bricks (grows after a fallback)
+  edm::Scratch list;                   // neighbour list kept between calls: ilist | first | jlist | row_of
+  long list_inum = 0, list_nlisted = 0;
+  int list_valid = 0;
+  int* list_ilist = nullptr;
+  long* list_first = nullptr;
+  int* list_jlist = nullptr;
+  int* list_row = nullptr;
   edm::Scratch fast;                   // centres | heights | bias_added of the parallel hill round
   // streaming triple
   int in_round = 0;

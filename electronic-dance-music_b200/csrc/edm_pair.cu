@@ -778,65 +778,80 @@ __global__ void pair_reset_kernel(BiasDev* st, int* fallback, int fallback_init,
   *fmax_bits = 0ull;
 }
 
-// Neighbour-list form: one thread per listed i-row (lammps/fix_edm_pair.cpp:177-240).
-__global__ void __launch_bounds__(128) pair_list_kernel(GridDesc g, PairParams pp, long nlocal, long inum,
-                                                        const int* __restrict__ ilist, const long* __restrict__ first,
-                                                        const int* __restrict__ jlist, const double* __restrict__ x,
-                                                        const int* __restrict__ type, const double* __restrict__ runiform,
-                                                        double* __restrict__ f, double* __restrict__ partial,
-                                                        BiasDev* st, HillAccepted* acc, unsigned long long* ncalls) {
+// ---- neighbour-list form, pair-parallel (lammps/fix_edm_pair.cpp:177-240) ------------------------------
+//
+// The list a caller hands over (LAMMPS rebuilds it every ten steps or so) stays on the device between
+// calls, flattened: row_of[k] is the list row of entry k.  One thread per listed pair: consecutive
+// threads share the row atom i, so its force is a segmented warp scan and one RED per run; the
+// partner's force goes out as fp64 REDs (x, 24 B per atom, lives in L2).
+__global__ void list_rows_kernel(long inum, const long* __restrict__ first, int* __restrict__ row_of) {
+  const long ii = (long)blockIdx.x * blockDim.y + threadIdx.y;  // a warp per row
+  if (ii >= inum) return;
+  for (long k = first[ii] + threadIdx.x; k < first[ii + 1]; k += 32) row_of[k] = (int)ii;
+}
+
+__global__ void __launch_bounds__(256) pair_list_flat_kernel(GridDesc g, const double* __restrict__ cellrec,
+                                                             PairParams pp, long nlocal, long nlisted,
+                                                             const int* __restrict__ ilist,
+                                                             const int* __restrict__ row_of,
+                                                             const int* __restrict__ jlist,
+                                                             const double* __restrict__ x,
+                                                             const int* __restrict__ type,
+                                                             const double* __restrict__ runiform,
+                                                             double* __restrict__ f, double* __restrict__ partial,
+                                                             BiasDev* st, HillAccepted* acc,
+                                                             unsigned long long* ncalls) {
   __shared__ double red[33];
   double e = 0.0;
   unsigned long long npairs = 0, calls = 0;
-  long stride = (long)gridDim.x * blockDim.x;
-  for (long ii = (long)blockIdx.x * blockDim.x + threadIdx.x; ii < inum; ii += stride) {
-    const int i = ilist[ii];
-    int type_ind = 0;
-    if (pp.use_types) {
-      int it = type[i];
-      if (it == pp.itype) type_ind = 1;
-      else if (it == pp.jtype) type_ind = 0;
-      else continue;
-    }
-    const double xi = x[3 * (long)i + 0], yi = x[3 * (long)i + 1], zi = x[3 * (long)i + 2];
-    double fx = 0.0, fy = 0.0, fz = 0.0;
-    for (long k = first[ii]; k < first[ii + 1]; k++) {
-      const int j = jlist[k];
-      if (pp.use_types) {
-        int jt = type[j];
-        if (type_ind && jt != pp.jtype) continue;
-        if (!type_ind && jt != pp.itype) continue;
+  const long stride = (long)gridDim.x * blockDim.x;
+  const long nround = (nlisted + 31) / 32 * 32;  // whole warps stay together for the scan
+  for (long k = (long)blockIdx.x * blockDim.x + threadIdx.x; k < nround; k += stride) {
+    int row = -1, i = 0, j = 0;
+    bool on = k < nlisted;
+    if (on) {
+      row = row_of[k];
+      i = ilist[row];
+      j = jlist[k];
+      if (pp.use_types) {  // lammps/fix_edm_pair.cpp:179-203
+        const int it = type[i], jt = type[j];
+        if (it == pp.itype) on = jt == pp.jtype;
+        else if (it == pp.jtype) on = jt == pp.itype;
+        else on = false;
       }
-      double dx = __dsub_rn(xi, x[3 * (long)j + 0]);
-      double dy = __dsub_rn(yi, x[3 * (long)j + 1]);
-      double dz = __dsub_rn(zi, x[3 * (long)j + 2]);
-      double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-      double r = sqrt(d2);
-      double rinv = 1.0 / r;
+    }
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (on) {
+      const double dx = __dsub_rn(x[3 * (long)i + 0], x[3 * (long)j + 0]);
+      const double dy = __dsub_rn(x[3 * (long)i + 1], x[3 * (long)j + 1]);
+      const double dz = __dsub_rn(x[3 * (long)i + 2], x[3 * (long)j + 2]);
+      const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      const double rinv = rsqrt(d2);
+      const double r = d2 * rinv;  // within 2 ulp of sqrt(d2): enough for V(r); hills take the exact root
       double force;
-      e += pair_eval(g, r, force);
+      e += pair_eval_fast(g, cellrec, pp.lean != 0, r, force);
       npairs++;
-      double px = dx * rinv * force, py = dy * rinv * force, pz = dz * rinv * force;
-      fx += px;
-      fy += py;
-      fz += pz;
+      const double sc = rinv * force;
+      px = dx * sc;
+      py = dy * sc;
+      pz = dz * sc;
       const bool jlocal = j < nlocal;
-      if (jlocal) {
+      if (jlocal) {  // fix_edm_pair.cpp:223
         atomicAdd(&f[3 * (long)j + 0], -px);
         atomicAdd(&f[3 * (long)j + 1], -py);
         atomicAdd(&f[3 * (long)j + 2], -pz);
       }
-      if (pp.do_hills) {
-        int nprop = jlocal ? 2 : 1;
+      if (pp.do_hills) {  // fix_edm_pair.cpp:230-236
+        const int nprop = jlocal ? 2 : 1;
         calls += nprop;
         for (int which = 0; which < nprop; which++) {
-          unsigned long long kk = 2ULL * (unsigned long long)k + which;
-          double u = runiform ? runiform[kk] : uniform_from_key(pp.key, kk);
+          const unsigned long long kk = 2ULL * (unsigned long long)k + which;
+          const double u = runiform ? runiform[kk] : uniform_from_key(pp.key, kk);
           if (pp.accept_all || u < pp.thresh) {
-            int slot = atomicAdd(&st->n_accepted, 1);
+            const int slot = atomicAdd(&st->n_accepted, 1);
             if (slot < pp.acc_cap) {
               acc[slot].key = kk;
-              acc[slot].x[0] = r;
+              acc[slot].x[0] = sqrt(d2);
               acc[slot].x[1] = 0.0;
               acc[slot].x[2] = 0.0;
             } else {
@@ -846,9 +861,11 @@ __global__ void __launch_bounds__(128) pair_list_kernel(GridDesc g, PairParams p
         }
       }
     }
-    atomicAdd(&f[3 * (long)i + 0], fx);
-    atomicAdd(&f[3 * (long)i + 1], fy);
-    atomicAdd(&f[3 * (long)i + 2], fz);
+    if (run_totals(on ? row : -1 - (int)(threadIdx.x & 31), px, py, pz)) {
+      atomicAdd(&f[3 * (long)i + 0], px);
+      atomicAdd(&f[3 * (long)i + 1], py);
+      atomicAdd(&f[3 * (long)i + 2], pz);
+    }
   }
   double tot = block_sum(e, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
@@ -1181,52 +1198,89 @@ int edm_pair_search_info(edm_bias_t* b, int* brick_dims, double* density_scale, 
   return EDM_OK;
 }
 
-int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
-                       int jtype, long inum, const int* ilist, const long* first, const int* jlist, int do_hills,
-                       long long est_hill_count, const double* runiform, uint64_t seed, uint64_t step,
-                       edm_pair_result_t* result) {
-  EDM_REQUIRE(b && x && f && ilist && first && (jlist || first[inum] == 0), "NULL argument");
+int edm_pair_list_set(edm_bias_t* b, long inum, const int* ilist, const long* first, const int* jlist) {
+  EDM_REQUIRE(b && inum >= 0 && (inum == 0 || (ilist && first)), "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  const long nlisted = inum ? first[inum] : 0;
+  EDM_REQUIRE(nlisted == 0 || jlist, "NULL argument");
+  // ilist[inum] | first[inum+1] | jlist[nlisted] | row_of[nlisted]
+  const size_t o_first = ((size_t)inum * 4 + 7) / 8 * 8, o_jl = o_first + (size_t)(inum + 1) * 8;
+  const size_t o_row = (o_jl + (size_t)nlisted * 4 + 7) / 8 * 8;
+  EDM_TRY(b->list.reserve(o_row + (size_t)nlisted * 4 + 8));
+  char* base = b->list.as<char>();
+  b->list_inum = inum;
+  b->list_nlisted = nlisted;
+  b->list_ilist = reinterpret_cast<int*>(base);
+  b->list_first = reinterpret_cast<long*>(base + o_first);
+  b->list_jlist = reinterpret_cast<int*>(base + o_jl);
+  b->list_row = reinterpret_cast<int*>(base + o_row);
+  if (inum) {
+    EDM_CUDA(cudaMemcpyAsync(b->list_ilist, ilist, (size_t)inum * 4, cudaMemcpyHostToDevice, 0));
+    EDM_CUDA(cudaMemcpyAsync(b->list_first, first, (size_t)(inum + 1) * 8, cudaMemcpyHostToDevice, 0));
+    if (nlisted) EDM_CUDA(cudaMemcpyAsync(b->list_jlist, jlist, (size_t)nlisted * 4, cudaMemcpyHostToDevice, 0));
+    list_rows_kernel<<<(unsigned)((inum + 7) / 8), dim3(32, 8)>>>(inum, b->list_first, b->list_row);
+    count_launches(1);
+    EDM_CUDA(cudaGetLastError());
+  }
+  b->list_valid = 1;
+  return EDM_OK;
+}
+
+int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
+                         int jtype, int do_hills, long long est_hill_count, const double* runiform, uint64_t seed,
+                         uint64_t step, edm_pair_result_t* result) {
+  EDM_REQUIRE(b && x && f, "NULL argument");
+  EDM_REQUIRE(b->list_valid, "edm_pair_list_set has not been called");
   EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");
   EDM_TRY(ensure_device(b->device));
-  long nlisted = first[inum];
-  size_t bx = (size_t)nall * 3 * sizeof(double);
+  const long nlisted = b->list_nlisted;
+  const size_t bx = (size_t)nall * 3 * sizeof(double);
   EDM_TRY(b->io.reserve(bx));
   EDM_TRY(b->io2.reserve(bx));
-  // list scratch: ilist[inum] | first[inum+1] | jlist[nlisted] | type[nall] | ncalls | uniforms
-  size_t o_il = 0, o_first = (o_il + (size_t)inum * 4 + 7) / 8 * 8, o_jl = o_first + (size_t)(inum + 1) * 8;
-  size_t o_ty = (o_jl + (size_t)nlisted * 4 + 7) / 8 * 8, o_nc = (o_ty + (size_t)nall * 4 + 7) / 8 * 8;
-  size_t o_u = o_nc + 8;
-  size_t total = o_u + (runiform ? (size_t)nlisted * 2 * sizeof(double) : 0);
-  EDM_TRY(b->io4.reserve(total));
+  // per-step scratch: type[nall] | ncalls | fmax bits | cell records of the bias grid | uniforms
+  const int npts = b->bias->d.n[0];
+  const size_t o_nc = ((size_t)nall * 4 + 7) / 8 * 8, o_fm = o_nc + 8, o_crec = (o_fm + 8 + 31) / 32 * 32;
+  const size_t o_u = o_crec + (size_t)npts * 4 * sizeof(double);
+  EDM_TRY(b->io4.reserve(o_u + (runiform ? (size_t)nlisted * 2 * sizeof(double) : 0)));
   char* base = b->io4.as<char>();
-  EDM_CUDA(cudaMemcpyAsync(base + o_il, ilist, (size_t)inum * 4, cudaMemcpyHostToDevice, 0));
-  EDM_CUDA(cudaMemcpyAsync(base + o_first, first, (size_t)(inum + 1) * 8, cudaMemcpyHostToDevice, 0));
-  if (nlisted) EDM_CUDA(cudaMemcpyAsync(base + o_jl, jlist, (size_t)nlisted * 4, cudaMemcpyHostToDevice, 0));
-  if (type) EDM_CUDA(cudaMemcpyAsync(base + o_ty, type, (size_t)nall * 4, cudaMemcpyHostToDevice, 0));
+  if (type) EDM_CUDA(cudaMemcpyAsync(base, type, (size_t)nall * 4, cudaMemcpyHostToDevice, 0));
   if (runiform)
     EDM_CUDA(cudaMemcpyAsync(base + o_u, runiform, (size_t)nlisted * 2 * sizeof(double), cudaMemcpyHostToDevice, 0));
   EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
   EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, 0));
   unsigned long long* ncalls = reinterpret_cast<unsigned long long*>(base + o_nc);
+  unsigned long long* fmax_bits = reinterpret_cast<unsigned long long*>(base + o_fm);
+  double* cellrec = reinterpret_cast<double*>(base + o_crec);
   if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, 0));
   PairParams pp = pair_params(b, type, itype, jtype, do_hills, est_hill_count, seed, step, 0.0, nall);
   reset_pairs_kernel<<<1, 1>>>(b->d_state, ncalls);
-  long long blocks = (inum + 127) / 128;
+  pair_prep_kernel<<<(npts + 255) / 256, 256>>>(b->bias->d, cellrec, fmax_bits);
+  long long blocks = (nlisted + 255) / 256;
   if (blocks > b->n_partial) blocks = b->n_partial;
   if (blocks < 1) blocks = 1;
-  pair_list_kernel<<<(int)blocks, 128>>>(b->bias->d, pp, nlocal, inum, reinterpret_cast<int*>(base + o_il),
-                                         reinterpret_cast<long*>(base + o_first), reinterpret_cast<int*>(base + o_jl),
-                                         b->io.as<double>(), type ? reinterpret_cast<int*>(base + o_ty) : nullptr,
-                                         runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, b->io2.as<double>(),
-                                         b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
+  pair_list_flat_kernel<<<(int)blocks, 256>>>(b->bias->d, cellrec, pp, nlocal, nlisted, b->list_ilist, b->list_row,
+                                              b->list_jlist, b->io.as<double>(), type ? reinterpret_cast<int*>(base) : nullptr,
+                                              runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, b->io2.as<double>(),
+                                              b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
   sum_partials2_kernel<<<1, 256>>>((int)blocks, b->d_energy_partial, b->d_scalar, nullptr, nullptr);
-  count_launches(3);
+  count_launches(4);
   EDM_CUDA(cudaGetLastError());
+  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, 0));  // the round below does not touch the forces
   if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, 0));
-  EDM_CUDA(cudaMemcpy(f, b->io2.p, bx, cudaMemcpyDeviceToHost));
+  EDM_CUDA(cudaDeviceSynchronize());
   EDM_TRY(read_pair_result(b, result, ncalls));
   if (do_hills) EDM_TRY(edm_bias_check_round(b));
   return EDM_OK;
+}
+
+int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
+                       int jtype, long inum, const int* ilist, const long* first, const int* jlist, int do_hills,
+                       long long est_hill_count, const double* runiform, uint64_t seed, uint64_t step,
+                       edm_pair_result_t* result) {
+  EDM_REQUIRE(b && x && f && ilist && first && (jlist || first[inum] == 0), "NULL argument");
+  EDM_TRY(edm_pair_list_set(b, inum, ilist, first, jlist));
+  return edm_pair_step_listed(b, nall, nlocal, x, f, type, itype, jtype, do_hills, est_hill_count, runiform, seed, step,
+                              result);
 }
 
 }  // extern "C"

@@ -81,23 +81,28 @@ void FixEDMPair::post_force(int) {
   if (force->newton_pair)
     error->all(FLERR, "fix edm_pair requires 'newton off' to be declared in the lammps input script");
   const int inum = list->inum;
-  // NeighList -> CSR; the NEIGHMASK strip of fix_edm_pair.cpp:196 happens here
-  first_.resize((size_t)inum + 1);
-  first_[0] = 0;
-  for (int ii = 0; ii < inum; ii++) first_[ii + 1] = first_[ii] + list->numneigh[list->ilist[ii]];
-  jlist_.resize((size_t)first_[inum]);
-  for (int ii = 0; ii < inum; ii++) {
-    const int i = list->ilist[ii];
-    const int* src = list->firstneigh[i];
-    int* dst = &jlist_[(size_t)first_[ii]];
-    for (int jj = 0; jj < list->numneigh[i]; jj++) dst[jj] = src[jj] & NEIGHMASK;
+  // NeighList -> CSR (the NEIGHMASK strip of fix_edm_pair.cpp:196 happens here), uploaded only on the steps
+  // LAMMPS rebuilt the list; in between the device keeps it and only positions and forces travel
+  if (neighbor->ago == 0 || !list_on_device_) {
+    first_.resize((size_t)inum + 1);
+    first_[0] = 0;
+    for (int ii = 0; ii < inum; ii++) first_[ii + 1] = first_[ii] + list->numneigh[list->ilist[ii]];
+    jlist_.resize((size_t)first_[inum]);
+    for (int ii = 0; ii < inum; ii++) {
+      const int i = list->ilist[ii];
+      const int* src = list->firstneigh[i];
+      int* dst = &jlist_[(size_t)first_[ii]];
+      for (int jj = 0; jj < list->numneigh[i]; jj++) dst[jj] = src[jj] & NEIGHMASK;
+    }
+    EDM::edm_check(edm_pair_list_set(bias->device_bias(), inum, list->ilist, first_.data(), jlist_.data()),
+                   "fix_edm_pair.cpp:post_force");
+    list_on_device_ = true;
   }
   const bool hills = stride > 0 && update->ntimestep % stride == 0;
   const long nall = atom->nlocal + atom->nghost;
   edm_pair_result_t res;
-  EDM::edm_check(edm_pair_step_list(bias->device_bias(), nall, atom->nlocal, atom->x[0], atom->f[0], atom->type, ipair,
-                                    jpair, inum, list->ilist, first_.data(), jlist_.data(), hills ? 1 : 0, last_calls,
-                                    NULL, seed, (uint64_t)update->ntimestep, &res),
+  EDM::edm_check(edm_pair_step_listed(bias->device_bias(), nall, atom->nlocal, atom->x[0], atom->f[0], atom->type, ipair,
+                                      jpair, hills ? 1 : 0, last_calls, NULL, seed, (uint64_t)update->ntimestep, &res),
                  "fix_edm_pair.cpp:post_force");
   edm_energy = res.energy;
   if (hills) {

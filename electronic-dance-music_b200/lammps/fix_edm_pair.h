@@ -45,6 +45,7 @@ class FixEDMPair : public Fix {
   int ipair, jpair;
   std::vector<long> first_;
   std::vector<int> jlist_;
+  bool list_on_device_ = false;  // the flattened list sits on the GPU until LAMMPS rebuilds it (neighbor->ago == 0)
 };
 
 }  // namespace LAMMPS_NS

@@ -103,9 +103,10 @@ class NeighList {
 class Neighbor {
  public:
   double skin;
+  int ago;  // steps since the lists were last rebuilt (neighbor.h of LAMMPS)
   NeighRequest** requests;
   int nrequest;
-  Neighbor() : skin(0), requests(NULL), nrequest(0) {}
+  Neighbor() : skin(0), ago(0), requests(NULL), nrequest(0) {}
   int request(void*) {
     requests = (NeighRequest**)realloc(requests, sizeof(NeighRequest*) * (size_t)(nrequest + 1));
     requests[nrequest] = new NeighRequest();

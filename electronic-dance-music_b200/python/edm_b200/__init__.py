@@ -111,6 +111,9 @@ EXPORTS = {
     "edm_bias_set_profiling": (C.c_int, [vp, C.c_int]),
     "edm_bias_profile_ms": (C.c_int, [vp, c_dp]),
     "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
+    "edm_pair_list_set": (C.c_int, [vp, C.c_long, c_ip, C.POINTER(C.c_long), c_ip]),
+    "edm_pair_step_listed": (C.c_int, [vp, C.c_long, C.c_long, c_dp, c_dp, c_ip, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                       c_dp, C.c_uint64, C.c_uint64, C.POINTER(PairResult)]),
     "edm_pair_search_info": (C.c_int, [vp, c_ip, c_dp, C.POINTER(C.c_longlong)]),
     "edm_bias_round_info": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "edm_bias_hills_commit_dev": (C.c_int, [vp, vp, C.c_int, C.c_long, C.c_longlong, vp]),
@@ -390,6 +393,23 @@ class Bias:
         fb = C.c_longlong(0)
         check(self.L.edm_pair_search_info(self.h, bd, C.byref(sc), C.byref(fb)))
         return dict(bricks=tuple(bd), density_scale=sc.value, fallbacks=fb.value)
+
+    def pair_list_set(self, ilist, first, jlist):
+        """Uploads a half neighbour list (CSR) once; pair_step_listed then reuses it until the next call."""
+        il, jl = _i(ilist), _i(jlist)
+        fi = np.ascontiguousarray(np.asarray(first, dtype=np.int64))
+        check(self.L.edm_pair_list_set(self.h, il.size, _ip(il), fi.ctypes.data_as(C.POINTER(C.c_long)), _ip(jl)))
+
+    def pair_step_listed(self, x, f, nlocal, do_hills=False, est=0, runiform=None, seed=0, step=0, types=None, itype=0,
+                         jtype=0):
+        assert x.flags.c_contiguous and f.flags.c_contiguous and x.shape[1] == 3 and f.shape[1] == 3
+        r = PairResult()
+        t = _i(types) if types is not None else None
+        u = _d(runiform) if runiform is not None else None
+        check(self.L.edm_pair_step_listed(self.h, x.shape[0], int(nlocal), _dp(x), _dp(f),
+                                          _ip(t) if t is not None else None, itype, jtype, 1 if do_hills else 0, int(est),
+                                          _dp(u) if u is not None else None, seed, step, C.byref(r)))
+        return dict(energy=r.energy, n_pairs=r.n_pairs, n_calls=r.n_calls)
 
     def round_info(self):
         a, m, b = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)

@@ -219,6 +219,14 @@ int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, d
                        int do_hills, long long est_hill_count, const double* runiform, uint64_t seed,
                        uint64_t step, edm_pair_result_t* result);
 
+/* The same with the list kept on the device between calls: LAMMPS rebuilds its neighbour list only every few steps
+ * (neighbor->ago == 0), so the fix uploads it with edm_pair_list_set on those steps and calls edm_pair_step_listed on
+ * every step; only positions, forces and types cross PCIe then.  edm_pair_step_list = both in one call. */
+int edm_pair_list_set(edm_bias_t* b, long inum, const int* ilist, const long* first, const int* jlist);
+int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,
+                         int jtype, int do_hills, long long est_hill_count, const double* runiform, uint64_t seed,
+                         uint64_t step, edm_pair_result_t* result);
+
 /* How the last edm_pair_*_cells step searched for pairs: the brick of home cells a CTA owned
  * (0,0,0 = direct search), the density inflation used to size bricks, and how many steps so far
  * had to fall back to the direct search (which then shrinks the bricks).  Outputs may be NULL. */

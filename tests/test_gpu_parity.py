@@ -577,6 +577,57 @@ def test_pair_list_parity(edm, port, tmp_path):
     compare_bias(bd, bo)
 
 
+def test_pair_list_kept_on_device_and_ghosts(edm, port, tmp_path):
+    """edm_pair_list_set once, edm_pair_step_listed on every step while the atoms move (LAMMPS keeps a list for
+    several steps: every listed pair is evaluated, whatever its distance has become); then ghost partners
+    (j >= nlocal): no force on them, one hill proposal instead of two (lammps/fix_edm_pair.cpp:223-236)."""
+    rng = np.random.default_rng(23)
+    n, L, rc = 3000, 30.0, 5.0
+    bd, bo = make_pair_biases(edm, port, tmp_path)
+    x = make_atoms(rng, n, L)
+    pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
+    keep = np.all(sh == 0.0, axis=1)
+    pi, pj = pi[keep], pj[keep]
+    ilist = np.arange(n, dtype=np.int32)
+    first = np.zeros(n + 1, np.int64)
+    np.add.at(first, pi + 1, 1)
+    first = np.cumsum(first)
+    bd.pair_list_set(ilist, first, pj)
+    for step in range(4):
+        u = rng.uniform(0, 1, 2 * pi.size)
+        fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+        eo, _ = bo.pair_step(pi, pj, x, fo, do_hills=True, est=2 * pi.size, uniforms=u)
+        res = bd.pair_step_listed(x, fd, n, do_hills=True, est=2 * pi.size, runiform=u)
+        assert res["n_pairs"] == pi.size and res["n_calls"] == 2 * pi.size
+        if step > 0:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "kept-list forces step %d" % step)
+        x = np.ascontiguousarray(x + rng.normal(0, 0.15, size=x.shape))   # the atoms drift, the list stays
+    compare_bias(bd, bo)
+    # ghosts: rows for the first 2000 atoms only, partners anywhere
+    nlocal = 2000
+    rows = pi < nlocal
+    gi, gj = pi[rows], pj[rows]
+    gfirst = np.zeros(nlocal + 1, np.int64)
+    np.add.at(gfirst, gi + 1, 1)
+    gfirst = np.cumsum(gfirst)
+    fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+    eo, _ = bo.pair_step(gi, gj, x, fo, do_hills=False)
+    res = bd.pair_step_list(x, fd, nlocal, np.arange(nlocal, dtype=np.int32), gfirst, gj, do_hills=True, est=10 ** 9)
+    assert res["n_pairs"] == gi.size
+    assert res["n_calls"] == 2 * int((gj < nlocal).sum()) + int((gj >= nlocal).sum())
+    assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+    assert not fd[nlocal:].any()
+    # a local atom's force: its own rows plus the reactions of rows whose partner it is (both from the oracle run)
+    fl = np.zeros((n, 3))
+    only_local = gj < nlocal
+    e1, _ = bo.pair_step(gi[only_local], gj[only_local], x, fl, do_hills=False)
+    fg = np.zeros((n, 3))
+    e2, _ = bo.pair_step(gi[~only_local], gj[~only_local], x, fg, do_hills=False)
+    fg[nlocal:] = 0.0
+    assert_close(fd[:nlocal], (fl + fg)[:nlocal], "forces with ghost partners")
+
+
 def test_full_size_properties_pair_rdf(edm):
     """BASELINE configs[1] at full size (10^6 atoms): size-independent properties only —
     Newton's third law (total bias force = 0), pair count against the ideal-gas expectation,
