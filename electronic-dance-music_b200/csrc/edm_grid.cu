@@ -671,6 +671,19 @@ double edm_uniform_pair(uint64_t seed, uint64_t step, uint64_t pairkey, int whic
   return pair_uniform_from_bits(pair_bits(uniform_key(seed, step), pairkey), which);
 }
 
+int edm_host_pin(void* ptr, size_t bytes) {
+  EDM_REQUIRE(ptr && bytes, "NULL argument");
+  EDM_TRY(ensure_device(0));
+  EDM_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return EDM_OK;
+}
+
+int edm_host_unpin(void* ptr) {
+  EDM_REQUIRE(ptr != nullptr, "NULL argument");
+  EDM_CUDA(cudaHostUnregister(ptr));
+  return EDM_OK;
+}
+
 int edm_launch_count(long long* count) {
   if (count) *count = g_launches.load();
   return EDM_OK;

@@ -39,9 +39,27 @@ FixEDM::FixEDM(LAMMPS* lmp, int narg, char** arg)
 }
 
 FixEDM::~FixEDM() {
+  unpin_atom_arrays();
   delete bias;
   delete random;
   free(random_numbers);
+}
+
+void FixEDM::pin_atom_arrays() {
+  if (!getenv("EDM_B200_PIN")) return;
+  if (pinned_x_ == (void*)atom->x[0] && pinned_f_ == (void*)atom->f[0] && pinned_nmax_ == atom->nmax) return;
+  unpin_atom_arrays();
+  const size_t bytes = (size_t)atom->nmax * 3 * sizeof(double);
+  if (edm_host_pin(atom->x[0], bytes) == EDM_OK) pinned_x_ = atom->x[0];
+  if (edm_host_pin(atom->f[0], bytes) == EDM_OK) pinned_f_ = atom->f[0];
+  pinned_nmax_ = atom->nmax;
+}
+
+void FixEDM::unpin_atom_arrays() {
+  if (pinned_x_) edm_host_unpin(pinned_x_);
+  if (pinned_f_) edm_host_unpin(pinned_f_);
+  pinned_x_ = pinned_f_ = 0;
+  pinned_nmax_ = 0;
 }
 
 int FixEDM::setmask() { return POST_FORCE | THERMO_ENERGY | POST_FORCE_RESPA | MIN_POST_FORCE; }
@@ -70,6 +88,7 @@ void FixEDM::min_setup(int vflag) { post_force(vflag); }
 
 void FixEDM::post_force(int) {
   const int n = atom->nlocal;
+  pin_atom_arrays();
   bias->set_mask(atom->mask);
   const int do_hills = (stride > 0 && update->ntimestep % stride == 0) ? 1 : 0;
   if (do_hills) {

@@ -38,6 +38,13 @@ class FixEDM : public Fix {
   double temperature, edm_energy;
   int stride, write_stride;
   unsigned int seed;
+  // atom->x / atom->f page-locked for the host<->device copies while EDM_B200_PIN is set; re-pinned when
+  // LAMMPS reallocates them
+  void pin_atom_arrays();
+  void unpin_atom_arrays();
+  void* pinned_x_ = 0;
+  void* pinned_f_ = 0;
+  long pinned_nmax_ = 0;
 };
 
 }  // namespace LAMMPS_NS

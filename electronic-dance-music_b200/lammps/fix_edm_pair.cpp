@@ -44,7 +44,27 @@ FixEDMPair::FixEDMPair(LAMMPS* lmp, int narg, char** arg)
   if (bias->dim_ != 1) error->all(FLERR, "Pairwise distance must be 1 dimension in EDM input file");
 }
 
-FixEDMPair::~FixEDMPair() { delete bias; }
+FixEDMPair::~FixEDMPair() {
+  unpin_atom_arrays();
+  delete bias;
+}
+
+void FixEDMPair::pin_atom_arrays() {
+  if (!getenv("EDM_B200_PIN")) return;
+  if (pinned_x_ == (void*)atom->x[0] && pinned_f_ == (void*)atom->f[0] && pinned_nmax_ == atom->nmax) return;
+  unpin_atom_arrays();
+  const size_t bytes = (size_t)atom->nmax * 3 * sizeof(double);
+  if (edm_host_pin(atom->x[0], bytes) == EDM_OK) pinned_x_ = atom->x[0];
+  if (edm_host_pin(atom->f[0], bytes) == EDM_OK) pinned_f_ = atom->f[0];
+  pinned_nmax_ = atom->nmax;
+}
+
+void FixEDMPair::unpin_atom_arrays() {
+  if (pinned_x_) edm_host_unpin(pinned_x_);
+  if (pinned_f_) edm_host_unpin(pinned_f_);
+  pinned_x_ = pinned_f_ = 0;
+  pinned_nmax_ = 0;
+}
 
 int FixEDMPair::setmask() { return POST_FORCE | THERMO_ENERGY | POST_FORCE_RESPA | MIN_POST_FORCE; }
 
@@ -80,6 +100,7 @@ void FixEDMPair::min_setup(int vflag) { post_force(vflag); }
 void FixEDMPair::post_force(int) {
   if (force->newton_pair)
     error->all(FLERR, "fix edm_pair requires 'newton off' to be declared in the lammps input script");
+  pin_atom_arrays();
   const int inum = list->inum;
   // NeighList -> CSR (the NEIGHMASK strip of fix_edm_pair.cpp:196 happens here), uploaded only on the steps
   // LAMMPS rebuilt the list; in between the device keeps it and only positions and forces travel

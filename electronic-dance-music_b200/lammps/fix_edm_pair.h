@@ -46,6 +46,13 @@ class FixEDMPair : public Fix {
   std::vector<long> first_;
   std::vector<int> jlist_;
   bool list_on_device_ = false;  // the flattened list sits on the GPU until LAMMPS rebuilds it (neighbor->ago == 0)
+  // atom->x / atom->f page-locked for the host<->device copies while EDM_B200_PIN is set; re-pinned when
+  // LAMMPS reallocates them
+  void pin_atom_arrays();
+  void unpin_atom_arrays();
+  void* pinned_x_ = 0;
+  void* pinned_f_ = 0;
+  long pinned_nmax_ = 0;
 };
 
 }  // namespace LAMMPS_NS

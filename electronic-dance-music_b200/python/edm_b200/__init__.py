@@ -111,6 +111,8 @@ EXPORTS = {
     "edm_bias_set_profiling": (C.c_int, [vp, C.c_int]),
     "edm_bias_profile_ms": (C.c_int, [vp, c_dp]),
     "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
+    "edm_host_pin": (C.c_int, [vp, C.c_size_t]),
+    "edm_host_unpin": (C.c_int, [vp]),
     "edm_pair_list_set": (C.c_int, [vp, C.c_long, c_ip, C.POINTER(C.c_long), c_ip]),
     "edm_pair_step_listed": (C.c_int, [vp, C.c_long, C.c_long, c_dp, c_dp, c_ip, C.c_int, C.c_int, C.c_int, C.c_longlong,
                                        c_dp, C.c_uint64, C.c_uint64, C.POINTER(PairResult)]),

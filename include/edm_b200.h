@@ -51,6 +51,13 @@ double edm_uniform(uint64_t seed, uint64_t step, uint64_t counter);
 /* The two proposals of pair `pairkey` (which = 0, 1) share one hash: 32-bit resolution each. */
 double edm_uniform_pair(uint64_t seed, uint64_t step, uint64_t pairkey, int which);
 
+/* Page-locks / releases a host array the caller owns (cudaHostRegister), so that the host-buffer entry points
+ * copy it at full PCIe rate and truly asynchronously; pageable arrays work everywhere, a few times slower.
+ * For hosts without CUDA headers (the LAMMPS fixes pin atom->x and atom->f when EDM_B200_PIN is set).
+ * Unpin before the array is freed or reallocated. */
+int edm_host_pin(void* ptr, size_t bytes);
+int edm_host_unpin(void* ptr);
+
 /* ------------------------------------------------------------------ Grid / GaussGrid */
 
 /* make_grid, lib/grid.h:911 -> DimmedGrid ctor lib/grid.h:190-213 */

@@ -50,6 +50,18 @@ for do_hills in (False, True):
     t = min(ts[1:])
     print("list on device, do_hills=%d: %d pairs, %.3f ms per call -> %.3e evals/s (48 MB up, 24 MB down, pageable)" %
           (do_hills, r["n_pairs"], 1e3 * t, r["n_pairs"] / t))
+L_ = edm.lib()
+edm.check(L_.edm_host_pin(x.ctypes.data, x.nbytes))
+edm.check(L_.edm_host_pin(fbuf.ctypes.data, fbuf.nbytes))
+ts = []
+for step in range(6):
+    t0 = time.perf_counter()
+    r = b.pair_step_listed(x, fbuf, n, do_hills=True, est=2 * jlist.size, seed=1, step=step)
+    ts.append(time.perf_counter() - t0)
+t = min(ts[1:])
+print("list on device, x and f pinned with edm_host_pin: %.3f ms per call -> %.3e evals/s" % (1e3 * t, r["n_pairs"] / t))
+edm.check(L_.edm_host_unpin(x.ctypes.data))
+edm.check(L_.edm_host_unpin(fbuf.ctypes.data))
 for do_hills in (False, True):
     ts = []
     for step in range(6):
