@@ -879,6 +879,11 @@ __global__ void __launch_bounds__(256) pair_list_flat_kernel(GridDesc g, const d
   }
 }
 
+__global__ void add_forces_kernel(long n, const double* __restrict__ d, double* __restrict__ f) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f[i] += d[i];
+}
+
 __global__ void reset_pairs_kernel(BiasDev* st, unsigned long long* ncalls) {
   st->n_pairs = 0;
   if (ncalls) *ncalls = 0;
@@ -1243,33 +1248,57 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   const size_t o_u = o_crec + (size_t)npts * 4 * sizeof(double);
   EDM_TRY(b->io4.reserve(o_u + (runiform ? (size_t)nlisted * 2 * sizeof(double) : 0)));
   char* base = b->io4.as<char>();
-  if (type) EDM_CUDA(cudaMemcpyAsync(base, type, (size_t)nall * 4, cudaMemcpyHostToDevice, 0));
+  // Two streams, as in edm_pair_step_cells: the pair forces accumulate into a zeroed buffer while the old
+  // forces are still on their way up; one pass adds the two, and the result travels down beside the hill round.
+  //   main: x up | pair kernel -> dF          | f += dF | hill round
+  //   copy:      | f up (after x, full rate)  |         | f down
+  if (!b->st_main) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
+  }
+  EDM_TRY(b->io3.reserve(bx));
+  EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
+  cudaStream_t sm = b->st_main, sc = b->st_copy;
+  double* dF = b->io3.as<double>();
+  if (type) EDM_CUDA(cudaMemcpyAsync(base, type, (size_t)nall * 4, cudaMemcpyHostToDevice, sm));
   if (runiform)
-    EDM_CUDA(cudaMemcpyAsync(base + o_u, runiform, (size_t)nlisted * 2 * sizeof(double), cudaMemcpyHostToDevice, 0));
-  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, 0));
-  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, 0));
+    EDM_CUDA(cudaMemcpyAsync(base + o_u, runiform, (size_t)nlisted * 2 * sizeof(double), cudaMemcpyHostToDevice, sm));
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, sm));
+  EDM_CUDA(cudaEventRecord(b->ev_f_final, sm));  // reused: "x is up"
+  EDM_CUDA(cudaStreamWaitEvent(sc, b->ev_f_final, 0));
+  EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, sc));
+  EDM_CUDA(cudaEventRecord(b->ev_f_up, sc));
+  EDM_CUDA(cudaMemsetAsync(dF, 0, bx, sm));
   unsigned long long* ncalls = reinterpret_cast<unsigned long long*>(base + o_nc);
   unsigned long long* fmax_bits = reinterpret_cast<unsigned long long*>(base + o_fm);
   double* cellrec = reinterpret_cast<double*>(base + o_crec);
-  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, 0));
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, sm));
   PairParams pp = pair_params(b, type, itype, jtype, do_hills, est_hill_count, seed, step, 0.0, nall);
-  reset_pairs_kernel<<<1, 1>>>(b->d_state, ncalls);
-  pair_prep_kernel<<<(npts + 255) / 256, 256>>>(b->bias->d, cellrec, fmax_bits);
+  reset_pairs_kernel<<<1, 1, 0, sm>>>(b->d_state, ncalls);
+  pair_prep_kernel<<<(npts + 255) / 256, 256, 0, sm>>>(b->bias->d, cellrec, fmax_bits);
   long long blocks = (nlisted + 255) / 256;
   if (blocks > b->n_partial) blocks = b->n_partial;
   if (blocks < 1) blocks = 1;
-  pair_list_flat_kernel<<<(int)blocks, 256>>>(b->bias->d, cellrec, pp, nlocal, nlisted, b->list_ilist, b->list_row,
-                                              b->list_jlist, b->io.as<double>(), type ? reinterpret_cast<int*>(base) : nullptr,
-                                              runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, b->io2.as<double>(),
-                                              b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
-  sum_partials2_kernel<<<1, 256>>>((int)blocks, b->d_energy_partial, b->d_scalar, nullptr, nullptr);
-  count_launches(4);
+  pair_list_flat_kernel<<<(int)blocks, 256, 0, sm>>>(b->bias->d, cellrec, pp, nlocal, nlisted, b->list_ilist, b->list_row,
+                                                     b->list_jlist, b->io.as<double>(),
+                                                     type ? reinterpret_cast<int*>(base) : nullptr,
+                                                     runiform ? reinterpret_cast<double*>(base + o_u) : nullptr, dF,
+                                                     b->d_energy_partial, b->d_state, b->d_accepted, ncalls);
+  sum_partials2_kernel<<<1, 256, 0, sm>>>((int)blocks, b->d_energy_partial, b->d_scalar, nullptr, nullptr);
+  EDM_CUDA(cudaStreamWaitEvent(sm, b->ev_f_up, 0));
+  add_forces_kernel<<<(unsigned)((nall * 3 + 255) / 256), 256, 0, sm>>>(nall * 3, dF, b->io2.as<double>());
+  count_launches(5);
   EDM_CUDA(cudaGetLastError());
-  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, 0));  // the round below does not touch the forces
-  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, 0));
-  EDM_CUDA(cudaDeviceSynchronize());
+  EDM_CUDA(cudaEventRecord(b->ev_f_final, sm));
+  EDM_CUDA(cudaStreamWaitEvent(sc, b->ev_f_final, 0));
+  EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, sc));  // the round does not touch the forces
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, sm));
+  EDM_CUDA(cudaStreamSynchronize(sm));
   EDM_TRY(read_pair_result(b, result, ncalls));
   if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  EDM_CUDA(cudaStreamSynchronize(sc));
   return EDM_OK;
 }
 
