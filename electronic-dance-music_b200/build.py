@@ -63,6 +63,7 @@ def build_lib(force=False, verbose=False):
 HOST_SRCS = ["edm.cpp", "grid.cpp", "gaussian_grid.cpp", "edm_bias.cpp", "edm_bias_py.cpp"]
 HOST_LIB = os.path.join(LIBDIR, "libedm.so")
 HOST_TEST = os.path.join(LIBDIR, "edm_host_test")
+FIX_DRIVER = os.path.join(LIBDIR, "fix_driver_test")
 CXX = "/usr/bin/g++"
 CXXFLAGS = ["-std=c++11", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
 
@@ -89,6 +90,13 @@ def build_host_tests(force=False):
         if force or _stale(obj, [src, os.path.join(lmp, f.replace(".cpp", ".h"))] + hdrs):
             subprocess.check_call([CXX] + CXXFLAGS + ["-I" + HERE, "-I" + os.path.join(lmp, "mock"), "-I" + lmp,
                                                       "-c", src, "-o", obj])
+    # the fake MD loop that drives the two fixes on the GPU
+    drv_src = os.path.join(HERE, "tests_host", "fix_driver_test.cpp")
+    objs = [os.path.join(LIBDIR, "fix_edm.o"), os.path.join(LIBDIR, "fix_edm_pair.o")]
+    if force or _stale(FIX_DRIVER, [drv_src, HOST_LIB] + objs):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-I" + HERE, "-I" + os.path.join(lmp, "mock"), "-I" + lmp, "-o",
+                                                  FIX_DRIVER, drv_src] + objs +
+                              ["-L" + LIBDIR, "-ledm", "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_TEST
 
 

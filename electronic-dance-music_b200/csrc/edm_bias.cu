@@ -1032,6 +1032,22 @@ static int ensure_accepted(edm_bias* b, long need) {
   return EDM_OK;
 }
 
+// Room for the candidates a round can accept: `candidates` proposals thinned with probability
+// hill_density / est (lib/edm_bias.cpp:543).  With a poor est -- fix edm_pair starts from atom->nmax,
+// lammps/fix_edm_pair.cpp:105 -- a round accepts many times hill_density; they must all reach the limiter,
+// which then fills the backlog or fails the way the reference does (lib/edm_bias.cpp:503-507).
+int edm_bias_size_accepted(edm_bias* b, double candidates, long long est) {
+  double expect = candidates;
+  if (b->prm.hill_density >= 0) {
+    double p = (int)est > 0 ? b->prm.hill_density / (double)(int)est : 1.0;
+    if (p > 1.0) p = 1.0;
+    expect = candidates * p;
+    expect += 6.0 * sqrt(expect) + 64.0;
+  }
+  if (expect > (double)(1 << 22)) expect = (double)(1 << 22);
+  return ensure_accepted(b, (long)expect);
+}
+
 int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st) {
   count_launches(1);
   reset_accepted_kernel<<<1, 1, 0, st>>>(b->d_state);
@@ -1338,7 +1354,7 @@ static int coords_pipeline(edm_bias* b, long n, const double* x, long xs, double
   }
   EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
   if (do_hills) {
-    if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+    EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
     EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
   }
   if (n > 0) {
@@ -1416,7 +1432,7 @@ int edm_bias_select_dev(edm_bias_t* b, long n, const double* x, long xstride, co
                         void* stream) {
   EDM_REQUIRE(b && (n == 0 || x), "NULL argument");
   EDM_TRY(ensure_device(b->device));
-  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, (long)first_counter + n));
+  EDM_TRY(edm_bias_size_accepted(b, (double)first_counter + (double)n, est_hill_count));
   return select_launch(b, n, x, xstride, runiform, mask, apply_mask, est_hill_count, seed, step, first_counter,
                        (cudaStream_t)stream);
 }
@@ -1426,7 +1442,7 @@ int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride,
   EDM_REQUIRE(b != nullptr, "NULL argument");
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+  EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
   EDM_TRY(edm_bias_reset_accepted(b, st));
   // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
   EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, st));
@@ -1460,7 +1476,7 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
   if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream));
   EDM_CUDA(cudaEventRecord(b->ev_forces, st));
-  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, n));
+  EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
   EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
   EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, b->st_side));
   b->round_after = b->ev_forces;
@@ -1528,7 +1544,7 @@ int edm_bias_add_hill_batch(edm_bias_t* b, long n, const double* x, const double
     EDM_CUDA(cudaMemcpyAsync(b->io2.p, runiform, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, 0));
     du = b->io2.as<double>();
   }
-  if (b->prm.hill_density < 0) EDM_TRY(ensure_accepted(b, (long)b->round_count + n));
+  EDM_TRY(edm_bias_size_accepted(b, (double)b->round_count + (double)n, b->round_est));
   EDM_TRY(select_launch(b, n, b->io.as<double>(), D, du, nullptr, -1, b->round_est, 0, 0, b->round_count, 0));
   b->round_count += (unsigned long long)n;
   EDM_CUDA(cudaDeviceSynchronize());

@@ -9,6 +9,7 @@
 #include "edm_host.h"
 
 int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st);
+int edm_bias_size_accepted(edm_bias* b, double candidates, long long est);
 int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st);
 int edm_bias_check_round(edm_bias* b);
 
@@ -979,6 +980,9 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   // x); forces_done: recorded once f is final (before any hill work the caller appends)
   EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");  // fix_edm_pair.cpp:52-53
   EDM_REQUIRE(natoms > 0 && natoms < 2000000000L, "bad atom count");
+  // two proposals per pair; the pair count is not known before the search: ~100 partners per atom is generous
+  // for a liquid at this cutoff, and a round that outgrows the buffer is reported, never truncated
+  if (do_hills) EDM_TRY(edm_bias_size_accepted(b, 200.0 * (double)natoms, est));
   CellGrid cg;
   long long ncell = 1;
   for (int d = 0; d < 3; d++) {
@@ -1274,7 +1278,10 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   unsigned long long* ncalls = reinterpret_cast<unsigned long long*>(base + o_nc);
   unsigned long long* fmax_bits = reinterpret_cast<unsigned long long*>(base + o_fm);
   double* cellrec = reinterpret_cast<double*>(base + o_crec);
-  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, sm));
+  if (do_hills) {
+    EDM_TRY(edm_bias_size_accepted(b, 2.0 * (double)nlisted, est_hill_count));
+    EDM_TRY(edm_bias_reset_accepted(b, sm));
+  }
   PairParams pp = pair_params(b, type, itype, jtype, do_hills, est_hill_count, seed, step, 0.0, nall);
   reset_pairs_kernel<<<1, 1, 0, sm>>>(b->d_state, ncalls);
   pair_prep_kernel<<<(npts + 255) / 256, 256, 0, sm>>>(b->bias->d, cellrec, fmax_bits);

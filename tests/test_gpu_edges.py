@@ -138,3 +138,21 @@ def test_deposit_empty_and_single(edm, port):
     bo = go.add_values(c, np.array([0.5]))
     assert_close(bd, bo, "bias_added")
     assert_close(gd.get_arrays()[0], go.get_arrays()[0], "grid")
+
+
+def test_poor_estimate_accepts_many_times_hill_density(edm, port, tmp_path):
+    """est_hill_count far below the real number of proposals (fix edm_pair's first round starts from atom->nmax,
+    lammps/fix_edm_pair.cpp:105): thirty times hill_density hills are accepted and all of them reach the limiter."""
+    text = ("tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 250\ndimension 1\nbox_low 1.68\n"
+            "box_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025")
+    bd, bo = make_both(edm, port, tmp_path, "poor", text, 300.0, 0.0019872, [1.68], [5.0], [0])
+    rng = np.random.default_rng(12)
+    r = rng.uniform(0.5, 5.5, 60000)
+    u = rng.uniform(0, 1, 60000)
+    for b in (bo, bd):
+        b.pre_add_hill(2000)            # acceptance 250/2000 per proposal -> ~7 500 hills
+        b.add_hill_many(r[:25000], u[:25000])
+        b.add_hill_many(r[25000:], u[25000:])
+        b.post_add_hill()
+    log = compare_bias(bd, bo)
+    assert 7000 < len(log) < 8000

@@ -117,6 +117,19 @@ def test_restated_reference_unit_tests_on_gpu(host_test_binary, tmp_path):
 
 
 @pytest.mark.gpu
+def test_fixes_driven_by_a_fake_md_loop_on_gpu(host_test_binary, tmp_path):
+    """fix edm / fix edm_pair constructed from a fix command, stepped like LAMMPS would (mock headers), every step's
+    energy and forces checked against a CPU accumulation over the batched grid evaluation."""
+    drv = os.path.join(PKG, "lib", "fix_driver_test")
+    assert os.path.exists(drv)
+    r = subprocess.run([drv], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:])
+    print(r.stderr[-2000:])
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert " 0 failed" in r.stdout
+
+
+@pytest.mark.gpu
 def test_python_api_reproduces_the_notebook_vector(host_test_binary, tmp_path, monkeypatch):
     """edm.EDMBias (python/edm/__init__.py) on the B200 engine: python-example/EDM.ipynb:86-103."""
     import sys
