@@ -1026,7 +1026,10 @@ static int ensure_accepted(edm_bias* b, long need) {
   while (cap < need) cap <<= 1;  // power of two: cta_sort_accepted pads in place
   HillAccepted* p = nullptr;
   EDM_CUDA(cudaMalloc(&p, 2 * (size_t)cap * sizeof(HillAccepted)));
-  if (b->d_accepted) cudaFree(b->d_accepted);
+  if (b->d_accepted) {  // candidates of earlier batches of the same round stay (add_hill_batch, select_dev)
+    EDM_CUDA(cudaMemcpy(p, b->d_accepted, (size_t)b->accepted_cap * sizeof(HillAccepted), cudaMemcpyDeviceToDevice));
+    cudaFree(b->d_accepted);
+  }
   b->d_accepted = p;
   b->accepted_cap = cap;
   return EDM_OK;
