@@ -442,7 +442,8 @@ def parse_edm_text(text):
     return kv
 
 
-def bias_from_edm(edm_file, temperature, boltz, sublo, subhi, boxlo, boxhi, periodic, skin, device=0, target=None):
+def bias_from_edm(edm_file, temperature, boltz, sublo, subhi, boxlo, boxhi, periodic, skin, device=0, target=None,
+                  expected_target=0.0):
     """Python rendering of `new EDMBias(file); setup(T, kB); subdivide(...)` (lib/edm_bias.cpp:34-69,
     264-269, 98-222) for test/bench drivers; the C++ EDM::EDMBias class does the same natively."""
     kv = parse_edm_text(open(edm_file).read())
@@ -480,5 +481,5 @@ def bias_from_edm(edm_file, temperature, boltz, sublo, subhi, boxlo, boxhi, peri
     tv += vol
     params = dict(dim=D, b_tempering=temp, b_targeting=1 if target is not None else 0, global_tempering=gt,
                   bias_factor=bf, boltzmann_factor=boltz * temperature, hill_prefactor=pref, bias_per_step=bps,
-                  hill_density=dens, expected_target=0.0, total_volume=tv)
+                  hill_density=dens, expected_target=float(expected_target), total_volume=tv)
     return Bias(g, hist, params, target=target)

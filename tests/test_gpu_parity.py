@@ -386,6 +386,48 @@ def test_fused_coordinate_step_many_chunks(edm, port, tmp_path):
     compare_bias(bd, bo)
 
 
+@pytest.mark.parametrize("dim", [1, 2])
+def test_targeting_parity(edm, port, tmp_path, dim):
+    """target_filename (lib/edm_bias.cpp:1054-1064): hill heights scaled by exp(target(x) - expected_target), the
+    target read without interpolation (lib/edm_bias.cpp:545-546, lib/grid.h:343-365, expected_bias :692-710)."""
+    if dim == 1:
+        text = ("tempering 1\nglobal_tempering 0.00002\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+                "hill_density 200\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.01\nbias_sigma 0.05")
+        lo, hi, per, sp = [0.0], [10.0], [1], [0.1]
+    else:
+        text = ("tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+                "hill_density 150\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\n"
+                "bias_sigma 0.25 0.25")
+        lo, hi, per, sp = [0.0, 0.0], [8.0, 8.0], [1, 1], [0.25, 0.5]
+    f = write_edm(tmp_path, "target%d.edm" % dim, text)
+    tg_o = port.Grid("port", dim, lo, hi, sp, per, 0, 0)
+    tg_d = edm.Grid(dim, lo, hi, sp, per, 0, 0)
+    rng = np.random.default_rng(31 + dim)
+    vals = 1.5 + np.sin(np.linspace(0, 9, tg_o.size)) + 0.1 * rng.uniform(size=tg_o.size)   # an unnormalised -ln p
+    tg_o.set_arrays(vals)
+    tg_d.set_arrays(vals)
+    bo = port.Bias("port", f)
+    bo.setup(300.0, 0.0019872)
+    bo.subdivide(lo, hi, lo, hi, per, [0.0] * dim)
+    bo.set_target(tg_o)
+    bd = edm.bias_from_edm(f, 300.0, 0.0019872, lo, hi, lo, hi, per, [0.0] * dim, target=tg_d,
+                           expected_target=tg_o.expected_bias())
+    n = 12000
+    for step in range(4):
+        x = np.ascontiguousarray(rng.uniform(-1.0, hi[0] + 1.0, size=(n, 3)))
+        u = rng.uniform(0, 1, n)
+        fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+        eo = bo.update_forces(x, fo, -1)
+        ed = bd.step_coords(x, fd, u)
+        if step:
+            assert abs(ed - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "forces step %d" % step)
+        bo.add_hills(x, u, -1)
+    log = compare_bias(bd, bo)
+    assert np.ptp(log["height"]) > 0.2 * log["height"].max()      # the target really modulates the heights
+    assert bd.round_info()["parallel"] == 4
+
+
 def test_streaming_triple_matches_add_hills(edm, port, tmp_path):
     """pre_add_hill / add_hill xN / post_add_hill (two batches) against the oracle's triple."""
     cfg = BIAS_CASES["c5_rdf_tight_limiter_backlog"]
