@@ -156,3 +156,29 @@ def test_poor_estimate_accepts_many_times_hill_density(edm, port, tmp_path):
         b.post_add_hill()
     log = compare_bias(bd, bo)
     assert 7000 < len(log) < 8000
+
+
+def test_grid_add_minmax_hist(edm, port):
+    """Grid::add (restart via initial_bias_filename, lib/grid.h:275-290, lib/edm_bias.cpp:166-167), max_value /
+    min_value (:292-309) and the histogram bump DimmedGrid::add_value (:370-385) as direct calls."""
+    rng = np.random.default_rng(41)
+    src = edm.GaussGrid(2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    src.add_values(rng.uniform(0, 4, size=(300, 2)), rng.uniform(0.5, 1.5, 300))
+    sv, sd = src.get_arrays()
+    dst = edm.GaussGrid(2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    dst.add_values(rng.uniform(0, 4, size=(50, 2)), rng.uniform(0.5, 1.5, 50))
+    dv, dd = dst.get_arrays()
+    dst.add(src, 2.0, 0.5)
+    v, d = dst.get_arrays()
+    assert_close(v, dv + 2.0 * sv + 0.5, "Grid::add values")
+    nz = (np.abs(sv) >= 1e-7)[:, None]      # interp drops the tabulated derivative under a near-zero value (T6)
+    assert_close(d, dd + 2.0 * sd * nz, "Grid::add derivatives")
+    mn, mx = dst.minmax()
+    assert mn == v.min() and mx == v.max()
+    ho = port.Grid("port", 2, [0.0, -1.0], [4.0, 3.0], [0.25, 0.5], [1, 0], 0, 0)
+    hd = edm.Grid(2, [0.0, -1.0], [4.0, 3.0], [0.25, 0.5], [1, 0], 0, 0)
+    pts = rng.uniform(-2, 6, size=(5000, 2))
+    w = rng.integers(-1, 2, 5000).astype(float)
+    ho.hist_add(pts, w)
+    hd.hist_add(pts, w)
+    assert np.array_equal(hd.get_arrays()[0], ho.get_arrays()[0])
