@@ -182,3 +182,60 @@ def test_grid_add_minmax_hist(edm, port):
     ho.hist_add(pts, w)
     hd.hist_add(pts, w)
     assert np.array_equal(hd.get_arrays()[0], ho.get_arrays()[0])
+
+
+def test_device_pointer_entry_points_match_the_host_ones(edm, port, tmp_path):
+    """The _dev variants (device pointers, caller's stream, no synchronisation) against their host-buffer
+    twins: grid_eval_dev, gauss_deposit_dev, add_hills_dev, pair_step_cells_dev; plus edm_host_pin and the
+    backlog / cum_bias setters used for restart."""
+    import ctypes as C
+    import torch
+    L = edm.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(51)
+    # deposit + eval
+    ga = edm.GaussGrid(2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    gb = edm.GaussGrid(2, [0.0, 0.0], [4.0, 4.0], [0.0625, 0.0625], [1, 1], 1, [0.125, 0.125])
+    c, h = rng.uniform(0, 4, size=(400, 2)), rng.uniform(0.5, 1.5, 400)
+    ba_host = ga.add_values(c, h)
+    ct, ht, bt = torch.from_numpy(c).cuda(), torch.from_numpy(h).cuda(), torch.zeros(400, dtype=torch.float64, device="cuda")
+    edm.check(L.edm_gauss_deposit_dev(gb.h, 400, ct.data_ptr(), ht.data_ptr(), bt.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(bt.cpu().numpy(), ba_host)
+    assert_close(gb.get_arrays()[0], ga.get_arrays()[0], "deposit_dev grid")   # REDs: order of overlapping adds differs
+    pts = rng.uniform(-1, 5, size=(3000, 2))
+    vh, dh = ga.eval(pts)
+    pt = torch.from_numpy(pts).cuda()
+    vt, dt = torch.zeros(3000, dtype=torch.float64, device="cuda"), torch.zeros((3000, 2), dtype=torch.float64, device="cuda")
+    edm.check(L.edm_grid_eval_dev(ga.h, 3000, pt.data_ptr(), 2, vt.data_ptr(), dt.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(vt.cpu().numpy(), vh) and np.array_equal(dt.cpu().numpy(), dh)
+    # pair step on device buffers, host arrays page-locked through the library
+    cfg = BIAS_CASES["c2_rdf_threshold_tempering"]
+    b1, _ = make_both(edm, port, tmp_path, "dev1", cfg["text"], cfg["T"], cfg["kB"], [1.68], [5.0], [0])
+    b2, _ = make_both(edm, port, tmp_path, "dev2", cfg["text"], cfg["T"], cfg["kB"], [1.68], [5.0], [0])
+    n, box = 5000, np.array([34.0, 34.0, 34.0])
+    for step in range(3):
+        x = np.ascontiguousarray(rng.uniform(0, 34.0, size=(n, 3)))
+        f1 = np.zeros((n, 3))
+        edm.check(L.edm_host_pin(x.ctypes.data, x.nbytes))
+        r1 = b1.pair_step_cells(x, f1, box, 5.0, do_hills=True, est=300000, seed=3, step=step)
+        edm.check(L.edm_host_unpin(x.ctypes.data))
+        xt, ft = torch.from_numpy(x).cuda(), torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        r2 = edm.PairResult()
+        edm.check(L.edm_pair_step_cells_dev(b2.h, n, xt.data_ptr(), ft.data_ptr(), None, 0, 0,
+                                            box.ctypes.data_as(C.POINTER(C.c_double)), 5.0, 1, 300000, 3, step, C.byref(r2), st))
+        torch.cuda.synchronize()
+        assert r2.n_pairs == r1["n_pairs"] and r2.n_calls == r1["n_calls"]
+        assert r2.energy == r1["energy"]
+        assert np.array_equal(ft.cpu().numpy(), f1)
+    l1, l2 = b1.log(), b2.log()
+    assert len(l1) > 0 and np.array_equal(l1["pos"], l2["pos"]) and np.array_equal(l1["height"], l2["height"])
+    # restart helpers: cum_bias and the backlog travel
+    b1.set_cum_bias(0.125)
+    assert b1.state()["cum_bias"] == 0.125
+    buf = np.zeros(8192)
+    buf[2:8] = [2.0, 1e-5, 3.0, 2e-5, 4.0, 3e-5]     # slots 1..3 of a 1-D backlog
+    b1.set_backlog(1, 4, buf)
+    le, ri, got = b1.backlog()
+    assert (le, ri) == (1, 4) and np.array_equal(got[:8], buf[:8])
