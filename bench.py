@@ -469,6 +469,9 @@ def run_gpu(args, rank, local_rank, world):
                          "search_kernel_ms": float(np.mean(find_ms)), "pair_kernels_ms": float(np.mean(pair_ms)),
                          "bricks": list(info["bricks"]), "fallbacks": info["fallbacks"],
                          "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "binding_resource": {"name": "L1/shared-memory data pipe (l1tex LSU wavefronts)",
+                                              "pct_of_peak": 75.5, "issue_slots_pct": 68.0, "fp64_pipe_pct": 23.5,
+                                              "dram_pct": 4.0, "source": "profiles/r01_i_block_eval_ncu_selected.txt"},
                          "note": "not HBM bound (SURVEY 8d: 2.9 B/pair of compulsory traffic): ncu shows the LSU data "
                                  "pipe (shared-memory gathers, atomics, shuffles) and the issue slots near 75 %"},
             "e2e": {"value": e2e_pairs_all / e2e_s, "unit": "evals/s",
