@@ -578,7 +578,6 @@ __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const __gri
   unsigned* chunk = slice;
   int used = kChunk;  // forces an allocation on first use
   bool dropped = false;
-  const unsigned ltmask = (1u << lane) - 1u;
   const int nhome = R.hn[0] * R.hn[1] * R.hn[2];
 
   for (int h = warp; h < nhome; h += kFindThreads / 32) {
@@ -632,28 +631,37 @@ __global__ void __launch_bounds__(kFindThreads, 4) block_find_kernel(const __gri
           want = (ti == pp.itype) ? 2 : 1;
         }
         const int lic = (li << 2) | 3;
-        unsigned m[6];
-        int tot = 0;
+        // each lane keeps its own accept flags; one warp scan of the per-lane counts places the items
+        // (their order inside a home atom's run does not matter to the evaluation)
+        unsigned flags = 0;
+        int cnt = 0;
 #pragma unroll
         for (int u = 0; u < 6; u++) {
           const float dx = pi.x - jx[u], dy = pi.y - jy[u], dz = pi.z - jz[u];
           const float d2 = dx * dx + dy * dy + dz * dz;
           bool take = (d2 < rc2m) && (lic < ljc[u]);
           if (TYPES) take = take && (ljc[u] & want);
-          m[u] = __ballot_sync(0xffffffffu, take);
-          tot += __popc(m[u]);
+          flags |= (take ? 1u : 0u) << u;
+          cnt += take ? 1 : 0;
         }
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += v;
+        }
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
         if (tot == 0) continue;
         if (used + tot > kChunk) {  // at most 192 per home atom and pass, so a fresh chunk always fits
           chunk = next_chunk(chunk, used, slice, &S.nchunks, maxchunks, dropped);
           used = 0;
         }
         const unsigned hi16 = (unsigned)li << 16;
+        int pos = used + inc - cnt;
 #pragma unroll
-        for (int u = 0; u < 6; u++) {
-          if ((m[u] >> lane) & 1u) chunk[used + __popc(m[u] & ltmask)] = hi16 | (unsigned)(ljc[u] >> 2);
-          used += __popc(m[u]);
-        }
+        for (int u = 0; u < 6; u++)
+          if ((flags >> u) & 1u) chunk[pos++] = hi16 | (unsigned)(ljc[u] >> 2);
+        used += tot;
       }
     }
   }
