@@ -49,10 +49,25 @@ def grid_case(name, dim, mn, mx, sp, per, sg, bnd, nh, seed, pad=0.15):
     print(name, "hills", nh, "points", v.size)
 
 
-def bias_case(name, text, T, kB, sub, periodic, skin, n, lo, hi, steps, seed):
+def bias_case(name, text, T, kB, sub, periodic, skin, n, lo, hi, steps, seed, target=None):
+    """target = (min, max, spacing, periodic, values): written as a PLUMED grid by the reference's own writer and named
+    by target_filename, so the reference reads it back itself (8 decimals); the fixture keeps the values as read."""
     tmp = tempfile.mkdtemp()
     f = os.path.join(tmp, name + ".edm")
-    open(f, "w").write(text + "\nhills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmp, tmp))
+    extra = {}
+    full_text = text
+    if target is not None:
+        tmn, tmx, tsp, tper, tvals = target
+        D = len(tmn)
+        tg = po.Grid("ref", D, tmn, tmx, tsp, tper, 0, 0)
+        tg.set_arrays(tvals)
+        tfile = os.path.join(tmp, "target.grid")
+        tg.write(tfile)
+        back = po.Grid("ref", dim=D, filename=tfile, b_interp=0)
+        extra = dict(target_min=tmn, target_max=tmx, target_spacing=tsp, target_periodic=tper,
+                     target_values=back.get_arrays()[0], target_n=back.info()["n"], target_dx=back.info()["dx"])
+        full_text = text + "\ntarget_filename " + tfile
+    open(f, "w").write(full_text + "\nhills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmp, tmp))
     b = po.Bias("ref", f)
     b.setup(T, kB)
     b.subdivide(sub[0], sub[1], sub[0], sub[1], periodic, skin)
@@ -79,8 +94,8 @@ def bias_case(name, text, T, kB, sub, periodic, skin, n, lo, hi, steps, seed):
                         log_hills_added=log["hills_added"], log_pos=log["pos"], log_height=log["height"],
                         log_bias_added=log["bias_added"], log_cum=log["cum_over_vol"], backlog_left=left,
                         backlog_right=right, backlog=buf, grid=v, deriv=d, hist=hist, cum_bias=p["cum_bias"],
-                        total_volume=p["total_volume"], steps=p["steps"])
-    print(name, "events", len(log), "backlog", left, right)
+                        total_volume=p["total_volume"], steps=p["steps"], expected_target=p["expected_target"], **extra)
+    print(name, "events", len(log), "backlog", left, right, "expected_target", p["expected_target"])
 
 
 def plumed_grids():
@@ -130,4 +145,18 @@ if __name__ == "__main__":
               "tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
               "hill_density 40\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.125 0.125\nbias_sigma 0.25 0.25",
               300.0, 0.0019872, ([0.0, 0.0], [8.0, 8.0]), [1, 1], [0.0, 0.0], 1500, 0.0, 8.0, 3, 9)
+    bias_case("bias_1d_targeting",
+              "tempering 1\nglobal_tempering 0.00002\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+              "hill_density 100\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.01\nbias_sigma 0.05",
+              300.0, 0.0019872, ([0.0], [10.0]), [1], [0.0], 4000, -1.0, 11.0, 4, 10,
+              target=([0.0], [10.0], [0.1], [1], 1.5 + np.sin(np.linspace(0, 9, 100)) + 0.05 * np.cos(np.arange(100.0))))
+    bias_case("bias_3d_density",
+              "tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
+              "bias_spacing 0.25 0.25 0.25\nbias_sigma 0.5 0.5 0.5\nhill_density 60",
+              1.0, 1.0, ([0.0] * 3, [8.0] * 3), [1, 1, 1], [0.0] * 3, 3000, -1.0, 9.0, 3, 11)
+    bias_case("bias_2d_walls_threshold",
+              "tempering 1\nglobal_tempering 0.00001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.006\n"
+              "hill_density 80\ndimension 2\nbox_low 0 0\nbox_high 4 4\nbias_spacing 0.0625 0.0625\n"
+              "bias_sigma 0.125 0.125",
+              300.0, 0.0019872, ([0.0, 0.0], [4.0, 4.0]), [0, 0], [0.0, 0.0], 2500, -0.5, 4.5, 5, 12)
     plumed_grids()

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GAUSS_FIXTURES = ["gauss_1d_rdf_mcgdp", "gauss_1d_periodic", "gauss_1d_inner_mcgdp", "gauss_2d_mixed", "gauss_2d_mcgdp",
                   "gauss_3d_inner_mcgdp"]
-BIAS_FIXTURES = ["bias_c5_tight_limiter", "bias_1d_local_tempering", "bias_2d_local_tempering"]
+BIAS_FIXTURES = ["bias_c5_tight_limiter", "bias_1d_local_tempering", "bias_2d_local_tempering", "bias_1d_targeting",
+                 "bias_3d_density", "bias_2d_walls_threshold"]
 
 
 @pytest.fixture(scope="module")
@@ -58,8 +59,15 @@ def test_bias_fixture(edm, name, tmp_path):
     z = load(name)
     f = tmp_path / "case.edm"
     f.write_text(str(z["edm_text"]) + "\nhills_filename %s/HILLS\nhistogram_filename %s/HIST\n" % (tmp_path, tmp_path))
+    target, expected = None, 0.0
+    if "target_values" in z.files:   # the reference's own read-back of the target grid file
+        D = len(z["target_min"])
+        target = edm.Grid(D, z["target_min"], z["target_max"], z["target_spacing"], z["target_periodic"], 0, 0)
+        assert np.array_equal(target.info()["n"], z["target_n"]) and np.array_equal(target.info()["dx"], z["target_dx"])
+        target.set_arrays(z["target_values"])
+        expected = float(z["expected_target"])
     b = edm.bias_from_edm(str(f), float(z["T"]), float(z["kB"]), z["sublo"], z["subhi"], z["sublo"], z["subhi"],
-                          z["periodic"], z["skin"])
+                          z["periodic"], z["skin"], target=target, expected_target=expected)
     for k, (x, u) in enumerate(zip(z["x"], z["u"])):
         x = np.ascontiguousarray(x)
         force = np.zeros_like(x)

@@ -12,7 +12,8 @@ import pytest
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GAUSS_FIXTURES = ["gauss_1d_rdf_mcgdp", "gauss_1d_periodic", "gauss_1d_inner_mcgdp", "gauss_2d_mixed", "gauss_2d_mcgdp",
                   "gauss_3d_inner_mcgdp"]
-BIAS_FIXTURES = ["bias_c5_tight_limiter", "bias_1d_local_tempering", "bias_2d_local_tempering"]
+BIAS_FIXTURES = ["bias_c5_tight_limiter", "bias_1d_local_tempering", "bias_2d_local_tempering", "bias_1d_targeting",
+                 "bias_3d_density", "bias_2d_walls_threshold"]
 
 
 def load(name):
@@ -49,6 +50,13 @@ def run_bias_fixture(po, kind, z, tmp_path):
     b = po.Bias(kind, str(f))
     b.setup(float(z["T"]), float(z["kB"]))
     b.subdivide(z["sublo"], z["subhi"], z["sublo"], z["subhi"], z["periodic"], z["skin"])
+    if "target_values" in z.files:   # the values the reference read back from its own 8-decimal grid file
+        D = len(z["target_min"])
+        tg = po.Grid(kind, D, z["target_min"], z["target_max"], z["target_spacing"], z["target_periodic"], 0, 0)
+        assert np.array_equal(tg.info()["n"], z["target_n"]) and np.array_equal(tg.info()["dx"], z["target_dx"])
+        tg.set_arrays(z["target_values"])
+        b.set_target(tg)
+        assert b.params()["expected_target"] == float(z["expected_target"])
     energies, forces = [], []
     for x, u in zip(z["x"], z["u"]):
         x = np.ascontiguousarray(x)
