@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
     if (threadIdx.x == 0) {
       st->n_accepted_last = st->n_accepted;
       st->n_accepted = 0;  // the next selection starts a fresh candidate list
+      st->accepted_sorted = 0;
     }
     return;
   }
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   int k_first = mode == 3 ? st->n_fast - st->n_plan_b : 0;  // planned entries: backlog slots, then candidates
   if (k_first < 0) k_first = 0;
   if (!rs.skip && nacc > k_first) {
-    if (mode == 0) cta_sort_accepted(acc, acc_tmp, nacc);  // mode 3: the plan already ordered them
+    if (mode == 0 && !st->accepted_sorted) cta_sort_accepted(acc, acc_tmp, nacc);  // mode 3: the plan ordered them
     double nxt[DIM];
     for (int d = 0; d < DIM; d++) nxt[d] = acc[k_first].x[d];
     for (int k = k_first; k < nacc; k++) {
@@ -460,6 +461,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
       st->rounds_in_order++;
     st->n_accepted_last = st->n_accepted;
     st->n_accepted = 0;  // the next selection starts a fresh candidate list
+    st->accepted_sorted = 0;
   }
 }
 
@@ -603,7 +605,7 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   }
   int nacc = st->n_accepted;
   if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
-  cta_sort_accepted(acc, acc_tmp, nacc);
+  if (!st->accepted_sorted) cta_sort_accepted(acc, acc_tmp, nacc);  // packed / unpacked lists arrive in key order
   const int nb = s_nb;
   const int nall = nb + nacc;
   const long long left = st->left;
@@ -959,6 +961,7 @@ __global__ void reset_mode_kernel(BiasDev* st) { st->round_mode = 0; }
 __global__ void reset_accepted_kernel(BiasDev* st) {
   st->n_accepted = 0;
   st->accepted_overflow = 0;
+  st->accepted_sorted = 0;
 }
 
 // hill exchange blocks: double[0] = count, then `count` centres of DIM doubles (key order)
@@ -966,8 +969,11 @@ template <int DIM>
 __global__ void pack_block_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* tmp, double* block, long cap) {
   int n = st->n_accepted;
   if (n > cap) n = (int)cap;
-  cta_sort_accepted(acc, tmp, n);
-  if (threadIdx.x == 0) block[0] = (double)n;
+  if (!st->accepted_sorted) cta_sort_accepted(acc, tmp, n);
+  if (threadIdx.x == 0) {
+    block[0] = (double)n;
+    st->accepted_sorted = 1;
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     for (int d = 0; d < DIM; d++) block[1 + (long)i * DIM + d] = acc[i].x[d];
 }
@@ -993,6 +999,7 @@ __global__ void unpack_blocks_kernel(BiasDev* st, HillAccepted* acc, long acc_ca
   if (threadIdx.x == 0) {
     s_off = off;
     st->n_accepted = s_off;
+    st->accepted_sorted = 1;  // keys are the positions in the rank-major concatenation
     if (off > acc_cap) st->accepted_overflow = 1;
   }
 }

@@ -86,6 +86,7 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   long long left, right;
   int n_accepted;
   int accepted_overflow;
+  int accepted_sorted;  // the accepted list is already in key order (packed or unpacked): rounds skip their sort
   int log_n;
   int log_dropped;
   int backlog_full;
