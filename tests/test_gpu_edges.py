@@ -241,3 +241,37 @@ def test_device_pointer_entry_points_match_the_host_ones(edm, port, tmp_path):
     b1.set_backlog(1, 4, buf)
     le, ri, got = b1.backlog()
     assert (le, ri) == (1, 4) and np.array_equal(got[:8], buf[:8])
+
+
+def test_pair_step_on_a_periodic_cv_grid_takes_the_general_interpolation(edm, port, tmp_path):
+    """The pair kernels' lean 1-D interpolation applies to the grid fix edm_pair sets up (non-periodic grid and
+    boundary); any other grid goes through the general routine.  A periodic CV axis exercises that branch in the
+    cell path and in the list path."""
+    text = ("tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 200\ndimension 1\nbox_low 0\nbox_high 6\n"
+            "bias_spacing 0.001\nbias_sigma 0.05")
+    bd, bo = make_both(edm, port, tmp_path, "pcv", text, 300.0, 0.0019872, [0.0], [6.0], [1])
+    rng = np.random.default_rng(61)
+    n, L, rc = 4000, 32.0, 5.0
+    for step in range(3):
+        x = np.ascontiguousarray(rng.uniform(0, L, size=(n, 3)))
+        pi, pj, sh = port.build_half_list(x, [L, L, L], rc)
+        u = port.pair_uniforms(5, step, pi, pj, n)
+        fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+        eo, _ = bo.pair_step(pi, pj, x, fo, shift=sh, do_hills=True, est=2 * pi.size, uniforms=u)
+        res = bd.pair_step_cells(x, fd, [L, L, L], rc, do_hills=True, est=2 * pi.size, seed=5, step=step)
+        assert res["n_pairs"] == pi.size
+        if step:
+            assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+            assert_close(fd, fo, "forces on a periodic CV grid, step %d" % step)
+    compare_bias(bd, bo)
+    # the list path on the same bias: plain pairs only (a list carries no image shifts)
+    keep = np.all(sh == 0.0, axis=1)
+    pi, pj = pi[keep], pj[keep]
+    first = np.zeros(n + 1, np.int64)
+    np.add.at(first, pi + 1, 1)
+    first = np.cumsum(first)
+    fo, fd = np.zeros((n, 3)), np.zeros((n, 3))
+    eo, _ = bo.pair_step(pi, pj, x, fo, do_hills=False)
+    res = bd.pair_step_list(x, fd, n, np.arange(n, dtype=np.int32), first, pj, do_hills=False)
+    assert abs(res["energy"] - eo) <= RTOL * abs(eo)
+    assert_close(fd, fo, "list forces on a periodic CV grid")
