@@ -232,6 +232,20 @@ BIAS_CASES = {
              "bias_sigma 0.25 0.25",
         T=300.0, kB=0.0019872, sub=([0.0, 0.0], [8.0, 8.0]), periodic=[1, 1], skin=[0.0, 0.0], n=20000, lo=0.0, hi=8.0,
         steps=2),
+    "fix_edm_pair_geometry_with_skin": dict(  # grid [-skin, cut + 2 skin] around the walls: duplicate_boundary is live
+        text="tempering 1\nglobal_tempering 0.0001\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 0.1\n"
+             "hill_density 250\ndimension 1\nbox_low 1.68\nbox_high 5.0\nbias_spacing 0.00025\nbias_sigma 0.025",
+        T=300.0, kB=0.0019872, sub=([0.0], [6.0]), periodic=[0], skin=[1.0], n=30000, lo=-0.5, hi=6.5, steps=5),
+    "2d_walls_inside_a_larger_grid": dict(  # sub-box larger than the bias box: walls inside the grid, copies outside them
+        text="tempering 0\nhill_prefactor 0.02\nbias_per_step 1000\nhill_density 120\ndimension 2\nbox_low 1 1\n"
+             "box_high 5 4\nbias_spacing 0.0625 0.0625\nbias_sigma 0.125 0.125",
+        T=1.0, kB=1.0, sub=([0.0, 0.0], [6.0, 5.0]), periodic=[0, 0], skin=[0.5, 0.5], n=8000, lo=-0.5, hi=6.5, steps=4),
+    "2d_walls_inside_a_larger_grid_local_tempering": dict(  # the same with local tempering: rounds run in order
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
+             "hill_density 120\ndimension 2\nbox_low 1 1\nbox_high 5 4\nbias_spacing 0.0625 0.0625\n"
+             "bias_sigma 0.125 0.125",
+        T=300.0, kB=0.0019872, sub=([0.0, 0.0], [6.0, 5.0]), periodic=[0, 0], skin=[0.5, 0.5], n=8000, lo=-0.5, hi=6.5,
+        steps=3),
     "3d_all_candidates_deposit": dict(
         text="tempering 0\nhill_prefactor 1.0\nbias_per_step 0.4\ndimension 3\nbox_low 0 0 0\nbox_high 8 8 8\n"
              "bias_spacing 0.25 0.25 0.25\nbias_sigma 0.5 0.5 0.5",
@@ -243,7 +257,7 @@ BIAS_CASES = {
 PARALLEL_ROUND_CASES = {"c1_sanity_density": 6, "1d_local_well_tempering": 5, "c5_rdf_tight_limiter_backlog": 10, "2d_limiter_cuts_the_round": 4,
                          "c2_rdf_threshold_tempering": 6, "2d_local_well_tempering": 4,
                         "c3_2d_local_tempering_sparse": 4, "2d_mcgdp_walls_threshold_tempering": 4,
-                        "c4_3d_density": 3, "3d_local_tempering_mixed_walls": 3}
+                        "c4_3d_density": 3, "fix_edm_pair_geometry_with_skin": 5, "2d_walls_inside_a_larger_grid": 4, "3d_local_tempering_mixed_walls": 3}
 
 
 def run_bias_case(edm, port, tmp_path, name, masked=False, fused=False):
