@@ -3,6 +3,7 @@ include/edm_b200.h declares, and refuses to compute without a GPU (no CPU fallba
 import ctypes as C
 import os
 import re
+import subprocess
 import sys
 
 import numpy as np
@@ -89,3 +90,25 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"oracle/|pyoracle|libedm_oracle|libedm_ref|edm_oracle\.h", text):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def _build_c_example(tmp_path):
+    exe = tmp_path / "c_abi_minimal"
+    libdir = os.path.join(ROOT, "electronic-dance-music_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_minimal.c"), "-L" + libdir, "-ledm_b200", "-Wl,-rpath," + libdir, "-lm",
+           "-o", str(exe)]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_c_example_builds_against_the_header_and_library(edm, tmp_path):
+    """A plain C99 caller: compiles against include/edm_b200.h and links libedm_b200.so (no CUDA headers needed)."""
+    assert os.path.exists(_build_c_example(tmp_path))
+
+
+@pytest.mark.gpu
+def test_c_example_reproduces_the_notebook_vector(edm, tmp_path):
+    r = subprocess.run([str(_build_c_example(tmp_path))], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "matches the reference's notebook vector" in r.stdout
