@@ -1,0 +1,53 @@
+"""The bench.py contract the driver relies on, checked on the CPU through the reference arm (the only arm
+that runs without a GPU): one JSON line with the agreed keys, same metric/unit/config as the GPU arm."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def reference_line(port):
+    import pyoracle
+    if not (pyoracle.available("ref") or pyoracle.available("port")):
+        pytest.skip("no oracle library built")
+    env = dict(os.environ)
+    # a bounded run: two worker processes instead of one per core keeps the CPU suite short
+    code = ("import os, sys; os.sched_setaffinity(0, set(sorted(os.sched_getaffinity(0))[:2])); "
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']; "
+            "import runpy; runpy.run_path(%r, run_name='__main__')" % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_one_line_with_the_agreed_keys(reference_line):
+    d = reference_line
+    assert d["impl"] == "reference"
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["metric"] == "CV bias+force evals/sec" and d["unit"] == "evals/s" and d["dtype"] == "f64"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "c2_pair_rdf"
+    assert d["value"] > 1e6
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: the product arm of bench.py refuses to run where no CUDA device is visible."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert "no CUDA device" in (r.stderr + r.stdout)
