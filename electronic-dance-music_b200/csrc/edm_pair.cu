@@ -250,7 +250,7 @@ struct PairCtx {
   HillAccepted* acc;
   int* fallback;  // set by the block search when a region does not fit: the direct search takes the step
   const double* cellrec;                // per grid cell {V_k, V'_k, V_k+1, V'_k+1}, 32 B aligned (pair_prep_kernel)
-  const unsigned long long* fmax_bits;  // bit pattern of a bound on |dV/dr| over the grid
+  const unsigned long long* fmax_bits;  // bit patterns of bounds on |dV/dr| ([0]) and |V| ([1]) over the grid
 };
 
 // Per step: the 1-D bias grid regrouped by cell, so the interpolation's two corners are one aligned
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(GridDesc g, double* __re
                                                         unsigned long long* fmax_bits) {
   const int n = g.n[0];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  double bound = 0.0;
+  double bound = 0.0, vbound = 0.0;
   if (k < n) {
     const int k1 = (k + 1 < n) ? k + 1 : (g.periodic[0] ? 0 : k);
     const double v0 = g.rec[2 * (long)k], d0 = g.rec[2 * (long)k + 1];
@@ -273,10 +273,16 @@ __global__ void __launch_bounds__(256) pair_prep_kernel(GridDesc g, double* __re
       cellrec[4 * (long)k + 3] = d1;
     }
     bound = 1.5 * fabs(v1 - v0) * g.inv_dx[0] + fmax(fabs(d0), fabs(d1));
+    // |V| inside the cell: the Hermite value weights sum to 1, the slope weights stay below 4/27 each
+    vbound = fmax(fabs(v0), fabs(v1)) + 0.3 * g.dx[0] * (fabs(d0) + fabs(d1));
   }
-  for (int o = 16; o > 0; o >>= 1) bound = fmax(bound, __shfl_down_sync(0xffffffffu, bound, o));
+  for (int o = 16; o > 0; o >>= 1) {
+    bound = fmax(bound, __shfl_down_sync(0xffffffffu, bound, o));
+    vbound = fmax(vbound, __shfl_down_sync(0xffffffffu, vbound, o));
+  }
   // non-negative doubles order like their bit patterns
   if ((threadIdx.x & 31) == 0 && bound > 0.0) atomicMax(fmax_bits, (unsigned long long)__double_as_longlong(bound));
+  if ((threadIdx.x & 31) == 0 && vbound > 0.0) atomicMax(fmax_bits + 1, (unsigned long long)__double_as_longlong(vbound));
 }
 
 __device__ __forceinline__ double shift_of(int code, int d, const CellGrid& cg) {
@@ -719,13 +725,18 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
   // fewer than kBlkCap < 2^11 partners, so with scale 2^(51-ex) no sum reaches 2^62; one unit is
   // 2^-51 of the largest possible pair force, the resolution fp64 itself has there.  Integer sums
   // do not depend on the order the atomics resolve in.
-  const double fmax_grid = __longlong_as_double((long long)*c.fmax_bits);
+  const double fmax_grid = __longlong_as_double((long long)c.fmax_bits[0]);
   const double scale = fmax_grid > 0.0 ? scalbn(1.0, 51 - (ilogb(fmax_grid) + 1)) : 1.0;
+  // The energy too: |V| < 2^ev, so with scale 2^(44-ev) a lane's integer sum (fewer than 2^18 pairs) stays
+  // below 2^62; the CTA adds the lanes in 128 bits.  The sum does not depend on which lane met which pair
+  // (the order chunks were handed out in); one unit is 2^-44 of the largest possible pair energy.
+  const double vmax_grid = __longlong_as_double((long long)c.fmax_bits[1]);
+  const double escale = vmax_grid > 0.0 ? scalbn(1.0, 44 - (ilogb(vmax_grid) + 1)) : 1.0;
   __syncthreads();
 
   const unsigned* const slice = items + (size_t)blockIdx.x * bg.capb;
   const int nbatch = nchunks_in[blockIdx.x] * (kChunk / 32);
-  double e = 0.0;
+  long long eq = 0;
   unsigned npairs = 0;
   unsigned it_next = warp < nbatch ? slice[(size_t)warp * 32 + lane] : kPad;
   for (int bt = warp; bt < nbatch; bt += kEvalThreads / 32) {
@@ -742,7 +753,11 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
       AtomRec ri, rj;
       ri.x = ia.x; ri.y = ia.y; ri.z = ib.x; ri.tag = __double_as_longlong(ib.y);
       rj.x = ja.x; rj.y = ja.y; rj.z = jb.x; rj.tag = __double_as_longlong(jb.y);
-      if (pair_exact(c, ri, rj, (int)(rj.tag >> 32), e, px, py, pz)) npairs++;
+      double e = 0.0;
+      if (pair_exact(c, ri, rj, (int)(rj.tag >> 32), e, px, py, pz)) {
+        npairs++;
+        eq += __double2ll_rn(e * escale);
+      }
     }
     // the partner takes -q, the home atom the run's sum of the same integers: the bias force on
     // the block's atoms adds up to exactly zero
@@ -775,8 +790,25 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
       atomicAdd(&c.f[o + 2], (double)q[2] * inv_scale);
     }
   }
-  double tot = block_sum(e, S.red);
-  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  // integer sum over the CTA: exact, so any order will do
+  __int128 wq = eq;
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long hi = __shfl_down_sync(0xffffffffu, (long long)(wq >> 64), o);
+    const unsigned long long lo = __shfl_down_sync(0xffffffffu, (unsigned long long)wq, o);
+    wq += ((__int128)hi << 64) | (__int128)lo;
+  }
+  unsigned long long* redq = reinterpret_cast<unsigned long long*>(S.red);  // 16 warps x (lo, hi) in the 33-double scratch
+  __syncthreads();
+  if (lane == 0) {
+    redq[2 * warp] = (unsigned long long)wq;
+    redq[2 * warp + 1] = (unsigned long long)(wq >> 64);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __int128 t = 0;
+    for (int i = 0; i < kEvalThreads / 32; i++) t += ((__int128)(long long)redq[2 * i + 1] << 64) | (__int128)redq[2 * i];
+    partial[blockIdx.x] = (double)t / escale;
+  }
   for (int o = 16; o > 0; o >>= 1) npairs += __shfl_down_sync(0xffffffffu, npairs, o);
   if (lane == 0 && npairs) atomicAdd(&c.st->n_pairs, (unsigned long long)npairs);
 }
@@ -784,7 +816,8 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
 __global__ void pair_reset_kernel(BiasDev* st, int* fallback, int fallback_init, unsigned long long* fmax_bits) {
   st->n_pairs = 0;
   *fallback = fallback_init;
-  *fmax_bits = 0ull;
+  fmax_bits[0] = 0ull;
+  fmax_bits[1] = 0ull;
 }
 
 // ---- neighbour-list form, pair-parallel (lammps/fix_edm_pair.cpp:177-240) ------------------------------
@@ -1256,7 +1289,7 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   EDM_TRY(b->io2.reserve(bx));
   // per-step scratch: type[nall] | ncalls | fmax bits | cell records of the bias grid | uniforms
   const int npts = b->bias->d.n[0];
-  const size_t o_nc = ((size_t)nall * 4 + 7) / 8 * 8, o_fm = o_nc + 8, o_crec = (o_fm + 8 + 31) / 32 * 32;
+  const size_t o_nc = ((size_t)nall * 4 + 7) / 8 * 8, o_fm = o_nc + 8, o_crec = (o_fm + 16 + 31) / 32 * 32;
   const size_t o_u = o_crec + (size_t)npts * 4 * sizeof(double);
   EDM_TRY(b->io4.reserve(o_u + (runiform ? (size_t)nlisted * 2 * sizeof(double) : 0)));
   char* base = b->io4.as<char>();
