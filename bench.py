@@ -13,11 +13,15 @@ all-gather of the accepted hills), height scaling, bias_per_step limiter, deposi
   value  evaluations/s over all ranks with positions and forces already resident in HBM
   e2e    the same step through the host-buffer C ABI call (edm_pair_step_cells): positions and
          forces copied host->device from pinned memory and forces + result copied back, every step
-  --impl reference   the reference's own CPU code (oracle/_ref, unmodified lib/ compiled here) on the
-         host cores: P independent single-rank instances, one per core, each on a shard of the
-         pairs with a full grid replica (the reference's scaling model for a replicated grid)
+  --impl reference   the reference's own CPU code (oracle/_ref, unmodified lib/ compiled here) running the
+         SAME step on the SAME 10^6-atom configuration on the host cores: the half neighbour list is built
+         once (untimed, as LAMMPS would hand it over), its rows are sharded over P single-rank EDMBias
+         instances, one per core, each with a full grid replica (the reference's scaling model for a
+         replicated grid), and every step runs fix edm_pair's own loop — r = sqrt, update_force, +-scatter,
+         two add_hill per pair, post_add_hill (lammps/fix_edm_pair.cpp:173-247)
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -41,9 +45,50 @@ PREWARM_HILLS = 20000        # hills deposited before timing so the evaluated bi
 DEPOSIT_BATCH = 1 << 20      # hills in the batched-deposit throughput measurement
 HILL_CAP = 4096              # records per rank in the exchange block
 ALG_BYTES_PER_ATOM = 76      # 24 B x + 48 B f read-modify-write + 4 B type, per atom per step
-# dram__bytes_read.sum + dram__bytes_write.sum of one block_eval_kernel launch on this workload
-NCU_TRAFFIC_BYTES = 188_613_376
-NCU_TRAFFIC_SOURCE = "profiles/r01_i_block_eval_ncu_selected.txt (ncu --set full, one launch: 180.32 MB read + 8.29 MB written)"
+SEED = 20261018
+# ncu-derived numbers (DRAM traffic of the dominant kernel, the resource that binds it) are never typed in here:
+# tools/ncu_summary.py --roofline writes them to this file together with a hash of the csrc/ tree they were
+# measured on, and they are reported only while that hash matches the tree being benchmarked.
+NCU_ROOFLINE_JSON = os.path.join(ROOT, "profiles", "ncu_roofline.json")
+
+
+def csrc_hash():
+    """sha1 over the CUDA sources of the build (file names + contents, sorted)."""
+    d = os.path.join(ROOT, "electronic-dance-music_b200", "csrc")
+    h = hashlib.sha1()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_roofline(workload, kernel):
+    """(traffic bytes per launch or None, binding-resource dict, note) from the last ncu capture of `kernel`."""
+    try:
+        rec = json.load(open(NCU_ROOFLINE_JSON))[workload][kernel]
+    except Exception:
+        return None, None, "no ncu capture on record for this kernel (profiles/ncu_roofline.json)"
+    if rec.get("csrc_hash") != csrc_hash():
+        return None, None, ("ncu capture on record (%s) was taken on csrc %s, this build is %s: not reported"
+                            % (rec.get("source"), rec.get("csrc_hash"), csrc_hash()))
+    return rec.get("dram_bytes_per_launch"), rec.get("binding"), rec.get("source")
+
+
+def c2_config(workload, world, pairs_per_step):
+    """The `config` object of both arms (ours and --impl reference): one definition, so they cannot drift."""
+    return {"workload": workload, "atoms_per_gpu": N_ATOMS, "number_density": DENSITY, "cutoff": CUTOFF,
+            "pairs_per_gpu_per_step": int(pairs_per_step), "grid_points": 13281, "hill_density": 250,
+            "step": "fix edm_pair post_force with hill addition: every pair inside the cutoff evaluated once, force "
+                    "scatter, two hill proposals per pair, limiter, deposit",
+            "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world}
+
+
+def c2_positions(rank, n_sets):
+    """Synthetic coordinates of one rank: uniform in a periodic cube at number density 0.1."""
+    box_len = (N_ATOMS / DENSITY) ** (1.0 / 3.0)
+    rng = np.random.default_rng(1234 + 1 + 1000 * rank)
+    return box_len, [rng.uniform(0, box_len, size=(N_ATOMS, 3)) for _ in range(n_sets)]
 
 
 # The other BASELINE.json configs (parity-test cases first; measurable on request with --workload).
@@ -185,8 +230,103 @@ def bind_to_gpu_numa_node(index):
 
 # ------------------------------------------------------------------ reference arm / CPU baseline
 
+def _farm_worker(conn, kind, edm_text, tmp, k, core, lo, hi, est, shared):
+    """One single-rank reference instance pinned to one core, owning pairs [lo, hi) of the half list."""
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    d = os.path.join(tmp, "w%d" % k)
+    os.makedirs(d, exist_ok=True)
+    b = pyoracle.Bias(kind, write_edm(d, edm_text))
+    b.log_enable(False)
+    b.setup(TEMPERATURE, BOLTZ)
+    b.subdivide([1.68], [5.0], [1.68], [5.0], [0], [0.0])
+    warm_c, warm_h = shared["warm"]
+    b.gauss.add_values(warm_c[:2000], warm_h[:2000])
+    x, box = shared["x"], shared["box"]
+    pi, pj, img = shared["pi"][lo:hi], shared["pj"][lo:hi], shared["img"][lo:hi]
+    f = np.zeros_like(x)
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg[0] == "stop":
+            break
+        _, do_hills, step = msg
+        t, e, ncalls = b.time_fix_pair(pi, pj, img, box, x, f, do_hills, est, seed=SEED + k, step=step)
+        conn.send((t, e, ncalls, hi - lo))
+    conn.close()
+
+
+class CpuFarm:
+    """The reference's scaling model for a replicated grid: P single-rank EDMBias instances, one per core, the
+    rows of ONE half neighbour list sharded over them (MPI itself is not in the image).  The list is built once,
+    outside every timed region, as LAMMPS hands fix edm_pair a ready NeighList."""
+
+    def __init__(self, kind, edm_text, x, box_len, cores, pair_limit=None):
+        import multiprocessing as mp
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        t0 = time.perf_counter()
+        pi, pj, img = pyoracle.build_half_list_fast(x, [box_len] * 3, CUTOFF)
+        self.list_build_s = time.perf_counter() - t0
+        self.pairs_total = int(pi.size)
+        n = self.pairs_total if pair_limit is None else min(pair_limit, self.pairs_total)
+        self.pairs = n
+        self.cores = cores
+        self.tmp = tempfile.mkdtemp()
+        rng = np.random.default_rng(1234 + 1)
+        shared = {"x": np.ascontiguousarray(x), "box": np.array([box_len] * 3), "pi": pi, "pj": pj, "img": img,
+                  "warm": prewarm_hills(rng)}
+        # equal pair counts, cut at row boundaries (a row = every listed partner of one atom i)
+        cuts = [0]
+        for k in range(1, cores):
+            c = int(n * k / cores)
+            while c < n and c > 0 and pi[c] == pi[c - 1]:
+                c += 1
+            cuts.append(max(c, cuts[-1]))
+        cuts.append(n)
+        # every instance thins with the job's proposal count: 2 per listed pair (fix_edm_pair.cpp:230-236, 245);
+        # the reference's MPI build divides hill_density by mpi_size_ instead (lib/edm_bias.cpp:175-180) — same rate
+        est = 2 * n
+        avail = sorted(os.sched_getaffinity(0))
+        ctx = mp.get_context("fork")
+        self.procs, self.conns = [], []
+        for k in range(cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_farm_worker, args=(b, kind, edm_text, self.tmp, k, avail[k % len(avail)], cuts[k],
+                                                       cuts[k + 1], est, shared), daemon=True)
+            p.start()
+            self.procs.append(p)
+            self.conns.append(a)
+        for c in self.conns:
+            assert c.recv() == "ready"
+
+    def step(self, step, do_hills=True):
+        """One MD step of fix edm_pair on every instance at once.  Returns (wall seconds on this host from release
+        to the last instance's answer, slowest instance's own loop time, pairs evaluated, hill proposals)."""
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send(("step", 1 if do_hills else 0, step))
+        res = [c.recv() for c in self.conns]
+        wall = time.perf_counter() - t0
+        return wall, max(r[0] for r in res), sum(r[3] for r in res), sum(r[2] for r in res)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(("stop",))
+            except Exception:
+                pass
+        for p in self.procs:
+            p.join(timeout=10)
+
+
 def _cpu_worker(args):
-    """One single-rank reference instance on one core: evaluates its shard of pair distances."""
+    """Bare EDMBias::update_force over pre-drawn pair distances (no list, no sqrt, no scatter, no hills): the
+    secondary CPU figure."""
     kind, edm_file, r, warm_c, warm_h, repeats, core = args
     try:
         os.sched_setaffinity(0, {core})
@@ -211,11 +351,9 @@ def cpu_pair_rate(kind, edm_file, r, warm, cores, repeats):
             for i, s in enumerate(shards)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        t0 = time.perf_counter()
         times = pool.map(_cpu_worker, jobs)
-        wall = time.perf_counter() - t0
     # every instance runs concurrently; the job is done when the slowest shard is
-    return r.size * repeats / max(times), max(times), wall
+    return r.size * repeats / max(times)
 
 
 def cpu_hill_rate(kind, n_hills, warm_rng):
@@ -243,37 +381,51 @@ def sample_pair_distances(rng, n):
     return CUTOFF * rng.uniform(0, 1, n) ** (1.0 / 3.0)
 
 
+def cpu_pair_loop(kind, edm_text, steps, warmup, cores=None, pair_limit=None):
+    """Times the reference's fix edm_pair step on rank 0's first coordinate set.  Returns a dict."""
+    cores = cores or len(os.sched_getaffinity(0))
+    box_len, (x,) = c2_positions(0, 1)
+    farm = CpuFarm(kind, edm_text, x, box_len, cores, pair_limit)
+    try:
+        for w in range(warmup):
+            farm.step(w)
+        walls, loops, pairs = [], [], 0
+        for k in range(steps):
+            wall, loop, n, _ = farm.step(warmup + k)
+            walls.append(wall)
+            loops.append(loop)
+            pairs += n
+    finally:
+        farm.close()
+    return {"evals_per_s": pairs / sum(walls), "ms_per_step": 1e3 * sum(walls) / steps,
+            "slowest_instance_ms_per_step": 1e3 * sum(loops) / steps, "pairs_per_step": farm.pairs,
+            "pairs_in_list": farm.pairs_total, "cores": cores, "list_build_s": farm.list_build_s}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if args.workload != "c2_pair_rdf":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm runs the benchmark workload c2_pair_rdf"}))
+        return
     kind, kind_name = oracle_kind()
-    tmp = tempfile.mkdtemp()
-    edm_file = write_edm(tmp)
-    rng = np.random.default_rng(1234 + 1)
-    warm = prewarm_hills(rng)
     cores = len(os.sched_getaffinity(0))
-    sample = 2_600_000 * cores                # bounded sample: 2.6e6 pair distances per instance per step
-    r = sample_pair_distances(rng, sample)
-    for _ in range(args.warmup):
-        cpu_pair_rate(kind, edm_file, r[: sample // 10], warm, cores, 1)
-    rates, tms = [], []
-    for _ in range(args.steps):
-        rate, t, _ = cpu_pair_rate(kind, edm_file, r, warm, cores, 1)
-        rates.append(rate)
-        tms.append(t)
-    value = sample * args.steps / sum(tms)
+    res = cpu_pair_loop(kind, EDM_TEXT, args.steps, args.warmup, cores)
+    value = res["evals_per_s"]
+    rng = np.random.default_rng(1234 + 1)
     hills = cpu_hill_rate(kind, 20000, rng)
+    sample = ("the full workload: all %d listed pairs of the 10^6-atom configuration (rank 0's first coordinate set) per "
+              "step, list rows sharded over %d single-rank instances pinned one per core; fix edm_pair's own loop "
+              "(sqrt, update_force, +-scatter, 2 add_hill per pair, post_add_hill); neighbour list built once, untimed "
+              "(%.1f s)" % (res["pairs_per_step"], cores, res["list_build_s"]))
     out = {
         "impl": "reference", "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(tms) / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "c2_pair_rdf", "atoms_per_gpu": N_ATOMS, "cutoff": CUTOFF,
-                   "step": "bounded sample: %d pair evaluations per step" % sample},
+        "config": c2_config(args.workload, args.gpus, res["pairs_in_list"]),
         "hills_per_s": hills,
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind_name,
-                         "sample": "%d pair distances (p(r)~r^2, r<5) per step through EDMBias::update_force, "
-                                   "%d single-rank instances pinned one per core; hills/s: 20000 add_value calls on "
-                                   "one core" % (sample, cores),
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": kind_name, "sample": sample,
+                         "slowest_instance_ms_per_step": res["slowest_instance_ms_per_step"],
                          "hills_per_s_1core": hills},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -292,50 +444,50 @@ def run_gpu(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
+    comm = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         bind_to_gpu_numa_node(local_rank)
+        # the hill exchange is the library's own (NCCL called from C++): torch.distributed only ships the 128-byte
+        # id once, synchronises the ranks around the timed region and reduces the final statistics
+        uid = [edm.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, 0)
+        comm = edm.Comm.init_rank(uid[0], world, rank, local_rank)
+    else:
+        comm = edm.Comm.init_rank(bytes(128), 1, 0, local_rank)
     L = edm.lib()
     tmp = tempfile.mkdtemp()
-    edm_file = write_edm(tmp, {"c5_pair_rdf_backlog": C5_TEXT, "c2_pair_rdf_local_tempering": C2_LOCAL_TEXT}.get(args.workload))
+    edm_text = {"c5_pair_rdf_backlog": C5_TEXT, "c2_pair_rdf_local_tempering": C2_LOCAL_TEXT}.get(args.workload, EDM_TEXT)
+    edm_file = write_edm(tmp, edm_text)
     bias = edm.bias_from_edm(edm_file, TEMPERATURE, BOLTZ, [1.68], [5.0], [1.68], [5.0], [0], [0.0], device=local_rank)
     warm_rng = np.random.default_rng(1234 + 1)
     warm = prewarm_hills(warm_rng)          # same hills on every rank: replicas start identical
     bias.bias_grid.add_values(*warm)
     edm.check(L.edm_bias_set_profiling(bias.h, 1))
 
-    box_len = (N_ATOMS / DENSITY) ** (1.0 / 3.0)
-    box = np.array([box_len] * 3)
-    rng = np.random.default_rng(1234 + 1 + 1000 * rank)
     n_sets = 3                               # rotate position sets; L2 is flushed between steps anyway
-    xs_host = [torch.from_numpy(rng.uniform(0, box_len, size=(N_ATOMS, 3))).pin_memory() for _ in range(n_sets)]
+    box_len, sets = c2_positions(rank, n_sets)
+    box = np.array([box_len] * 3)
+    xs_host = [torch.from_numpy(x).pin_memory() for x in sets]
     xs_dev = [x.cuda(non_blocking=True) for x in xs_host]
     f_dev = torch.zeros((N_ATOMS, 3), dtype=torch.float64, device="cuda")
     f_host = torch.zeros((N_ATOMS, 3), dtype=torch.float64).pin_memory()
     energy_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    blk_doubles = L.edm_hill_block_doubles(1, HILL_CAP)
-    block = torch.zeros(blk_doubles, dtype=torch.float64, device="cuda")
-    gathered = torch.zeros(blk_doubles * world, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     boxp = box.ctypes.data_as(C.POINTER(C.c_double))
     expected_pairs = N_ATOMS * (4.0 / 3.0) * np.pi * CUTOFF ** 3 * DENSITY / 2
     est_local = int(2 * expected_pairs)
-    seed = 20261018
+    seed = SEED
 
     def step_resident(step):
         x = xs_dev[step % n_sets]
         est_total = est_local * world
         edm.check(L.edm_pair_select_cells_dev(bias.h, N_ATOMS, x.data_ptr(), f_dev.data_ptr(), None, 0, 0, boxp,
                                               CUTOFF, est_total, seed + rank, step, energy_dev.data_ptr(), stream))
-        edm.check(L.edm_bias_hills_pack_dev(bias.h, block.data_ptr(), HILL_CAP, stream))
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, block)
-            src = gathered
-        else:
-            src = block
-        edm.check(L.edm_bias_hills_commit_dev(bias.h, src.data_ptr(), world, HILL_CAP, est_total, stream))
+        # pack -> ncclAllGather -> commit inside the library (one rank: pack -> commit)
+        edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, stream))
 
     def barrier():
         if world > 1:
@@ -375,12 +527,17 @@ def run_gpu(args, rank, local_rank, world):
     st1 = bias.state()
     hills_timed = len(bias.log())             # events logged since creation (prewarm deposits are not logged)
 
-    # ---- e2e through the host-buffer C ABI
+    bias.check()                              # nothing was dropped or overflowed in the timed rounds
+
+    # ---- e2e through the host-buffer C ABI.  With the communicator attached the call exchanges the hills by
+    # itself and takes this rank's est_hill_count, as fix edm_pair passes it.
+    bias.set_comm(comm, HILL_CAP)
+
     def step_e2e(step):
         xh = xs_host[step % n_sets]
         r = edm.PairResult()
         edm.check(L.edm_pair_step_cells(bias.h, N_ATOMS, xh.data_ptr(), f_host.data_ptr(), None, 0, 0, boxp, CUTOFF,
-                                        1, est_local * world, seed + rank, step, C.byref(r)))
+                                        1, est_local, seed + rank, step, C.byref(r)))
         return r
 
     r0 = step_e2e(step_no)
@@ -391,15 +548,23 @@ def run_gpu(args, rank, local_rank, world):
         pairs_per_step[step_no % n_sets] = rr.n_pairs
         step_no += 1
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
+    e2e_steps = args.steps                    # the same K as the device-timed figure
     e2e_pairs = 0
+    split = np.zeros(4)
+    t0 = time.perf_counter()
     for k in range(e2e_steps):
         rr = step_e2e(step_no)
         e2e_pairs += rr.n_pairs
         step_no += 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    for k in range(3):                        # the device-side split, outside the timed loop (event queries synchronise)
+        step_e2e(step_no)
+        step_no += 1
+        v = [C.c_double(0) for _ in range(4)]
+        edm.check(L.edm_bias_profile_e2e_ms(bias.h, *[C.byref(t) for t in v]))
+        split += np.array([t.value for t in v]) / 3.0
+    bias.set_comm(None)
 
     pairs_timed = sum(pairs_per_step[(st0["steps"] + k) % n_sets] for k in range(args.steps))
 
@@ -425,14 +590,15 @@ def run_gpu(args, rank, local_rank, world):
     clk = clocks.stop()   # covers the timed steps, the e2e steps and the deposit batches
 
     # ---- reduce over ranks: max time, summed work
-    stats = torch.tensor([total_ms, e2e_s, float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)],
-                         dtype=torch.float64, device="cuda")
+    stats = torch.tensor([total_ms, e2e_s, float(pairs_timed), float(e2e_pairs), hills_per_s, float(launches)] +
+                         list(split), dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms, e2e_s = float(mx[0]), float(mx[1])
+        split = mx[6:10].cpu().numpy()
         mn = stats.clone()
         dist.all_reduce(mn, op=dist.ReduceOp.MIN)
         # hills are NOT sharded: every replica deposits every hill, so the job's rate is one replica's
@@ -448,35 +614,44 @@ def run_gpu(args, rank, local_rank, world):
         info = bias.pair_search_info()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         st_hills = st1["steps"] - st0["steps"]
+        traffic, binding, traffic_src = ncu_roofline(args.workload, "block_eval_kernel")
+        h2d, d2h = 2 * N_ATOMS * 24, N_ATOMS * 24
         out = {
             "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "atoms_per_gpu": N_ATOMS, "number_density": DENSITY,
-                       "cutoff": CUTOFF, "pairs_per_gpu_per_step": pairs_per_step[0], "grid_points": 13281,
-                       "hill_density": 250, "hill_rounds_timed": st_hills,
+            "config": c2_config(args.workload, world, pairs_per_step[0]),
+            "timing": {"hill_rounds_timed": st_hills,
                        "l2": "flushed between timed steps (512 MiB memset outside the per-step CUDA-event pair)",
-                       "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
+                       "exchange": "edm_bias_exchange_dev: pack -> ncclAllGather -> commit, NCCL called by the library"},
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
                       "in_situ_hill_events": int(hills_timed),
                       "in_situ_hills_per_s": (st1["steps"] - st0["steps"]) * 250.0 / (total_ms * 1e-3) if total_ms else None,
                       "rounds": bias.round_info(),
                       "backlog": list(bias.backlog()[:2])},
-            "roofline": {"bound": "hbm", "kernel": "block_eval_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+            # achieved/peak/frac are the HBM figures the contract asks for (algorithmic bytes over the measured copy
+            # peak); `bound` names the resource that actually binds the kernel, read from the ncu capture on record
+            # for THIS build (null when there is none), never typed in
+            "roofline": {"bound": (binding or {}).get("bound", "hbm"), "kernel": "block_eval_kernel",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "hbm_frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "search_kernel_ms": float(np.mean(find_ms)), "pair_kernels_ms": float(np.mean(pair_ms)),
                          "bricks": list(info["bricks"]), "fallbacks": info["fallbacks"],
-                         "traffic_source": NCU_TRAFFIC_SOURCE,
-                         "binding_resource": {"name": "L1/shared-memory data pipe (l1tex LSU wavefronts)",
-                                              "pct_of_peak": 75.5, "issue_slots_pct": 68.0, "fp64_pipe_pct": 23.5,
-                                              "dram_pct": 4.0, "source": "profiles/r01_i_block_eval_ncu_selected.txt"},
-                         "note": "not HBM bound (SURVEY 8d: 2.9 B/pair of compulsory traffic): ncu shows the LSU data "
-                                 "pipe (shared-memory gathers, atomics, shuffles) and the issue slots near 75 %"},
+                         "traffic_source": traffic_src, "binding_resource": binding, "csrc_hash": csrc_hash(),
+                         "note": "not HBM bound by design (SURVEY 8d: 2.9 B/pair of compulsory traffic)"},
             "e2e": {"value": e2e_pairs_all / e2e_s, "unit": "evals/s",
-                    "h2d_bytes_per_step": 2 * N_ATOMS * 24, "d2h_bytes_per_step": N_ATOMS * 24 + 24,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + 32,
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "split_ms": {"x_h2d": float(split[0]), "kernels": float(split[1]), "f_d2h": float(split[2]),
+                                 "device_span": float(split[3]),
+                                 "host_overhead": 1e3 * e2e_s / e2e_steps - float(split[3]),
+                                 "note": "max over ranks; the 24 MB f upload and the f download run on a copy stream "
+                                         "beside the search and the hill round"},
+                    "pcie_gbs": {"x_h2d": 24e-6 * N_ATOMS / float(split[0]) if split[0] > 0 else None,
+                                 "f_d2h": 24e-6 * N_ATOMS / float(split[2]) if split[2] > 0 else None,
+                                 "note": "slowest rank's achieved host-link rate; ranks share the host's root complexes"}},
             "gpu_launches": int(launches_all),
             "clocks": clk,
         }
@@ -484,21 +659,26 @@ def run_gpu(args, rank, local_rank, world):
             kind, kind_name = oracle_kind()
             cores = len(os.sched_getaffinity(0))
             crng = np.random.default_rng(4321)
-            sample = 2_600_000 * cores
-            r = sample_pair_distances(crng, sample)
-            rate, t, _ = cpu_pair_rate(kind, edm_file, r, warm, cores, 2)
-            rate1, _, _ = cpu_pair_rate(kind, edm_file, r[:2_600_000], warm, 1, 2)
+            res = cpu_pair_loop(kind, edm_text, 4, 1, cores)                    # the real loop, all cores
+            res1 = cpu_pair_loop(kind, edm_text, 2, 1, 1, pair_limit=2_000_000)  # and one core on a 2e6-pair sample
+            r = sample_pair_distances(crng, 1_000_000 * cores)
+            bare = cpu_pair_rate(kind, edm_file, r, warm, cores, 2)
             hills = cpu_hill_rate(kind, 20000, crng)
             out["cpu_baseline"] = {
-                "value": rate, "unit": "evals/s", "cores": cores, "kind": kind_name,
-                "sample": "%d pair distances x2 through EDMBias::update_force on %d single-rank instances (one per "
-                          "core, full grid replica each); hills/s: 20000 GaussGrid::add_value calls on one core"
-                          % (sample, cores),
-                "evals_per_s_1core": rate1, "hills_per_s_1core": hills}
+                "value": res["evals_per_s"], "unit": "evals/s", "cores": cores, "kind": kind_name,
+                "sample": "4 steps of fix edm_pair's own loop (lammps/fix_edm_pair.cpp:173-247: sqrt, update_force, "
+                          "+-scatter, 2 add_hill per pair, post_add_hill) over all %d listed pairs of this workload, list "
+                          "rows sharded over %d single-rank instances, one per core; list built once, untimed"
+                          % (res["pairs_per_step"], cores),
+                "ms_per_step": res["ms_per_step"], "evals_per_s_1core": res1["evals_per_s"],
+                "bare_update_force_evals_per_s": bare,
+                "bare_update_force_note": "EDMBias::update_force alone over pre-drawn distances (no list walk, sqrt, "
+                                          "scatter or hills), %d instances: the round-1 figure, kept for continuity" % cores,
+                "hills_per_s_1core": hills}
         print(json.dumps(out))
+    comm.destroy()
     if world > 1:
         dist.destroy_process_group()
-
 
 
 # ------------------------------------------------------------------ GPU arm, coordinate workloads
@@ -516,6 +696,11 @@ def run_coord(args, rank, local_rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        uid = [edm.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, 0)
+        comm = edm.Comm.init_rank(uid[0], world, rank, local_rank)
+    else:
+        comm = edm.Comm.init_rank(bytes(128), 1, 0, local_rank)
     cfg = COORD_WORKLOADS[args.workload]
     L = edm.lib()
     tmp = tempfile.mkdtemp()
@@ -539,11 +724,8 @@ def run_coord(args, rank, local_rank, world):
     f_host = torch.zeros((n_atoms, D), dtype=torch.float64).pin_memory()
     energy_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-    blk_doubles = L.edm_hill_block_doubles(D, HILL_CAP)
-    block = torch.zeros(blk_doubles, dtype=torch.float64, device="cuda")
-    gathered = torch.zeros(blk_doubles * world, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
-    seed = 20261018
+    seed = SEED
     est_total = n_atoms * world
 
     def forces(step):
@@ -558,9 +740,7 @@ def run_coord(args, rank, local_rank, world):
         else:
             edm.check(L.edm_bias_select_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, est_total, seed, step,
                                             rank * n_atoms, stream))
-            edm.check(L.edm_bias_hills_pack_dev(bias.h, block.data_ptr(), HILL_CAP, stream))
-            dist.all_gather_into_tensor(gathered, block)
-            edm.check(L.edm_bias_hills_commit_dev(bias.h, gathered.data_ptr(), world, HILL_CAP, est_total, stream))
+            edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, stream))
 
     def barrier():
         if world > 1:
@@ -586,10 +766,8 @@ def run_coord(args, rank, local_rank, world):
             sst = side.cuda_stream
             edm.check(L.edm_bias_select_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, est_total, seed, step,
                                             rank * n_atoms, sst))
-            edm.check(L.edm_bias_hills_pack_dev(bias.h, block.data_ptr(), HILL_CAP, sst))
-            dist.all_gather_into_tensor(gathered, block)
             edm.check(L.edm_bias_round_after(bias.h, ev_k1.cuda_event))   # the deposit waits for the force update
-            edm.check(L.edm_bias_hills_commit_dev(bias.h, gathered.data_ptr(), world, HILL_CAP, est_total, sst))
+            edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, sst))
             ev_join.record(side)
         main.wait_event(ev_join)
 
@@ -684,7 +862,11 @@ def run_coord(args, rank, local_rank, world):
                       "rounds_split": info1["split"] - info0["split"],
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},
             "roofline": {"bound": "hbm", "kernel": "forces_kernel<%d>" % D, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[0],
+                         "traffic_source": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[2],
+                         "binding_resource": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[1],
+                         "peak_source": peak_src,
                          "kernel_ms": k1, "algorithmic_bytes_per_launch": alg,
                          "note": "kernel_ms spans forces_kernel + the 1-CTA energy sum (CUDA events on the launch stream)"},
             "gpu_launches": int(launches_all),
@@ -695,6 +877,8 @@ def run_coord(args, rank, local_rank, world):
                           "h2d_bytes_per_step": 2 * n_atoms * D * 8, "d2h_bytes_per_step": n_atoms * D * 8 + 8,
                           "ms_per_step": e2e_ms}
         print(json.dumps(out))
+    bias.check()
+    comm.destroy()
     if world > 1:
         dist.destroy_process_group()
 
@@ -706,10 +890,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--csrc-hash", action="store_true", help="print the hash of the csrc/ tree and exit")
     ap.add_argument("--workload", default="c2_pair_rdf",
                     choices=["c2_pair_rdf", "c5_pair_rdf_backlog", "c2_pair_rdf_local_tempering"] + sorted(COORD_WORKLOADS),
                     help="c2_pair_rdf is the benchmark (BASELINE.json configs[1]); the others are the remaining configs")
     args = ap.parse_args()
+    if args.csrc_hash:
+        print(csrc_hash())
+        return
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

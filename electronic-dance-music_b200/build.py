@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libedm_b200.so")
-SOURCES = ["edm_grid.cu", "edm_bias.cu", "edm_pair.cu"]
+SOURCES = ["edm_grid.cu", "edm_bias.cu", "edm_pair.cu", "edm_comm.cu"]
 HEADERS = ["edm_device.cuh", "edm_host.h", os.path.join("..", "..", "include", "edm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -55,7 +55,7 @@ def build_lib(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs
+        cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-ldl"]
         subprocess.check_call(cmd)
     return LIB
 
@@ -64,6 +64,7 @@ HOST_SRCS = ["edm.cpp", "grid.cpp", "gaussian_grid.cpp", "edm_bias.cpp", "edm_bi
 HOST_LIB = os.path.join(LIBDIR, "libedm.so")
 HOST_TEST = os.path.join(LIBDIR, "edm_host_test")
 FIX_DRIVER = os.path.join(LIBDIR, "fix_driver_test")
+EXCHANGE_TEST = os.path.join(LIBDIR, "exchange_test")
 CXX = "/usr/bin/g++"
 CXXFLAGS = ["-std=c++11", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
 
@@ -97,6 +98,11 @@ def build_host_tests(force=False):
         subprocess.check_call([CXX] + CXXFLAGS + ["-I" + HERE, "-I" + os.path.join(lmp, "mock"), "-I" + lmp, "-o",
                                                   FIX_DRIVER, drv_src] + objs +
                               ["-L" + LIBDIR, "-ledm", "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
+    # the multi-device hill exchange driven from C++ (ncclCommInitAll, one host thread per device)
+    xt_src = os.path.join(HERE, "tests_host", "exchange_test.cpp")
+    if force or _stale(EXCHANGE_TEST, [xt_src, HOST_LIB]):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-pthread", "-I" + HERE, "-o", EXCHANGE_TEST, xt_src,
+                                                  "-L" + LIBDIR, "-ledm", "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_TEST
 
 

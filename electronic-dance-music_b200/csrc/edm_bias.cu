@@ -584,7 +584,9 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
     int mode = (!st->accepted_overflow && nb + st->n_accepted <= n_max) ? 1 : 0;
     s_nb = (int)nb;
     st->n_plan_b = (int)nb;
-    if (DIM > 1 && bias.dup_possible) mode = 0;    // concurrent hills would revisit points of their own window
+    // a periodic window wider than the grid revisits its own points: concurrent hills (DIM > 1) and the plan's
+    // one-term-per-predecessor corner patches (local tempering) both assume a single visit
+    if (bias.dup_possible && (DIM > 1 || local)) mode = 0;
     if (local && bias.n_dup > 0) mode = 0;         // duplicate_boundary rewrites records between hills
     s_mode = mode;
     st->round_mode = mode;
@@ -968,7 +970,10 @@ __global__ void reset_accepted_kernel(BiasDev* st) {
 template <int DIM>
 __global__ void pack_block_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* tmp, double* block, long cap) {
   int n = st->n_accepted;
-  if (n > cap) n = (int)cap;
+  if (n > cap) {  // never drop hills silently: edm_bias_check / the next host-synchronising call reports it
+    if (threadIdx.x == 0) st->accepted_overflow = 1;
+    n = (int)cap;
+  }
   if (!st->accepted_sorted) cta_sort_accepted(acc, tmp, n);
   if (threadIdx.x == 0) {
     block[0] = (double)n;
@@ -1090,7 +1095,8 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     int* term_j = reinterpret_cast<int*>(b->fast.as<char>() + b_dbl + b_plan + b_cells + b_terms);
     round_plan_kernel<DIM><<<1, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres,
                                                heights, plan, cells, terms, term_j, term_cap);
-    const int blocks = (int)(n_max < 148 * 4 ? n_max : 148 * 4);
+    const long nsm4 = 4L * sm_count(b->device);
+    const int blocks = (int)(n_max < nsm4 ? n_max : nsm4);
     round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
     round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
     count_launches(3);
@@ -1128,7 +1134,9 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
 }
 
 // launches the hill round over whatever sits in the accepted buffer
-int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st) {
+int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st, bool exchange) {
+  // post_add_hill's flush_buffers (lib/edm_bias.cpp:576-577): gather every rank's accepted hills first
+  if (exchange && b->comm) return edm_bias_exchange_round(b, est, st);
   RoundParams rp = round_params(b, est);
   GridDesc none;
   memset(&none, 0, sizeof(none));
@@ -1169,7 +1177,7 @@ static int select_launch(edm_bias* b, long n, const double* x, long xs, const do
   double thresh = accept_all ? 2.0 : p.hill_density / (double)(int)est;  // lib/edm_bias.cpp:543 (est is an int there)
   uint64_t key = uniform_key(seed, step);
   long long blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 8LL * sm_count(b->device)) blocks = 8LL * sm_count(b->device);
   count_launches(1);
   switch (p.dim) {
     case 1: select_kernel<1><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
@@ -1198,7 +1206,7 @@ int edm_bias_create(edm_bias_t** out, edm_grid_t* bias, edm_grid_t* cv_hist, edm
   EDM_CUDA(cudaMemset(b->d_state, 0, sizeof(BiasDev)));  // T19: the backlog storage starts zero-filled
   b->log_cap = 1 << 16;
   EDM_CUDA(cudaMalloc(&b->d_log, (size_t)b->log_cap * sizeof(edm_hill_event_t)));
-  b->n_partial = 148 * 8;
+  b->n_partial = sm_count(b->device) * 8;
   EDM_CUDA(cudaMalloc(&b->d_energy_partial, (size_t)b->n_partial * sizeof(double)));
   EDM_CUDA(cudaMalloc(&b->d_scalar, 8 * sizeof(double)));
   EDM_TRY(ensure_accepted(b, 4096));
@@ -1221,9 +1229,13 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->io4.release();
   b->cells.release();
   b->fast.release();
+  b->xchg.release();
   b->list.release();
   b->cand.release();
   if (b->h_pair_flags) cudaFreeHost((void*)b->h_pair_flags);
+  if (b->ev_prev) cudaEventDestroy(b->ev_prev);
+  for (int i = 0; i < 5; i++)
+    if (b->ev_e2e[i]) cudaEventDestroy(b->ev_e2e[i]);
   if (b->st_main) cudaStreamDestroy(b->st_main);
   if (b->st_copy) cudaStreamDestroy(b->st_copy);
   if (b->ev_f_up) cudaEventDestroy(b->ev_f_up);
@@ -1363,8 +1375,9 @@ static int coords_pipeline(edm_bias* b, long n, const double* x, long xs, double
     EDM_CUDA(cudaMalloc(&b->d_chunk_energy, edm_bias::kMaxChunks * sizeof(double)));
   }
   EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
+  const long long est = edm_job_est(b, n);  // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
   if (do_hills) {
-    EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
+    EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
     EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
   }
   if (n > 0) {
@@ -1390,15 +1403,15 @@ static int coords_pipeline(edm_bias* b, long n, const double* x, long xs, double
       EDM_CUDA(cudaStreamWaitEvent(b->st_main, b->ev_chunk_up[c], 0));
       EDM_TRY(edm_bias_update_forces_dev(b, cnt, dx + o * xs, xs, df + o * fs, fs, dm ? dm + o : nullptr, apply_mask,
                                          b->d_chunk_energy + c, b->st_main));
-      // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17); candidate keys = atom indices
+      // candidate keys = atom indices
       if (do_hills)
-        EDM_TRY(select_launch(b, cnt, dx + o * xs, xs, du ? du + o : nullptr, dm ? dm + o : nullptr, apply_mask, n, seed,
+        EDM_TRY(select_launch(b, cnt, dx + o * xs, xs, du ? du + o : nullptr, dm ? dm + o : nullptr, apply_mask, est, seed,
                               step, (uint64_t)o, b->st_main));
       EDM_CUDA(cudaEventRecord(b->ev_chunk_done[c], b->st_main));
       EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_chunk_done[c], 0));
       EDM_CUDA(cudaMemcpyAsync(f + o * fs, df + o * fs, (size_t)cnt * fs * sizeof(double), cudaMemcpyDeviceToHost, b->st_copy));
     }
-    if (do_hills) EDM_TRY(edm_bias_launch_round(b, n, b->st_main));
+    if (do_hills) EDM_TRY(edm_bias_launch_round(b, est, b->st_main));
     double e[edm_bias::kMaxChunks];
     EDM_CUDA(cudaMemcpyAsync(e, b->d_chunk_energy, nchunks * sizeof(double), cudaMemcpyDeviceToHost, b->st_main));
     EDM_CUDA(cudaStreamSynchronize(b->st_main));
@@ -1407,7 +1420,7 @@ static int coords_pipeline(edm_bias* b, long n, const double* x, long xs, double
     if (energy) *energy = tot;
     EDM_CUDA(cudaStreamSynchronize(b->st_copy));
   } else if (do_hills) {
-    EDM_TRY(edm_bias_launch_round(b, n, b->st_main));
+    EDM_TRY(edm_bias_launch_round(b, est, b->st_main));
     EDM_CUDA(cudaStreamSynchronize(b->st_main));
   }
   return do_hills ? edm_bias_check_round(b) : EDM_OK;
@@ -1452,11 +1465,11 @@ int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride,
   EDM_REQUIRE(b != nullptr, "NULL argument");
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
-  EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
+  const long long est = edm_job_est(b, n);  // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
+  EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
   EDM_TRY(edm_bias_reset_accepted(b, st));
-  // est_hill_count = nlocal, masked or not (lib/edm_bias.cpp:404, T17)
-  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, st));
-  return edm_bias_launch_round(b, n, st);
+  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, est, seed, step, 0, st));
+  return edm_bias_launch_round(b, est, st);
 }
 
 int edm_bias_round_after(edm_bias_t* b, void* event) {
@@ -1486,11 +1499,12 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
   if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream));
   EDM_CUDA(cudaEventRecord(b->ev_forces, st));
-  EDM_TRY(edm_bias_size_accepted(b, (double)n, n));
+  const long long est = edm_job_est(b, n);
+  EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
   EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
-  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, n, seed, step, 0, b->st_side));
+  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, est, seed, step, 0, b->st_side));
   b->round_after = b->ev_forces;
-  EDM_TRY(edm_bias_launch_round(b, n, b->st_side));
+  EDM_TRY(edm_bias_launch_round(b, est, b->st_side));
   EDM_CUDA(cudaEventRecord(b->ev_join, b->st_side));
   EDM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
   return EDM_OK;
@@ -1530,7 +1544,7 @@ int edm_bias_pre_add_hill(edm_bias_t* b, int est_hill_count) {
   EDM_TRY(ensure_device(b->device));
   EDM_TRY(edm_bias_reset_accepted(b, 0));
   b->in_round = 1;
-  b->round_est = est_hill_count;
+  b->round_est = edm_job_est(b, est_hill_count);
   b->round_count = 0;
   return EDM_OK;
 }
@@ -1624,6 +1638,28 @@ int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms) 
   return EDM_OK;
 }
 
+// Where the last profiled edm_pair_step_cells (host buffers) spent its time on the device: upload of the
+// positions, everything from there to the step's last kernel (binning, pair kernels, hill round, report),
+// the download of the forces (which overlaps the hill round), and the whole span from the first copy to
+// the later of the two ends.  Synchronises on the recorded events.
+int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, double* f_down_ms, double* span_ms) {
+  EDM_REQUIRE(b && b->e2e_valid, "no profiled host-buffer pair step (edm_bias_set_profiling, then edm_pair_step_cells)");
+  EDM_TRY(ensure_device(b->device));
+  EDM_CUDA(cudaEventSynchronize(b->ev_e2e[2]));
+  EDM_CUDA(cudaEventSynchronize(b->ev_e2e[4]));
+  float up = 0, k = 0, dn = 0, s1 = 0, s2 = 0;
+  EDM_CUDA(cudaEventElapsedTime(&up, b->ev_e2e[0], b->ev_e2e[1]));
+  EDM_CUDA(cudaEventElapsedTime(&k, b->ev_e2e[1], b->ev_e2e[2]));
+  EDM_CUDA(cudaEventElapsedTime(&dn, b->ev_e2e[3], b->ev_e2e[4]));
+  EDM_CUDA(cudaEventElapsedTime(&s1, b->ev_e2e[0], b->ev_e2e[2]));
+  EDM_CUDA(cudaEventElapsedTime(&s2, b->ev_e2e[0], b->ev_e2e[4]));
+  if (x_up_ms) *x_up_ms = up;
+  if (kernels_ms) *kernels_ms = k;
+  if (f_down_ms) *f_down_ms = dn;
+  if (span_ms) *span_ms = s1 > s2 ? s1 : s2;
+  return EDM_OK;
+}
+
 // ------------------------------------------------------------------ multi-GPU exchange
 
 size_t edm_hill_block_doubles(int dim, long cap) { return 1 + (size_t)cap * dim; }
@@ -1656,7 +1692,13 @@ int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, 
     default: unpack_blocks_kernel<3><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
   }
   EDM_CUDA(cudaGetLastError());
-  return edm_bias_launch_round(b, est_hill_count, st);
+  return edm_bias_launch_round(b, est_hill_count, st, false);
+}
+
+int edm_bias_check(edm_bias_t* b) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  return edm_bias_check_round(b);
 }
 
 }  // extern "C"

@@ -37,6 +37,16 @@ int ensure_device(int device) {
   EDM_CUDA(cudaSetDevice(device));
   return EDM_OK;
 }
+int sm_count(int device) {
+  static int cached[64];
+  if (device < 0 || device >= 64) return 148;
+  if (cached[device] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    cached[device] = n;
+  }
+  return cached[device];
+}
 int Scratch::reserve(size_t need) {
   if (need <= bytes) return EDM_OK;
   if (p) EDM_CUDA(cudaFree(p));
@@ -857,7 +867,9 @@ int edm_grid_set_interpolation(edm_grid_t* g, int b) {
 
 static int launch_blocks(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
-  long long cap = 148LL * 16;
+  int dev = 0;
+  cudaGetDevice(&dev);  // callers have selected the grid's device (ensure_device)
+  long long cap = (long long)sm_count(dev) * 16;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
@@ -1074,7 +1086,8 @@ int edm_gauss_deposit_dev(edm_grid_t* g, long n, const double* centres, const do
   cudaStream_t st = (cudaStream_t)stream;
   const GridDesc& d = g->d;
   if (d.dim == 1 && d.minisize[0] < d.n[0]) return deposit_1d_owner(g, n, centres, heights, bias_added, st);
-  int blocks = (int)(n < 148L * 8 ? n : 148L * 8);
+  const long nsm8 = 8L * sm_count(g->device);
+  int blocks = (int)(n < nsm8 ? n : nsm8);
   switch (d.dim) {
     case 1: deposit_hills_kernel<1><<<blocks, 256, 0, st>>>(d, n, centres, heights, bias_added, g->d_flags); break;
     case 2: deposit_hills_kernel<2><<<blocks, 256, 0, st>>>(d, n, centres, heights, bias_added, g->d_flags); break;

@@ -34,6 +34,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
   } while (0)
 
 int ensure_device(int device);
+// multiprocessors of a device (cudaDevAttrMultiProcessorCount, cached): grids are sized in multiples of it
+int sm_count(int device);
 // 1-D owner-computes deposit split in two so a caller can decide between them (edm_grid.cu):
 // stage = prepare + accumulate into scratch (+ per-hill integrals), commit = write the grid back
 // only if *flag >= want.  n is read from *n_dev (clamped to n_max) when n_dev is not NULL.
@@ -102,6 +104,21 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int hill_done[EDM_ROUND_MAX];          // parallel deposit: hill k finished in round hill_done[k]
 };
 
+// Host-mapped (zero-copy) block a host-buffer step writes its scalars to with its last kernel, so the host
+// reads them right after the stream synchronise instead of issuing three blocking 8-byte copies.
+struct HostReport {
+  int fallback;  // a pair step fell back to the direct search (read without synchronising by the next launch)
+  int backlog_full, accepted_overflow, pad;
+  double energy;
+  unsigned long long n_pairs, n_calls;
+};
+
+struct edm_comm {  // one rank's end of the hill exchange (edm_comm.cu)
+  void* nccl = nullptr;  // ncclComm_t
+  int nranks = 1, rank = 0, device = 0;
+  int owned = 0;         // the ncclComm_t is destroyed with the handle
+};
+
 struct edm_bias {
   int device = 0;
   edm_bias_params_t prm;
@@ -119,8 +136,11 @@ struct edm_bias {
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels
   edm::Scratch cand;                   // candidate items of the block pair search, one slice per brick
-  volatile int* h_pair_flags = nullptr; // host-mapped: [0] = a pair step fell back to the direct search
+  volatile int* h_pair_flags = nullptr; // host-mapped HostReport: [0] = a pair step fell back to the direct search
   int* d_pair_flags = nullptr;
+  cudaEvent_t ev_prev = nullptr;        // "everything enqueued on the default stream before this call"
+  cudaEvent_t ev_e2e[5] = {};           // profiling: start, x is up, kernels done, f-down start, f-down end
+  int e2e_valid = 0;
   int brick_dims[3] = {0, 0, 0};       // bricks of the last pair step (0: direct search)
   long long pair_fallbacks = 0;        // steps that fell back to the direct search
   double brick_scale = 1.0;            // density inflation used to size the bricks (grows after a fallback)
@@ -132,11 +152,16 @@ struct edm_bias {
   int* list_jlist = nullptr;
   int* list_row = nullptr;
   edm::Scratch fast;                   // centres | heights | bias_added of the parallel hill round
+  // multi-GPU: communicator attached by edm_bias_set_comm (borrowed) and the exchange buffers
+  edm_comm_t* comm = nullptr;
+  long comm_cap = 4096;
+  edm::Scratch xchg;                   // this rank's hill block | the rank-major concatenation of all blocks
   // streaming triple
   int in_round = 0;
   long long round_est = 0;
   unsigned long long round_count = 0;
   int profiling = 0;
+  int eval_attr_set = 0;               // block_eval_kernel's dynamic shared-memory limit raised on this device
   cudaStream_t st_main = nullptr, st_copy = nullptr;  // host-buffer pair step: kernels / overlapped copies
   cudaEvent_t ev_f_up = nullptr, ev_f_final = nullptr;
   // host-buffer coordinate step: chunks pipelined over upload / kernels / download
@@ -150,3 +175,17 @@ struct edm_bias {
   cudaEvent_t round_after = nullptr;  // borrowed, one-shot: the next round's first grid write waits for it
   cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };
+
+// ---- internal entry points shared by the translation units.  est is always the JOB-WIDE est_hill_count here;
+// the public whole-round entry points convert their per-rank argument with edm_job_est.
+int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st);
+int edm_bias_size_accepted(edm_bias* b, double candidates, long long est);
+// the hill round over whatever sits in the accepted buffer; with a communicator attached and
+// exchange = true the accepted hills of all ranks are gathered first (edm_bias_exchange_round)
+int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st, bool exchange = true);
+int edm_bias_exchange_round(edm_bias* b, long long est, cudaStream_t st);
+int edm_bias_check_round(edm_bias* b);
+int edm_host_report_ensure(edm_bias* b);
+inline long long edm_job_est(const edm_bias* b, long long est) {
+  return (b->comm && b->comm->nranks > 1) ? est * b->comm->nranks : est;
+}

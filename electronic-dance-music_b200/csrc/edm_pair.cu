@@ -8,11 +8,6 @@
 
 #include "edm_host.h"
 
-int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st);
-int edm_bias_size_accepted(edm_bias* b, double candidates, long long est);
-int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st);
-int edm_bias_check_round(edm_bias* b);
-
 namespace edm {
 
 struct CellGrid {
@@ -947,9 +942,68 @@ __global__ void sum_partials2_kernel(int n, const double* __restrict__ partial, 
   }
 }
 
+// last kernel of a host-buffer step: the scalars the host wants, into host-mapped memory
+__global__ void step_report_kernel(const BiasDev* st, const double* energy, const unsigned long long* ncalls,
+                                   HostReport* rep) {
+  rep->energy = energy ? *energy : 0.0;
+  rep->n_pairs = st->n_pairs;
+  rep->n_calls = ncalls ? *ncalls : 2ULL * st->n_pairs;
+  rep->backlog_full = st->backlog_full;
+  rep->accepted_overflow = st->accepted_overflow;
+  __threadfence_system();
+}
+
 }  // namespace edm
 
 using namespace edm;
+
+int edm_host_report_ensure(edm_bias* b) {
+  if (b->h_pair_flags) return EDM_OK;
+  static_assert(sizeof(HostReport) <= 64, "HostReport outgrew its allocation");
+  EDM_CUDA(cudaHostAlloc((void**)&b->h_pair_flags, 64, cudaHostAllocMapped));
+  memset((void*)b->h_pair_flags, 0, 64);
+  EDM_CUDA(cudaHostGetDevicePointer((void**)&b->d_pair_flags, (void*)b->h_pair_flags, 0));
+  return EDM_OK;
+}
+
+// streams and events of the host-buffer pair steps; orders both streams after whatever the caller
+// enqueued on the default stream before this call (uploads, _dev entry points), without stalling the host
+static int pair_host_streams(edm_bias* b) {
+  if (!b->st_main) {
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
+    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
+    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
+  }
+  if (!b->ev_prev) EDM_CUDA(cudaEventCreateWithFlags(&b->ev_prev, cudaEventDisableTiming));
+  EDM_CUDA(cudaEventRecord(b->ev_prev, 0));
+  EDM_CUDA(cudaStreamWaitEvent(b->st_main, b->ev_prev, 0));
+  EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_prev, 0));
+  if (b->profiling && !b->ev_e2e[0])
+    for (int i = 0; i < 5; i++) EDM_CUDA(cudaEventCreate(&b->ev_e2e[i]));
+  return edm_host_report_ensure(b);
+}
+
+// after the stream that ran step_report_kernel has been synchronised
+static int pair_host_result(edm_bias* b, edm_pair_result_t* result, int do_hills) {
+  const HostReport* rep = reinterpret_cast<const HostReport*>(const_cast<const int*>(b->h_pair_flags));
+  if (result) {
+    result->energy = rep->energy;
+    result->n_pairs = (long long)rep->n_pairs;
+    result->n_calls = (long long)rep->n_calls;
+  }
+  if (do_hills) {
+    if (rep->backlog_full) {
+      set_error("The bias overflow buffer is full. Too many hills (lib/edm_bias.cpp:503-507)");
+      return EDM_ERR_BACKLOG_FULL;
+    }
+    if (rep->accepted_overflow) {
+      set_error("accepted-hill buffer exhausted");
+      return EDM_ERR_CAPACITY;
+    }
+  }
+  return EDM_OK;
+}
 
 static PairParams pair_params(const edm_bias* b, const int* type, int itype, int jtype, int do_hills, long long est,
                               uint64_t seed, uint64_t step, double cutoff, long natoms) {
@@ -969,7 +1023,8 @@ static PairParams pair_params(const edm_bias* b, const int* type, int itype, int
     pp.thresh_bits = tb >= 4294967296.0 ? 4294967296ULL : (tb <= 0.0 ? 0ULL : (uint64_t)tb);
   }
   pp.key = uniform_key(seed, step);
-  pp.dbg = getenv("EDM_DBG") ? atoi(getenv("EDM_DBG")) : 0;
+  static const int dbg_env = getenv("EDM_DBG") ? atoi(getenv("EDM_DBG")) : 0;  // read once, not per step
+  pp.dbg = dbg_env;
   pp.rc2 = cutoff * cutoff;
   pp.rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;
   pp.natoms = natoms;
@@ -1037,11 +1092,7 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   cg.ncell = (int)ncell;
 
   // feedback from earlier steps (device-written, host-mapped): a fallback shrinks the bricks
-  if (!b->h_pair_flags) {
-    EDM_CUDA(cudaHostAlloc(&b->h_pair_flags, 64, cudaHostAllocMapped));
-    memset((void*)b->h_pair_flags, 0, 64);
-    EDM_CUDA(cudaHostGetDevicePointer(&b->d_pair_flags, (void*)b->h_pair_flags, 0));
-  }
+  EDM_TRY(edm_host_report_ensure(b));
   if (b->h_pair_flags[0]) {
     b->h_pair_flags[0] = 0;
     b->pair_fallbacks++;
@@ -1057,7 +1108,7 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   const bool bricks = (mode != 0) && choose_bricks(cg, natoms, cutoff, b->brick_scale, bg);
   const int nblocks = bricks ? bg.nb[0] * bg.nb[1] * bg.nb[2] : 0;
   for (int d = 0; d < 3; d++) b->brick_dims[d] = bricks ? bg.bd[d] : 0;
-  const int dblocks = 148 * 8;  // direct search: grid-stride over the atoms
+  const int dblocks = sm_count(b->device) * 8;  // direct search: grid-stride over the atoms
 
   // scratch: cell_of[n] order[n] | count[ncell+1] start[ncell+1] tiles | flags | nchunks[nblocks] |
   //          partial[nblocks + dblocks] | arec[n] | xs32[n]
@@ -1116,10 +1167,9 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   if (b->profiling) EDM_CUDA(cudaEventRecord(b->ev_pair[0], st));
   int launched = 7;
   if (bricks) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!b->eval_attr_set) {  // per device: one process may drive several
       EDM_CUDA(cudaFuncSetAttribute(block_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EvalSmem)));
-      attr_set = true;
+      b->eval_attr_set = 1;
     }
     if (type)
       block_find_kernel<true><<<nblocks, kFindThreads, 0, st>>>(ctx, bg, b->cand.as<unsigned>(), nchunks);
@@ -1179,6 +1229,7 @@ int edm_pair_step_cells_dev(edm_bias_t* b, long natoms, const double* x, double*
   EDM_REQUIRE(b && x && f && box, "NULL argument");
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
+  est_hill_count = edm_job_est(b, est_hill_count);
   if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, st));
   EDM_TRY(pair_cells_launch(b, natoms, x, f, type, itype, jtype, box, cutoff, do_hills, est_hill_count, seed, step,
                             b->d_scalar, st));
@@ -1196,20 +1247,18 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
                         uint64_t step, edm_pair_result_t* result) {
   EDM_REQUIRE(b && x && f && box && natoms > 0, "bad argument");
   EDM_TRY(ensure_device(b->device));
+  est_hill_count = edm_job_est(b, est_hill_count);
   // Two streams so the copies hide behind the kernels that do not need them (pinned host buffers
   // make the copies truly asynchronous; pageable ones still work, staged by the driver):
-  //   main: x up | binning, search                | evaluation | hill round
+  //   main: x up | binning, search                | evaluation | hill round | report
   //   copy:      | f up (needed by the evaluation) |            | f down (final once the evaluation ends)
-  if (!b->st_main) {
-    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
-    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
-    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
-    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
-  }
+  // One host synchronisation per stream at the end; the scalars come back through host-mapped memory.
+  EDM_TRY(pair_host_streams(b));
   const size_t bx = (size_t)natoms * 3 * sizeof(double);
   EDM_TRY(b->io.reserve(bx));
   EDM_TRY(b->io2.reserve(bx));
-  EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
+  const bool prof = b->profiling != 0;
+  if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[0], b->st_main));
   const int* dt = nullptr;
   if (type) {
     EDM_TRY(b->io3.reserve((size_t)natoms * sizeof(int)));
@@ -1217,21 +1266,25 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
     dt = b->io3.as<int>();
   }
   EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, b->st_main));
+  if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[1], b->st_main));
   EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, b->st_copy));
   EDM_CUDA(cudaEventRecord(b->ev_f_up, b->st_copy));
   if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
   EDM_TRY(pair_cells_launch(b, natoms, b->io.as<double>(), b->io2.as<double>(), dt, itype, jtype, box, cutoff, do_hills,
                             est_hill_count, seed, step, b->d_scalar, b->st_main, b->ev_f_up, b->ev_f_final));
   EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_f_final, 0));
+  if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[3], b->st_copy));
   EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, b->st_copy));
+  if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[4], b->st_copy));
   if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, b->st_main));
+  step_report_kernel<<<1, 1, 0, b->st_main>>>(b->d_state, b->d_scalar, nullptr, reinterpret_cast<HostReport*>(b->d_pair_flags));
+  count_launches(1);
+  if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[2], b->st_main));
+  b->e2e_valid = prof ? 1 : 0;
   EDM_CUDA(cudaStreamSynchronize(b->st_main));
-  edm_pair_result_t local;
-  EDM_TRY(read_pair_result(b, &local, nullptr));
-  if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  const int rc = pair_host_result(b, result, do_hills);
   EDM_CUDA(cudaStreamSynchronize(b->st_copy));
-  if (result) *result = local;
-  return EDM_OK;
+  return rc;
 }
 
 int edm_pair_search_info(edm_bias_t* b, int* brick_dims, double* density_scale, long long* fallbacks) {
@@ -1283,6 +1336,7 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   EDM_REQUIRE(b->list_valid, "edm_pair_list_set has not been called");
   EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");
   EDM_TRY(ensure_device(b->device));
+  est_hill_count = edm_job_est(b, est_hill_count);
   const long nlisted = b->list_nlisted;
   const size_t bx = (size_t)nall * 3 * sizeof(double);
   EDM_TRY(b->io.reserve(bx));
@@ -1297,14 +1351,8 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   // forces are still on their way up; one pass adds the two, and the result travels down beside the hill round.
   //   main: x up | pair kernel -> dF          | f += dF | hill round
   //   copy:      | f up (after x, full rate)  |         | f down
-  if (!b->st_main) {
-    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_main, cudaStreamNonBlocking));
-    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_copy, cudaStreamNonBlocking));
-    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_up, cudaEventDisableTiming));
-    EDM_CUDA(cudaEventCreateWithFlags(&b->ev_f_final, cudaEventDisableTiming));
-  }
   EDM_TRY(b->io3.reserve(bx));
-  EDM_CUDA(cudaDeviceSynchronize());  // earlier work of this handle may sit on other streams
+  EDM_TRY(pair_host_streams(b));
   cudaStream_t sm = b->st_main, sc = b->st_copy;
   double* dF = b->io3.as<double>();
   if (type) EDM_CUDA(cudaMemcpyAsync(base, type, (size_t)nall * 4, cudaMemcpyHostToDevice, sm));
@@ -1343,11 +1391,12 @@ int edm_pair_step_listed(edm_bias_t* b, long nall, long nlocal, const double* x,
   EDM_CUDA(cudaStreamWaitEvent(sc, b->ev_f_final, 0));
   EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bx, cudaMemcpyDeviceToHost, sc));  // the round does not touch the forces
   if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, sm));
+  step_report_kernel<<<1, 1, 0, sm>>>(b->d_state, b->d_scalar, ncalls, reinterpret_cast<HostReport*>(b->d_pair_flags));
+  count_launches(1);
   EDM_CUDA(cudaStreamSynchronize(sm));
-  EDM_TRY(read_pair_result(b, result, ncalls));
-  if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  const int rc = pair_host_result(b, result, do_hills);
   EDM_CUDA(cudaStreamSynchronize(sc));
-  return EDM_OK;
+  return rc;
 }
 
 int edm_pair_step_list(edm_bias_t* b, long nall, long nlocal, const double* x, double* f, const int* type, int itype,

@@ -67,7 +67,7 @@ EDMBias::EDMBias(const std::string& input_filename)
       boltzmann_factor_(0), temperature_(-1.0), hill_prefactor_(0), bias_per_step_(0), hill_density_(-1),
       cum_bias_(0), total_volume_(0), expected_target_(0), b_outofbounds_(0), bias_dx_(NULL), bias_sigma_(NULL),
       min_(NULL), max_(NULL), b_periodic_boundary_(NULL), target_(NULL), initial_bias_(NULL), bias_(NULL), mask_(NULL),
-      dev_(NULL), cv_hist_(NULL), est_hill_count_(0), in_round_(0), steps_(0) {
+      dev_(NULL), comm_(NULL), comm_cap_(0), cv_hist_(NULL), est_hill_count_(0), in_round_(0), steps_(0) {
   read_input(input_filename);  // a failed parse leaves a half-initialised object, as in the reference
 }
 
@@ -211,6 +211,21 @@ void EDMBias::create_device_state() {
   edm_check(edm_bias_create(&dev_, bias_->device_grid(), cv_hist_->device_grid(),
                             target_ ? target_->device_grid() : NULL, &p),
             "edm_bias.cpp:subdivide");
+  if (comm_) edm_check(edm_bias_set_comm(dev_, comm_, comm_cap_), "edm_bias.cpp:set_comm");
+}
+
+void EDMBias::set_comm(edm_comm_t* comm, long block_capacity) {
+  comm_ = comm;
+  comm_cap_ = block_capacity;
+  mpi_rank_ = 0;
+  mpi_size_ = 0;  // the serial build's values (lib/edm_bias.cpp:36-37)
+  if (comm) {
+    int n = 1, r = 0;
+    edm_check(edm_comm_info(comm, &n, &r, NULL), "edm_bias.cpp:set_comm");
+    mpi_rank_ = r;
+    mpi_size_ = n;
+  }
+  if (dev_) edm_check(edm_bias_set_comm(dev_, comm_, comm_cap_), "edm_bias.cpp:set_comm");
 }
 
 void EDMBias::set_mask(const int* mask) { mask_ = mask; }

@@ -2,9 +2,11 @@
 // B200 HBM.  Same constructor (an edm input file), same call sequence (setup -> subdivide ->
 // update_forces / add_hills or the pre/add/post triple), same public data members; every
 // evaluation, selection, limiter and deposit step runs in the CUDA library behind
-// include/edm_b200.h.  There is no MPI here: one process drives one GPU, the grid is replicated
-// and hills are exchanged by the caller with an all-gather (edm_bias_hills_pack_dev /
-// edm_bias_hills_commit_dev), so mpi_rank_/mpi_size_ are kept only as data members.
+// include/edm_b200.h.  There is no MPI here: one process drives one GPU and the grid is replicated.
+// With a communicator attached (set_comm) post_add_hill / add_hills exchange the accepted hills of all
+// ranks through one NCCL all-gather inside the library — the stand-in for flush_buffers and
+// update_height's reduction (lib/edm_bias.cpp:565-583, 614-706, 922-931) — and mpi_rank_/mpi_size_
+// mirror the communicator.
 #ifndef EDM_B200_EDM_BIAS_H_
 #define EDM_B200_EDM_BIAS_H_
 
@@ -71,6 +73,12 @@ class EDMBias {
   double update_forces_add_hills(int nlocal, const double* const* positions, double** forces,
                                  const double* runiform, int apply_mask, int do_hills);
   edm_bias_t* device_bias() const { return dev_; }
+  // Multi-GPU: one EDMBias per process/GPU, grid replicated.  After set_comm every hill round
+  // (add_hills, post_add_hill, update_forces_add_hills, pair_step) gathers the accepted hills of all
+  // ranks and commits them in rank-major order on every replica; est_hill_count stays this rank's
+  // count, as in the reference's MPI build (lib/edm_bias.cpp:175-180).  May be called before or
+  // after subdivide; the communicator is borrowed.
+  void set_comm(edm_comm_t* comm, long block_capacity = 0);
   // after a hill round launched directly through the C ABI: HILLS lines, cum_bias_, host mirrors
   void after_device_round() {
     drain_hill_log();
@@ -114,6 +122,8 @@ class EDMBias {
   std::string clean_string(const std::string& input, int append_rank);
 
   edm_bias_t* dev_;
+  edm_comm_t* comm_;
+  long comm_cap_;
   Grid* cv_hist_;
   std::string hist_output_;
   int est_hill_count_;

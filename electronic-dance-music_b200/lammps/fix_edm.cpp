@@ -33,6 +33,9 @@ FixEDM::FixEDM(LAMMPS* lmp, int narg, char** arg)
   seed = atoi(arg[8]);
   if (stride < 0) error->all(FLERR, "Illegal stride given to EDM command");
   if (write_stride < 0) error->all(FLERR, "Illegal write bias stride given to EDM command");
+  int ndev = 0;
+  if (!getenv("EDM_B200_DEVICE") && edm_device_count(&ndev) == EDM_OK && ndev > 0)
+    EDM::set_default_device(me % ndev);  // one GPU per MPI rank of the node
   bias = new EDM::EDMBias(arg[4]);
   thermo_energy = 1;
   random = new RanMars(lmp, seed + me);
@@ -41,6 +44,7 @@ FixEDM::FixEDM(LAMMPS* lmp, int narg, char** arg)
 FixEDM::~FixEDM() {
   unpin_atom_arrays();
   delete bias;
+  if (comm_) edm_comm_destroy(comm_);
   delete random;
   free(random_numbers);
 }
@@ -62,11 +66,29 @@ void FixEDM::unpin_atom_arrays() {
   pinned_nmax_ = 0;
 }
 
+// The reference's MPI build broadcasts every rank's hills inside post_add_hill (lib/edm_bias.cpp:565-583,
+// 614-706).  Here each rank drives one GPU with a replica of the whole grid; the ranks agree on an NCCL
+// communicator once (the 128-byte id travels over LAMMPS' own MPI world) and EDMBias then all-gathers the
+// accepted hills inside every hill round, so all replicas deposit the same hills in the same order.
+void FixEDM::setup_exchange() {
+  int me = 0, nprocs = 1;
+  MPI_Comm_rank(world, &me);
+  MPI_Comm_size(world, &nprocs);
+  if (nprocs <= 1 || comm_) return;
+  unsigned char id[EDM_COMM_ID_BYTES];
+  memset(id, 0, sizeof(id));
+  if (me == 0) EDM::edm_check(edm_comm_unique_id(id), "fix_edm.cpp:setup_exchange");
+  MPI_Bcast(id, EDM_COMM_ID_BYTES, MPI_BYTE, 0, world);
+  EDM::edm_check(edm_comm_init_rank(&comm_, id, nprocs, me, EDM::default_device()), "fix_edm.cpp:setup_exchange");
+  bias->set_comm(comm_);
+}
+
 int FixEDM::setmask() { return POST_FORCE | THERMO_ENERGY | POST_FORCE_RESPA | MIN_POST_FORCE; }
 
 void FixEDM::init() {
   if (strcmp(update->integrate_style, "respa") == 0) nlevels_respa = ((Respa*)update->integrate)->nlevels;
   bias->setup(temperature, force->boltz);
+  setup_exchange();
   double skin[3] = {neighbor->skin, neighbor->skin, neighbor->skin};
   // the bias grid is replicated on every GPU: the "sub-box" handed over is the whole box
   bias->subdivide(domain->boxlo, domain->boxhi, domain->boxlo, domain->boxhi, domain->periodicity, skin);

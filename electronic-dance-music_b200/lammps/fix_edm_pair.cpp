@@ -40,6 +40,9 @@ FixEDMPair::FixEDMPair(LAMMPS* lmp, int narg, char** arg)
   jpair = atoi(arg[10]);
   if (!ipair || !jpair) error->all(FLERR, "Illegeal EDM command, invalid types");
   thermo_energy = 1;
+  int ndev = 0;
+  if (!getenv("EDM_B200_DEVICE") && edm_device_count(&ndev) == EDM_OK && ndev > 0)
+    EDM::set_default_device(me % ndev);  // one GPU per MPI rank of the node
   bias = new EDM::EDMBias(arg[4]);
   if (bias->dim_ != 1) error->all(FLERR, "Pairwise distance must be 1 dimension in EDM input file");
 }
@@ -47,6 +50,7 @@ FixEDMPair::FixEDMPair(LAMMPS* lmp, int narg, char** arg)
 FixEDMPair::~FixEDMPair() {
   unpin_atom_arrays();
   delete bias;
+  if (comm_) edm_comm_destroy(comm_);
 }
 
 void FixEDMPair::pin_atom_arrays() {
@@ -66,11 +70,29 @@ void FixEDMPair::unpin_atom_arrays() {
   pinned_nmax_ = 0;
 }
 
+// The reference's MPI build broadcasts every rank's hills inside post_add_hill (lib/edm_bias.cpp:565-583,
+// 614-706).  Here each rank drives one GPU with a replica of the whole grid; the ranks agree on an NCCL
+// communicator once (the 128-byte id travels over LAMMPS' own MPI world) and EDMBias then all-gathers the
+// accepted hills inside every hill round, so all replicas deposit the same hills in the same order.
+void FixEDMPair::setup_exchange() {
+  int me = 0, nprocs = 1;
+  MPI_Comm_rank(world, &me);
+  MPI_Comm_size(world, &nprocs);
+  if (nprocs <= 1 || comm_) return;
+  unsigned char id[EDM_COMM_ID_BYTES];
+  memset(id, 0, sizeof(id));
+  if (me == 0) EDM::edm_check(edm_comm_unique_id(id), "fix_edm_pair.cpp:setup_exchange");
+  MPI_Bcast(id, EDM_COMM_ID_BYTES, MPI_BYTE, 0, world);
+  EDM::edm_check(edm_comm_init_rank(&comm_, id, nprocs, me, EDM::default_device()), "fix_edm_pair.cpp:setup_exchange");
+  bias->set_comm(comm_);
+}
+
 int FixEDMPair::setmask() { return POST_FORCE | THERMO_ENERGY | POST_FORCE_RESPA | MIN_POST_FORCE; }
 
 void FixEDMPair::init() {
   if (strcmp(update->integrate_style, "respa") == 0) nlevels_respa = ((Respa*)update->integrate)->nlevels;
   bias->setup(temperature, force->boltz);
+  setup_exchange();
   // every rank biases the same whole-range 1-D grid [-skin, cut + 2 skin] (fix_edm_pair.cpp:96-104)
   double skin[3] = {neighbor->skin, 0, 0};
   double lo[3] = {0, 0, 0}, hi[3] = {force->pair->cutforce + neighbor->skin, 0, 0};

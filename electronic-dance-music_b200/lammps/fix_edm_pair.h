@@ -50,6 +50,9 @@ class FixEDMPair : public Fix {
   // LAMMPS reallocates them
   void pin_atom_arrays();
   void unpin_atom_arrays();
+  // more than one MPI rank: one GPU per rank, hills exchanged through the library's NCCL all-gather
+  void setup_exchange();
+  edm_comm_t* comm_ = 0;
   void* pinned_x_ = 0;
   void* pinned_f_ = 0;
   long pinned_nmax_ = 0;

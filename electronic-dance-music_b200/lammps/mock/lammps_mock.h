@@ -15,6 +15,9 @@
 typedef int MPI_Comm;
 inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = 0; return 0; }
 inline int MPI_Comm_size(MPI_Comm, int* s) { *s = 1; return 0; }
+typedef int MPI_Datatype;
+#define MPI_BYTE 1
+inline int MPI_Bcast(void*, int, MPI_Datatype, int, MPI_Comm) { return 0; }  // one rank: nothing to send
 #endif
 
 #define FLERR __FILE__, __LINE__

@@ -111,6 +111,7 @@ EXPORTS = {
     "edm_bias_set_profiling": (C.c_int, [vp, C.c_int]),
     "edm_bias_profile_ms": (C.c_int, [vp, c_dp]),
     "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
+    "edm_bias_profile_e2e_ms": (C.c_int, [vp, c_dp, c_dp, c_dp, c_dp]),
     "edm_host_pin": (C.c_int, [vp, C.c_size_t]),
     "edm_host_unpin": (C.c_int, [vp]),
     "edm_pair_list_set": (C.c_int, [vp, C.c_long, c_ip, C.POINTER(C.c_long), c_ip]),
@@ -119,6 +120,21 @@ EXPORTS = {
     "edm_pair_search_info": (C.c_int, [vp, c_ip, c_dp, C.POINTER(C.c_longlong)]),
     "edm_bias_round_info": (C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "edm_bias_hills_commit_dev": (C.c_int, [vp, vp, C.c_int, C.c_long, C.c_longlong, vp]),
+    "edm_comm_nccl_version": (C.c_int, [c_ip]),
+    "edm_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "edm_comm_init_rank": (C.c_int, [C.POINTER(vp), C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    "edm_comm_init_file": (C.c_int, [C.POINTER(vp), C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "edm_comm_init_all": (C.c_int, [C.POINTER(vp), C.c_int, c_ip]),
+    "edm_comm_from_nccl": (C.c_int, [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]),
+    "edm_comm_destroy": (C.c_int, [vp]),
+    "edm_comm_info": (C.c_int, [vp, c_ip, c_ip, c_ip]),
+    "edm_comm_group_start": (C.c_int, []),
+    "edm_comm_group_end": (C.c_int, []),
+    "edm_comm_allreduce_sum_dev": (C.c_int, [vp, vp, C.c_long, vp]),
+    "edm_bias_exchange_dev": (C.c_int, [vp, vp, C.c_long, C.c_longlong, vp]),
+    "edm_bias_exchange_all_dev": (C.c_int, [C.c_int, C.POINTER(vp), C.POINTER(vp), C.c_long, C.c_longlong, C.POINTER(vp)]),
+    "edm_bias_set_comm": (C.c_int, [vp, vp, C.c_long]),
+    "edm_bias_check": (C.c_int, [vp]),
 }
 
 _lib = None
@@ -179,6 +195,55 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(c_ip)
+
+
+class Comm:
+    """One rank's end of the hill exchange (an NCCL communicator owned by the library)."""
+
+    def __init__(self, handle):
+        self.L = lib()
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        check(lib().edm_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def init_rank(cls, uid, nranks, rank, device):
+        h = vp()
+        check(lib().edm_comm_init_rank(C.byref(h), uid, nranks, rank, device))
+        return cls(h)
+
+    @classmethod
+    def init_file(cls, path, nranks, rank, device, timeout_s=120.0):
+        h = vp()
+        check(lib().edm_comm_init_file(C.byref(h), path.encode(), nranks, rank, device, timeout_s))
+        return cls(h)
+
+    @classmethod
+    def init_all(cls, ndev, devices=None):
+        hs = (vp * ndev)()
+        d = _i(devices) if devices is not None else None
+        check(lib().edm_comm_init_all(hs, ndev, _ip(d) if d is not None else None))
+        return [cls(vp(h)) for h in hs]
+
+    def info(self):
+        n, r, d = C.c_int(0), C.c_int(0), C.c_int(0)
+        check(self.L.edm_comm_info(self.h, C.byref(n), C.byref(r), C.byref(d)))
+        return dict(nranks=n.value, rank=r.value, device=d.value)
+
+    def destroy(self):
+        if self.h:
+            self.L.edm_comm_destroy(self.h)
+            self.h = None
+
+
+def nccl_version():
+    v = C.c_int(0)
+    check(lib().edm_comm_nccl_version(C.byref(v)))
+    return v.value
 
 
 class Grid:
@@ -412,6 +477,12 @@ class Bias:
                                           _ip(t) if t is not None else None, itype, jtype, 1 if do_hills else 0, int(est),
                                           _dp(u) if u is not None else None, seed, step, C.byref(r)))
         return dict(energy=r.energy, n_pairs=r.n_pairs, n_calls=r.n_calls)
+
+    def set_comm(self, comm, cap=0):
+        check(self.L.edm_bias_set_comm(self.h, comm.h if comm is not None else None, cap))
+
+    def check(self):
+        check(self.L.edm_bias_check(self.h))
 
     def round_info(self):
         a, m, b = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)

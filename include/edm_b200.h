@@ -34,11 +34,13 @@ typedef enum edm_status {
   EDM_ERR_CUDA = -3,        /* a CUDA call failed */
   EDM_ERR_STATE = -4,       /* call order violated (add_hill before pre_add_hill, ...) */
   EDM_ERR_CAPACITY = -5,    /* accepted-hill or hill-log buffer exhausted */
-  EDM_ERR_BACKLOG_FULL = -6 /* overflow deque full: the reference aborts, lib/edm_bias.cpp:503-507 */
+  EDM_ERR_BACKLOG_FULL = -6,/* overflow deque full: the reference aborts, lib/edm_bias.cpp:503-507 */
+  EDM_ERR_COMM = -7         /* NCCL missing or a collective / rendezvous failed */
 } edm_status_t;
 
 typedef struct edm_grid edm_grid_t; /* Grid / GaussGrid resident in HBM */
 typedef struct edm_bias edm_bias_t; /* EDMBias step state resident in HBM */
+typedef struct edm_comm edm_comm_t; /* one rank's end of the hill exchange (an NCCL communicator) */
 
 #define EDM_BUFFER_SLOTS 2048 /* BIAS_BUFFER_SIZE, lib/edm_bias.h:15 */
 #define EDM_BUFFER_DBLS 8192  /* BIAS_BUFFER_DBLS, lib/edm_bias.h:16 */
@@ -262,6 +264,50 @@ int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, 
  * `event`, still reads the start-of-step bias. */
 int edm_bias_round_after(edm_bias_t* b, void* event);
 
+/* The exchange itself, inside the library (lib/edm_bias.cpp:565-583 post_add_hill -> flush_buffers
+ * :614-706 -> update_height :922-931, where the reference talks to MPI_COMM_WORLD directly).  NCCL is
+ * resolved at run time; without it these calls fail with EDM_ERR_COMM.
+ *
+ * Bootstrap, one of:
+ *   - one process per GPU: rank 0 calls edm_comm_unique_id and ships the 128 bytes to the others by any
+ *     means (MPI_Bcast in a LAMMPS build, a torch.distributed broadcast in bench.py), every rank then
+ *     calls edm_comm_init_rank; or edm_comm_init_file, which passes the id through a file all ranks see;
+ *   - one process driving several devices: edm_comm_init_all (ncclCommInitAll);
+ *   - an ncclComm_t the application already owns: edm_comm_from_nccl (borrowed, never destroyed here). */
+#define EDM_COMM_ID_BYTES 128
+int edm_comm_nccl_version(int* version);
+int edm_comm_unique_id(unsigned char* id /* [EDM_COMM_ID_BYTES] */);
+int edm_comm_init_rank(edm_comm_t** out, const unsigned char* id, int nranks, int rank, int device);
+int edm_comm_init_file(edm_comm_t** out, const char* path, int nranks, int rank, int device, double timeout_s);
+int edm_comm_init_all(edm_comm_t** out /* [ndev] */, int ndev, const int* devices);
+int edm_comm_from_nccl(edm_comm_t** out, void* nccl_comm, int nranks, int rank, int device);
+int edm_comm_destroy(edm_comm_t* comm);
+int edm_comm_info(const edm_comm_t* comm, int* nranks, int* rank, int* device);
+int edm_comm_group_start(void);
+int edm_comm_group_end(void);
+/* in-place sum over ranks of n doubles on the device (the bias energy, when a job-wide scalar is wanted;
+ * replaces the MPI_Allreduce of lib/edm_bias.cpp:925 for callers that need one) */
+int edm_comm_allreduce_sum_dev(edm_comm_t* comm, double* buf, long n, void* stream);
+/* pack -> ncclAllGather -> commit in one call, on `stream`, never synchronising the host: what
+ * post_add_hill does between the local add_hill calls and update_height.  est_total = the job-wide
+ * est_hill_count (the same on every rank); cap = records per rank in the block (the same on every rank;
+ * a rank that accepted more raises EDM_ERR_CAPACITY at the next edm_bias_state-style check instead of
+ * dropping hills). */
+int edm_bias_exchange_dev(edm_bias_t* b, edm_comm_t* comm, long cap, long long est_total, void* stream);
+/* the same for n replicas driven by one thread (communicators from edm_comm_init_all) */
+int edm_bias_exchange_all_dev(int n, edm_bias_t** b, edm_comm_t** comm, long cap, long long est_total,
+                              void** streams);
+/* Attaches a communicator: from now on every whole-round entry point of `b` (edm_bias_add_hills, the
+ * pre/add/post triple, edm_bias_step_coords, edm_pair_step_cells, edm_pair_step_listed, and their _dev
+ * forms) exchanges the accepted hills before the limiter, and its est_hill_count argument is this
+ * rank's share: the job-wide count is est * nranks (the reference divides hill_density and
+ * hill_prefactor by mpi_size_ instead, lib/edm_bias.cpp:175-180 — same acceptance, same heights).
+ * The select/pack/commit building blocks above are not affected.  comm = NULL detaches. */
+int edm_bias_set_comm(edm_bias_t* b, edm_comm_t* comm, long cap);
+/* Error state of the last round(s): EDM_ERR_BACKLOG_FULL, EDM_ERR_CAPACITY (accepted-hill buffer or
+ * exchange block exhausted) or EDM_OK.  Synchronises on a small device-to-host copy. */
+int edm_bias_check(edm_bias_t* b);
+
 /* ------------------------------------------------------------------ measurement hooks (bench.py) */
 
 /* Kernels launched by this library since load (all devices, this process). */
@@ -273,6 +319,11 @@ int edm_bias_profile_ms(edm_bias_t* b, double* pair_kernel_ms);
 /* The same interval split at the boundary between the block search and the block evaluation
  * kernel (both 0 when the generic search ran). */
 int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms);
+
+/* Device-side split of the last profiled edm_pair_step_cells call (host buffers): positions host->device,
+ * kernels (binning .. hill round), forces device->host (overlaps the hill round), and the span from the
+ * first copy to the later of the two ends.  Outputs may be NULL. */
+int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, double* f_down_ms, double* span_ms);
 
 /* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
  * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,

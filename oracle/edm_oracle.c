@@ -1082,12 +1082,165 @@ void orc_uniform_pair_fill(unsigned long long seed, unsigned long long step, lon
   }
 }
 
+/* ------------------------------------------------------------------ bench-size neighbour list
+
+ * The same half list as orc_build_half_list (all i<j with minimum-image distance < cutoff, rows ascending in
+ * i), built fast enough for the 10^6-atom benchmark configuration: atoms counting-sorted into cells, each
+ * row atom walks its 27 neighbour cells over contiguous cell-sorted coordinates.  The image shift is
+ * returned as three int8 codes per pair (shift = code * box) instead of three doubles.  Stand-in for the
+ * LAMMPS NeighList (half, newton off, every atom local), which is outside the reference tree. */
+typedef struct { long n, cap; int* pi; int* pj; signed char* img; } orc_half_list;
+
+void* orc_half_list_build(long natoms, const double* x, const double* box, double cutoff) {
+  int nc[3];
+  double cs[3];
+  for (int d = 0; d < 3; d++) {
+    nc[d] = (int)floor(box[d] / cutoff);
+    if (nc[d] < 3) return NULL; /* small boxes: use orc_build_half_list */
+    cs[d] = box[d] / nc[d];
+  }
+  const long ncell = (long)nc[0] * nc[1] * nc[2];
+  long* start = (long*)calloc((size_t)ncell + 1, sizeof(long));
+  int* cell_of = (int*)malloc(sizeof(int) * (size_t)natoms);
+  for (long a = 0; a < natoms; a++) {
+    int c[3];
+    for (int d = 0; d < 3; d++) {
+      c[d] = (int)floor(x[3 * a + d] / cs[d]);
+      if (c[d] < 0) c[d] = 0;
+      if (c[d] >= nc[d]) c[d] = nc[d] - 1;
+    }
+    cell_of[a] = (int)(((long)c[2] * nc[1] + c[1]) * nc[0] + c[0]);
+    start[cell_of[a] + 1]++;
+  }
+  for (long c = 0; c < ncell; c++) start[c + 1] += start[c];
+  long* fill = (long*)malloc(sizeof(long) * (size_t)ncell);
+  memcpy(fill, start, sizeof(long) * (size_t)ncell);
+  double* xs = (double*)malloc(sizeof(double) * 3 * (size_t)natoms);
+  int* idx = (int*)malloc(sizeof(int) * (size_t)natoms);
+  for (long a = 0; a < natoms; a++) { /* ascending a: slots inside a cell are in ascending atom index */
+    const long s = fill[cell_of[a]]++;
+    idx[s] = (int)a;
+    xs[3 * s + 0] = x[3 * a + 0];
+    xs[3 * s + 1] = x[3 * a + 1];
+    xs[3 * s + 2] = x[3 * a + 2];
+  }
+  orc_half_list* hl = (orc_half_list*)calloc(1, sizeof(orc_half_list));
+  hl->cap = 32 * natoms + 1024;
+  hl->pi = (int*)malloc(sizeof(int) * (size_t)hl->cap);
+  hl->pj = (int*)malloc(sizeof(int) * (size_t)hl->cap);
+  hl->img = (signed char*)malloc(3 * (size_t)hl->cap);
+  const double rc2 = cutoff * cutoff;
+  for (long a = 0; a < natoms; a++) {
+    const int ca = cell_of[a];
+    const int c0 = ca % nc[0], c1 = (ca / nc[0]) % nc[1], c2 = ca / (nc[0] * nc[1]);
+    const double ax = x[3 * a + 0], ay = x[3 * a + 1], az = x[3 * a + 2];
+    for (int dz = -1; dz <= 1; dz++)
+      for (int dy = -1; dy <= 1; dy++)
+        for (int dxx = -1; dxx <= 1; dxx++) {
+          int q0 = c0 + dxx, q1 = c1 + dy, q2 = c2 + dz;
+          signed char i0 = 0, i1 = 0, i2 = 0; /* x[a] - x[b] - img*box is the minimum image */
+          if (q0 < 0) { q0 += nc[0]; i0 = -1; } else if (q0 >= nc[0]) { q0 -= nc[0]; i0 = 1; }
+          if (q1 < 0) { q1 += nc[1]; i1 = -1; } else if (q1 >= nc[1]) { q1 -= nc[1]; i1 = 1; }
+          if (q2 < 0) { q2 += nc[2]; i2 = -1; } else if (q2 >= nc[2]) { q2 -= nc[2]; i2 = 1; }
+          /* a partner reached across the upper face sits at x[b] + box: x[a] - x[b] - (+box) is the separation */
+          const double s0 = i0 * box[0], s1 = i1 * box[1], s2 = i2 * box[2];
+          const long q = ((long)q2 * nc[1] + q1) * nc[0] + q0;
+          for (long sidx = start[q]; sidx < start[q + 1]; sidx++) {
+            const int bb = idx[sidx];
+            if (bb <= a) continue;
+            const double d0 = (ax - xs[3 * sidx + 0]) - s0, d1 = (ay - xs[3 * sidx + 1]) - s1;
+            const double d2v = (az - xs[3 * sidx + 2]) - s2;
+            const double d2 = d0 * d0 + d1 * d1 + d2v * d2v;
+            if (d2 < rc2) {
+              if (hl->n == hl->cap) {
+                hl->cap *= 2;
+                hl->pi = (int*)realloc(hl->pi, sizeof(int) * (size_t)hl->cap);
+                hl->pj = (int*)realloc(hl->pj, sizeof(int) * (size_t)hl->cap);
+                hl->img = (signed char*)realloc(hl->img, 3 * (size_t)hl->cap);
+              }
+              hl->pi[hl->n] = (int)a;
+              hl->pj[hl->n] = bb;
+              hl->img[3 * hl->n + 0] = i0;
+              hl->img[3 * hl->n + 1] = i1;
+              hl->img[3 * hl->n + 2] = i2;
+              hl->n++;
+            }
+          }
+        }
+  }
+  free(start); free(cell_of); free(fill); free(xs); free(idx);
+  return hl;
+}
+long orc_half_list_size(void* p) { return p ? ((orc_half_list*)p)->n : -1; }
+void orc_half_list_copy(void* p, int* pi, int* pj, signed char* img) {
+  orc_half_list* hl = (orc_half_list*)p;
+  memcpy(pi, hl->pi, sizeof(int) * (size_t)hl->n);
+  memcpy(pj, hl->pj, sizeof(int) * (size_t)hl->n);
+  memcpy(img, hl->img, 3 * (size_t)hl->n);
+}
+void orc_half_list_free(void* p) {
+  orc_half_list* hl = (orc_half_list*)p;
+  if (!hl) return;
+  free(hl->pi); free(hl->pj); free(hl->img); free(hl);
+}
+
 /* ------------------------------------------------------------------ CPU-baseline timers */
 
 static double now_s(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+/* FixEDMPair::post_force's pair loop, lammps/fix_edm_pair.cpp:173-247, in the REFERENCE'S OWN order — per pair:
+ * r = sqrt(del^2), rinv, update_force at r, +-force scatter into f[i] and f[j] (both local), and on a hill step
+ * two add_hill calls (interleaved with the evaluations, T24) between pre_add_hill(last_calls) and post_add_hill.
+ * Timed here so that marshalling stays outside the measured region; the uniforms come from a counter hash in
+ * place of LAMMPS' RanMars (one draw per add_hill, as there).  Returns seconds. */
+double orc_time_fix_pair(void* p, long npairs, const int* pi, const int* pj, const signed char* img,
+                         const double* box, const double* x, double* f, int do_hills, int est,
+                         unsigned long long seed, unsigned long long step, double* energy_out, long* ncalls_out) {
+  orc_bias* b = (orc_bias*)p;
+  const uint64_t key = orc_mix64(seed ^ orc_mix64(step + 0x9E3779B97F4A7C15ULL));
+  uint64_t ctr = 0;
+  double energy = 0;
+  long ncalls = 0;
+  const double t0 = now_s();
+  if (do_hills) orc_bias_pre_add_hill(b, est);
+  for (long k = 0; k < npairs; k++) {
+    const int i = pi[k], j = pj[k];
+    double delx = x[3 * i + 0] - x[3 * j + 0] - img[3 * k + 0] * box[0];
+    double dely = x[3 * i + 1] - x[3 * j + 1] - img[3 * k + 1] * box[1];
+    double delz = x[3 * i + 2] - x[3 * j + 2] - img[3 * k + 2] * box[2];
+    double r = sqrt(delx * delx + dely * dely + delz * delz);
+    const double rinv = 1.0 / r;
+    delx *= rinv;
+    dely *= rinv;
+    delz *= rinv;
+    double der[3] = {0, 0, 0};
+    double edm_force = 0;
+    if (!b->b_outofbounds) {
+      energy += gauss_get_value_deriv(b->bias, &r, der);
+      edm_force -= der[0];
+    }
+    f[3 * i + 0] += delx * edm_force;
+    f[3 * i + 1] += dely * edm_force;
+    f[3 * i + 2] += delz * edm_force;
+    f[3 * j + 0] -= delx * edm_force;
+    f[3 * j + 1] -= dely * edm_force;
+    f[3 * j + 2] -= delz * edm_force;
+    if (do_hills) {
+      for (int w = 0; w < 2; w++) {
+        const uint64_t bits = orc_mix64(key + (ctr++) * 0x9E3779B97F4A7C15ULL);
+        bias_add_hill(b, &r, (double)(bits >> 11) * (1.0 / 9007199254740992.0));
+        ncalls++;
+      }
+    }
+  }
+  if (do_hills) orc_bias_post_add_hill(b);
+  const double t1 = now_s();
+  if (energy_out) *energy_out = energy;
+  if (ncalls_out) *ncalls_out = ncalls;
+  return t1 - t0;
 }
 double orc_time_pair_eval(void* p, long npairs, const double* r, int repeats) {
   orc_bias* b = (orc_bias*)p;

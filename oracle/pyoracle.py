@@ -109,6 +109,8 @@ class _Lib:
             "pair_step": (d, [vp, l, c_ip, c_ip, c_dp, c_dp, c_dp, i, i, c_dp, c_dp]),
             "time_pair_eval": (d, [vp, l, c_dp, i]),
             "time_add_values": (d, [vp, l, c_dp, c_dp]),
+            "time_fix_pair": (d, [vp, l, c_ip, c_ip, C.POINTER(C.c_byte), c_dp, c_dp, c_dp, i, i, C.c_ulonglong,
+                                  C.c_ulonglong, c_dp, C.POINTER(l)]),
         }
         if kind == "port":
             sig.update({
@@ -119,6 +121,10 @@ class _Lib:
                 "bias_log_clear": (None, [vp]),
                 "bias_log_enable": (None, [vp, i]),
                 "build_half_list": (l, [l, c_dp, c_dp, d, l, c_ip, c_ip, c_dp]),
+                "half_list_build": (vp, [l, c_dp, c_dp, d]),
+                "half_list_size": (l, [vp]),
+                "half_list_copy": (None, [vp, c_ip, c_ip, C.POINTER(C.c_byte)]),
+                "half_list_free": (None, [vp]),
                 "uniform": (d, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]),
                 "uniform_fill": (None, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, l, c_dp]),
                 "uniform_pair": (d, [C.c_ulonglong, C.c_ulonglong, C.c_ulonglong, i]),
@@ -413,6 +419,17 @@ class Bias:
         e = self.L.pair_step(self.h, npairs, _ip(pi), _ip(pj), _dp(x), _dp(f), sh, int(do_hills), int(est), un, _dp(r))
         return float(e), r
 
+    def time_fix_pair(self, pi, pj, img, box, x, f, do_hills, est, seed=0, step=0):
+        """The reference's own pair loop (lammps/fix_edm_pair.cpp:173-247, evaluation and hill proposals interleaved)
+        over pairs (pi, pj, img) from build_half_list_fast; returns (seconds, energy, hill proposals made)."""
+        assert pi.dtype == np.int32 and pj.dtype == np.int32 and img.dtype == np.int8
+        assert x.flags.c_contiguous and f.flags.c_contiguous
+        e = C.c_double(0)
+        nc = C.c_long(0)
+        t = self.L.time_fix_pair(self.h, pi.size, _ip(pi), _ip(pj), img.ctypes.data_as(C.POINTER(C.c_byte)), _dp(_d(box)),
+                                 _dp(x), _dp(f), int(do_hills), int(est), seed, step, C.byref(e), C.byref(nc))
+        return float(t), e.value, nc.value
+
     def time_pair_eval(self, r, repeats=1):
         r = _d(r)
         return float(self.L.time_pair_eval(self.h, r.size, _dp(r), int(repeats)))
@@ -459,6 +476,22 @@ def build_half_list(x, box, cutoff):
     sh = np.zeros((max(cnt, 1), 3))
     L.build_half_list(n, _dp(x), _dp(box), float(cutoff), cnt, _ip(pi), _ip(pj), _dp(sh))
     return pi[:cnt], pj[:cnt], sh[:cnt]
+
+
+def build_half_list_fast(x, box, cutoff):
+    """The same pair set as build_half_list for boxes of >= 3 cutoffs per side, fast enough for 10^6 atoms;
+    returns (pi, pj, img) with the image shift as int8 codes: separation = x[i] - x[j] - img * box."""
+    L = load("port")
+    x = _d(x).reshape(-1, 3)
+    h = L.half_list_build(x.shape[0], _dp(x), _dp(_d(box)), float(cutoff))
+    if not h:
+        raise ValueError("box smaller than 3 cutoffs per side")
+    n = L.half_list_size(h)
+    pi, pj = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    img = np.zeros((n, 3), np.int8)
+    L.half_list_copy(h, _ip(pi), _ip(pj), img.ctypes.data_as(C.POINTER(C.c_byte)))
+    L.half_list_free(h)
+    return pi, pj, img
 
 
 def uniform_fill(seed, step, first, n):

@@ -396,6 +396,57 @@ double ref_time_pair_eval(void* p, long npairs, const double* r, int repeats) {
   if (sink == 1.2345e-300) std::cerr << "";
   return std::chrono::duration<double>(t1 - t0).count();
 }
+// FixEDMPair::post_force's pair loop, lammps/fix_edm_pair.cpp:173-247, as a driver over the UNMODIFIED reference
+// library in the reference's own order: per pair r = sqrt(del^2), update_force(&r), +-scatter into f[i], f[j] (both
+// local), and on a hill step two add_hill calls, between pre_add_hill(last_calls) and post_add_hill.  The uniforms
+// come from a counter hash in place of LAMMPS' RanMars (one draw per add_hill, as there).  Returns seconds.
+static inline unsigned long long shim_mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+double ref_time_fix_pair(void* p, long npairs, const int* pi, const int* pj, const signed char* img,
+                         const double* box, const double* x, double* f, int do_hills, int est,
+                         unsigned long long seed, unsigned long long step, double* energy_out, long* ncalls_out) {
+  EDMBias* b = ((BiasHandle*)p)->b;
+  const unsigned long long key = shim_mix64(seed ^ shim_mix64(step + 0x9E3779B97F4A7C15ULL));
+  unsigned long long ctr = 0;
+  double edm_energy = 0;
+  long ncalls = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  if (do_hills) b->pre_add_hill(est);
+  for (long k = 0; k < npairs; k++) {
+    const int i = pi[k], j = pj[k];
+    double delx = x[3 * i + 0] - x[3 * j + 0] - img[3 * k + 0] * box[0];
+    double dely = x[3 * i + 1] - x[3 * j + 1] - img[3 * k + 1] * box[1];
+    double delz = x[3 * i + 2] - x[3 * j + 2] - img[3 * k + 2] * box[2];
+    double r = sqrt(delx * delx + dely * dely + delz * delz);
+    double rinv = 1.0 / r;
+    delx *= rinv;
+    dely *= rinv;
+    delz *= rinv;
+    double edm_force[1] = {0};
+    edm_energy += b->update_force(&r, edm_force);
+    f[3 * i + 0] += delx * edm_force[0];
+    f[3 * i + 1] += dely * edm_force[0];
+    f[3 * i + 2] += delz * edm_force[0];
+    f[3 * j + 0] -= delx * edm_force[0];
+    f[3 * j + 1] -= dely * edm_force[0];
+    f[3 * j + 2] -= delz * edm_force[0];
+    if (do_hills) {
+      for (int w = 0; w < 2; w++) {
+        const unsigned long long bits = shim_mix64(key + (ctr++) * 0x9E3779B97F4A7C15ULL);
+        b->add_hill(&r, (double)(bits >> 11) * (1.0 / 9007199254740992.0));
+        ncalls++;
+      }
+    }
+  }
+  if (do_hills) b->post_add_hill();
+  auto t1 = std::chrono::steady_clock::now();
+  if (energy_out) *energy_out = edm_energy;
+  if (ncalls_out) *ncalls_out = ncalls;
+  return std::chrono::duration<double>(t1 - t0).count();
+}
 double ref_time_add_values(void* p, long n, const double* x, const double* h) {
   GaussHandle* g = (GaussHandle*)p;
   double sink = 0;

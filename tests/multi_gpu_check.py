@@ -1,5 +1,7 @@
 """Run under torchrun on N GPUs: every rank evaluates its own atoms' pairs, selects hills locally,
-packs them on the device, all-gathers the blocks over NCCL and commits the concatenation.  Checks:
+and calls the library's own exchange (edm_bias_exchange_dev: pack -> ncclAllGather -> commit, NCCL
+called from C++ on a communicator bootstrapped with edm_comm_init_rank; torch.distributed only ships
+the 128-byte id and compares the replicas afterwards).  Checks:
 replicas bit-identical across ranks; rank 0 equal (1e-10) to a single-rank oracle that sees the
 rank-major concatenation of all ranks' pairs."""
 import ctypes as C
@@ -26,6 +28,10 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    uid = [edm.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, 0)
+    comm = edm.Comm.init_rank(uid[0], world, rank, local)
+    assert comm.info() == dict(nranks=world, rank=rank, device=local)
     d = os.path.join(tmp, "r%d" % rank)
     os.makedirs(d, exist_ok=True)
     f = os.path.join(d, "c.edm")
@@ -49,10 +55,9 @@ def main():
         xd = torch.from_numpy(x).cuda()
         edm.check(L.edm_pair_select_cells_dev(b.h, n, xd.data_ptr(), fdev.data_ptr(), None, 0, 0, boxp, rc, est_total,
                                               seed + rank, step, edev.data_ptr(), st))
-        edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, st))
-        dist.all_gather_into_tensor(gathered, block)
-        edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, est_total, st))
+        edm.check(L.edm_bias_exchange_dev(b.h, comm.h, cap, est_total, st))
     torch.cuda.synchronize()
+    b.check()
     v, dv = b.bias_grid.get_arrays()
     # replicas identical across ranks
     mine = torch.from_numpy(np.concatenate([v, dv.ravel()])).cuda()
@@ -90,7 +95,8 @@ def main():
         assert len(ld) == len(lo) and np.array_equal(ld["type"], lo["type"]) and np.array_equal(ld["pos"], lo["pos"])
         assert b.backlog()[:2] == bo.backlog()[:2]
         print("MULTI_GPU_CHECK_OK world=%d events=%d" % (world, len(ld)))
-    coord_check(tmp, rank, world, local)
+    coord_check(tmp, rank, world, local, comm)
+    comm.destroy()
     dist.destroy_process_group()
 
 
@@ -99,7 +105,7 @@ COORD_TEXT = ("tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0
               "bias_sigma 0.0625 0.0625\n")
 
 
-def coord_check(tmp, rank, world, local):
+def coord_check(tmp, rank, world, local, comm):
     """fix edm sharded: every rank owns a block of atoms (2-D coordinate CV, local well-tempering), selects
     with the job-wide est_hill_count and atom-index counters, and commits the all-gathered hills; checked
     against a single-rank oracle run on the rank-major concatenation."""
@@ -138,10 +144,8 @@ def coord_check(tmp, rank, world, local):
             sst = side.cuda_stream
             edm.check(L.edm_bias_select_dev(b.h, n, xd.data_ptr(), 2, ud.data_ptr(), None, -1, n * world, 0, step,
                                             rank * n, sst))
-            edm.check(L.edm_bias_hills_pack_dev(b.h, block.data_ptr(), cap, sst))
-            dist.all_gather_into_tensor(gathered, block)
             edm.check(L.edm_bias_round_after(b.h, ev_k1.cuda_event))
-            edm.check(L.edm_bias_hills_commit_dev(b.h, gathered.data_ptr(), world, cap, n * world, sst))
+            edm.check(L.edm_bias_exchange_dev(b.h, comm.h, cap, n * world, sst))
             ev_join.record(side)
         main.wait_event(ev_join)
         es.append(float(edev.item()))

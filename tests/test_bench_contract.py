@@ -36,6 +36,11 @@ def test_reference_arm_prints_one_line_with_the_agreed_keys(reference_line):
     assert d["metric"] == "CV bias+force evals/sec" and d["unit"] == "evals/s" and d["dtype"] == "f64"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["config"]["workload"] == "c2_pair_rdf"
+    # the same config object as the GPU arm prints (bench.c2_config): the driver's same_config check
+    for k in ("atoms_per_gpu", "number_density", "cutoff", "pairs_per_gpu_per_step", "grid_points", "hill_density",
+              "step", "parallelism"):
+        assert k in d["config"], k
+    assert abs(d["config"]["pairs_per_gpu_per_step"] - 26179939) < 30000   # N (4/3) pi rc^3 rho / 2
     assert d["value"] > 1e6
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]

@@ -112,3 +112,15 @@ def test_c_example_reproduces_the_notebook_vector(edm, tmp_path):
     r = subprocess.run([str(_build_c_example(tmp_path))], capture_output=True, text=True, timeout=120)
     print(r.stdout, r.stderr)
     assert r.returncode == 0 and "matches the reference's notebook vector" in r.stdout
+
+
+def test_nccl_is_resolved_at_run_time_and_the_exchange_needs_a_gpu(edm):
+    """The hill exchange lives in the library (edm_comm_*, edm_bias_exchange_dev): NCCL is found by dlopen, so
+    the library itself loads without it; without a GPU a communicator cannot be created (no CPU fallback)."""
+    assert "libnccl" not in subprocess.run(["ldd", edm.LIB_PATH], capture_output=True, text=True).stdout
+    assert edm.nccl_version() >= 21800
+    uid = edm.Comm.unique_id()
+    assert len(uid) == 128 and uid != bytes(128)
+    if edm.device_count() == 0:
+        with pytest.raises(edm.EdmError, match="no CUDA device"):
+            edm.Comm.init_rank(uid, 1, 0, 0)

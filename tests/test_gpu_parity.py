@@ -2,11 +2,16 @@
 seeded inputs.  Bars (BASELINE.json north_star): hill selection and buffering decisions bit-exact;
 energies, forces and grid values within 1e-10 relative in fp64.
 
-"Relative" is taken per element against max(|ref|, FLOOR * max|ref|) with FLOOR = 1e-2: interpolated
-derivatives and summed pair forces are differences of O(V/dx) terms and pass through zero, where the
-reference's own rounding noise (a few ulp(V)/dx, about 1e-13 of the array's scale for dx = 0.00025)
-exceeds 1e-10 of the element.  So every element larger than 1 % of the array's largest magnitude is
-held to 1e-10 of its own size, and nothing is ever looser than 1e-12 of the array's scale.
+Two forms of "1e-10 relative":
+  * strict (assert_close(..., strict=True)): every element against ITS OWN magnitude, |dev - ref| <= 1e-10 |ref|.
+    Used for everything that is a sum of same-sign terms or a single product: grid values, bias_added, hill
+    heights, backlog contents, cum_bias.
+  * floored: per element against max(|ref|, FLOOR * max|ref|) with FLOOR = 1e-2, for interpolated derivatives,
+    grid derivatives and summed forces only: those are differences of O(V/dx) terms that pass through zero,
+    where the reference's own rounding noise (a few ulp(V)/dx, about 1e-13 of the array's scale for
+    dx = 0.00025) exceeds 1e-10 of the element.  Nothing is ever looser than 1e-12 of the array's scale.
+Either way the worst strict error is recorded (WORST_STRICT) and printed at the end of the module, so the
+slack the floored form grants is a measured number.
 """
 import os
 import zlib
@@ -20,15 +25,40 @@ RTOL = 1e-10
 FLOOR = 1e-2
 
 
-def assert_close(dev, refv, what, rtol=RTOL):
+WORST_STRICT = {}   # what -> worst element-wise |dev - ref| / |ref| seen in this session
+
+
+def strict_error(dev, refv):
+    """Worst |dev - ref| / |ref| over the elements with ref != 0 (where ref == 0 the device must be 0 too)."""
+    nz = refv != 0
+    worst = float((np.abs(dev[nz] - refv[nz]) / np.abs(refv[nz])).max()) if nz.any() else 0.0
+    return worst, bool(np.all(dev[~nz] == 0.0))
+
+
+def assert_close(dev, refv, what, rtol=RTOL, strict=False):
     dev, refv = np.asarray(dev, float), np.asarray(refv, float)
     assert dev.shape == refv.shape, what
+    worst_strict, zeros_ok = strict_error(dev, refv)
+    WORST_STRICT[what] = max(WORST_STRICT.get(what, 0.0), worst_strict)
+    if strict:
+        assert zeros_ok, "%s: the reference is exactly 0 somewhere the device is not" % what
+        assert worst_strict <= rtol, "%s: worst element-wise relative error %.3e (tolerance %.1e)" % (what, worst_strict, rtol)
+        return
     scale = np.abs(refv).max() if refv.size else 0.0
     denom = np.maximum(np.abs(refv), FLOOR * scale)
     denom[denom == 0] = 1.0
     err = np.abs(dev - refv) / denom
     worst = err.max() if err.size else 0.0
     assert worst <= rtol, "%s: worst relative error %.3e (tolerance %.1e)" % (what, worst, rtol)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def report_worst_strict_errors():
+    yield
+    if WORST_STRICT:
+        print("\nworst element-wise relative error per quantity (strict, |dev-ref|/|ref|):")
+        for k in sorted(WORST_STRICT):
+            print("  %-40s %.3e" % (k, WORST_STRICT[k]))
 
 
 @pytest.fixture(scope="module")
@@ -59,6 +89,11 @@ GRID_CASES = {
     "3d_inner_mcgdp": (3, [-10.0] * 3, [10.0] * 3, [0.9, 1.1, 1.4], [1, 1, 1], [3.0, 3.0, 3.0],
                        ([-5.0] * 3, [5.0] * 3, [0, 0, 0])),
 }
+
+
+# grid values are sums of same-sign hill terms: strict everywhere.  (A case would be listed here as False only
+# with a measured reason; none is.)
+STRICT_GRID = {}
 
 
 def make_pair(edm, port, case):
@@ -105,11 +140,11 @@ def test_deposit_and_eval_parity(edm, port, case):
     ba_d = gd.add_values(centres, heights)
     ba_o = go.add_values(centres, heights)
     assert np.array_equal(ba_d == 0.0, ba_o == 0.0), "rejected-hill decisions differ"
-    assert_close(ba_d, ba_o, "bias_added")
+    assert_close(ba_d, ba_o, "bias_added", strict=True)
     vd, dd = gd.get_arrays()
     vo, do = go.get_arrays()
     assert np.array_equal(vd == 0.0, vo == 0.0), "support / boundary membership differs"
-    assert_close(vd, vo, "grid values")
+    assert_close(vd, vo, "grid values", strict=STRICT_GRID.get(case, True))
     assert_close(dd, do, "grid derivatives")
     # evaluation on the oracle's grid (bit-identical tables), incl. points outside grid and boundary
     gd.set_arrays(vo, do)
@@ -192,6 +227,10 @@ BIAS_CASES = {
         text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.5\nbias_per_step 1000\n"
              "hill_density 120\ndimension 1\nbox_low 0\nbox_high 10\nbias_spacing 0.01\nbias_sigma 0.1",
         T=300.0, kB=0.0019872, sub=([0.0], [10.0]), periodic=[1], skin=[0.0], n=5000, lo=0.0, hi=10.0, steps=5),
+    "1d_local_tempering_window_wider_than_grid": dict(  # periodic window revisits its own points: rounds run in order
+        text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.5\nbias_per_step 1000\n"
+             "hill_density 40\ndimension 1\nbox_low 2\nbox_high 10\nbias_spacing 1.0\nbias_sigma 1.0",
+        T=300.0, kB=0.0019872, sub=([2.0], [10.0]), periodic=[1], skin=[0.0], n=2000, lo=2.0, hi=10.0, steps=4),
     "2d_local_well_tempering": dict(
         text="tempering 1\nglobal_tempering -1\nbias_factor 5\nhill_prefactor 0.02\nbias_per_step 1000\n"
              "hill_density 100\ndimension 2\nbox_low 0 0\nbox_high 8 8\nbias_spacing 0.0625 0.0625\n"
@@ -333,9 +372,15 @@ def compare_bias(bd, bo):
     for k in ("steps", "type", "hills_added"):
         assert np.array_equal(ld[k], lo[k]), "hill log field %s differs" % k
     assert np.array_equal(ld["pos"], lo["pos"]), "hill centres differ"
-    assert_close(ld["height"], lo["height"], "hill heights")
-    assert_close(ld["bias_added"], lo["bias_added"], "bias_added")
-    assert_close(ld["cum_over_vol"], lo["cum_over_vol"], "cum_bias/volume")
+    # full hills (h, b): a product / a sum of same-sign terms -> strict.  Undo hills (u, v) carry the height
+    # fmax(bias_per_step - running sum, -h) (lib/edm_bias.cpp:479, 338), a difference of two nearly equal numbers:
+    # those, and the backlog slots that store such remainders, keep the floored form.
+    full = np.isin(lo["type"], [ord("h"), ord("b")])
+    assert_close(ld["height"][full], lo["height"][full], "hill heights (h, b)", strict=True)
+    assert_close(ld["bias_added"][full], lo["bias_added"][full], "bias_added (h, b)", strict=True)
+    assert_close(ld["height"][~full], lo["height"][~full], "undo heights (u, v)")
+    assert_close(ld["bias_added"][~full], lo["bias_added"][~full], "undo bias_added (u, v)")
+    assert_close(ld["cum_over_vol"], lo["cum_over_vol"], "cum_bias/volume", strict=True)
     sd, po = bd.state(), bo.params()
     assert sd["steps"] == int(po["steps"])
     assert abs(sd["cum_bias"] - po["cum_bias"]) <= RTOL * abs(po["cum_bias"])
@@ -345,7 +390,7 @@ def compare_bias(bd, bo):
     assert_close(buf_d, buf_o, "backlog contents")
     vd, dd = bd.bias_grid.get_arrays()
     vo, do = bo.gauss.get_arrays()
-    assert_close(vd, vo, "bias grid")
+    assert_close(vd, vo, "bias grid", strict=True)
     assert_close(dd, do, "bias grid derivative")
     hd = bd.hist_grid.get_arrays()[0]
     ho = bo.hist.get_arrays()[0]
@@ -363,6 +408,8 @@ def test_bias_round_parity(edm, port, tmp_path, name):
     assert info["parallel"] + info["split"] + info["in_order"] == BIAS_CASES[name]["steps"]
     if name == "2d_local_tempering_too_entangled":
         assert info["in_order"] == 2, info
+    if name == "1d_local_tempering_window_wider_than_grid":
+        assert info["in_order"] == BIAS_CASES[name]["steps"], info
     if name in PARALLEL_ROUND_CASES:   # the all-hills-at-once round really ran (and fell back where it must)
         assert info["parallel"] + info["split"] >= PARALLEL_ROUND_CASES[name], info
 

@@ -1,10 +1,18 @@
 """Condenses an .ncu-rep (one kernel launch, --set full) into the text summary kept under profiles/.
 
     python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x_ncu_selected.txt
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep --roofline WORKLOAD KERNEL CSRC_HASH SOURCE.txt
+        additionally records the kernel's DRAM traffic and busiest resource in profiles/ncu_roofline.json under
+        the hash of the csrc/ tree the capture was taken on (bench.py reports them only while that hash matches
+        the build it is measuring; the hash is printed by `python bench.py --csrc-hash` ON THE SNAPSHOT that ran).
 """
 import csv
+import json
+import os
 import subprocess
 import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WANT = [
     "Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
@@ -27,18 +35,56 @@ WANT = [
 ]
 
 
+def to_bytes(value, unit):
+    v = float(value.replace(",", ""))
+    u = unit.strip().lower()
+    return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+
+
+def record_roofline(hdr, units, vals, workload, kernel, csrc, source):
+    get = lambda k: (vals[hdr.index(k)], units[hdr.index(k)]) if k in hdr else (None, None)
+    rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
+    pct = {
+        "lsu": get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")[0],
+        "issue": get("smsp__issue_active.avg.pct_of_peak_sustained_active")[0],
+        "fp64": get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")[0],
+        "dram": get("dram__throughput.avg.pct_of_peak_sustained_elapsed")[0],
+        "l2": get("lts__throughput.avg.pct_of_peak_sustained_elapsed")[0],
+    }
+    pct = {k: float(v.replace(",", "")) for k, v in pct.items() if v not in (None, "")}
+    names = {"lsu": "L1/shared-memory data pipe (l1tex LSU wavefronts)", "issue": "warp issue slots",
+             "fp64": "fp64 pipe", "dram": "HBM (dram throughput)", "l2": "L2 (lts throughput)"}
+    top = max(pct, key=pct.get)
+    path = os.path.join(ROOT, "profiles", "ncu_roofline.json")
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data.setdefault(workload, {})[kernel] = {
+        "csrc_hash": csrc, "source": source,
+        "dram_bytes_per_launch": int(to_bytes(*rd) + to_bytes(*wr)),
+        "dram_bytes_read": int(to_bytes(*rd)), "dram_bytes_write": int(to_bytes(*wr)),
+        "gpu_time_us": float(get("gpu__time_duration.sum")[0].replace(",", "")),
+        "binding": {"bound": {"dram": "hbm"}.get(top, top), "name": names[top], "pct_of_peak": pct[top],
+                    "all_pct": pct, "source": source},
+    }
+    json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+
+
 def main():
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
+    roof = sys.argv[sys.argv.index("--roofline") + 1:] if "--roofline" in sys.argv else None
     print("# %s  (ncu --set full --clock-control none, one launch; values as ncu reports them)" % rep)
+    if roof:
+        print("# csrc tree %s" % roof[2])
     for vals in rows[2:]:
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
                 print("%-82s %s %s" % (w, vals[i], units[i]))
         print()
+    if roof:
+        record_roofline(hdr, units, rows[2], *roof)
 
 
 if __name__ == "__main__":
