@@ -747,7 +747,7 @@ def run_coord(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    side = torch.cuda.Stream()
+    side = torch.cuda.Stream(priority=-1)   # the round's small kernels must not queue behind the force update's CTAs
     ev_fork, ev_k1, ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def step_fused(step):

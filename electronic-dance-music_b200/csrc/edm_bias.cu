@@ -559,39 +559,77 @@ __device__ __forceinline__ double d_local_height(const GridDesc& bias, const Rou
   return fmin(h, 1.0 * prm.bias_per_step);  // BIAS_CLAMP, lib/edm_bias.h:14
 }
 
+// The plan runs as ONE thread-block cluster of kPlanCtas CTAs (hardware cluster barriers between its phases, all
+// exchange through global memory, which the barrier's release/acquire covers cluster-wide): as a single CTA it
+// was a latency chain of 62-108 us at 8 % warp occupancy (profiles/r01_k_plan_c3_ncu_selected.txt) and the
+// longest kernel of every 2-D/3-D round.  Phases:
+//   0  every CTA derives the round's mode and the threshold-tempered prefactor from the same state words;
+//      rank 0 publishes them.  Hills arrive either in the accepted buffer (selection on this device) or as the
+//      rank-major blocks of the exchange (`blocks` != NULL): then the unpack is folded in here.
+//   1  (accepted buffer only) rank sort by key, one candidate per thread across the cluster.
+//   2  one entry per thread: centre, target scaling, hill geometry, interpolation cell and its corner records.
+//   3  (local tempering) a warp per entry counts the earlier entries that can reach its corners; entries with
+//      none take their height from the start-of-round records at once.
+//   4  (local tempering) list offsets (every CTA scans the counts redundantly), then a warp per dependent entry
+//      lists the per-unit-height terms of its predecessors.
+//   5  (local tempering) one warp walks the dependent entries in list order.
+constexpr int kPlanCtas = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 template <int DIM>
-__global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc target, RoundParams prm, int n_max,
-                                                         BiasDev* st, HillAccepted* acc, HillAccepted* acc_tmp,
-                                                         double* __restrict__ centres, double* heights,
-                                                         PlanHill<DIM>* plan, int4* __restrict__ cells,
-                                                         double* terms, int* term_j, int term_cap) {
+__global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
+    round_plan_kernel(GridDesc bias, GridDesc target, RoundParams prm, int n_max, BiasDev* st, HillAccepted* acc,
+                      HillAccepted* acc_tmp, double* __restrict__ centres, double* heights, PlanHill<DIM>* plan,
+                      int4* __restrict__ cells, int4* __restrict__ cells_folded, int* __restrict__ ndep_g,
+                      double* terms, int* term_j, int term_cap, const double* __restrict__ blocks, int nblocks,
+                      long block_cap) {
   constexpr int W = RecW<DIM>::value;
   constexpr int NC = 1 << DIM;
   __shared__ double s_prefactor;
-  __shared__ int s_mode;
+  __shared__ int s_mode, s_nb, s_nacc, s_total;
   __shared__ double s_rec[NC][W];
-  __shared__ int s_off[EDM_ROUND_MAX];  // where entry k's list of reaching predecessors starts
-  __shared__ int s_total;
-  __shared__ int s_nb;
-  __shared__ int4 s_cells[EDM_ROUND_MAX];          // centre cell + ok of every planned entry
+  __shared__ int s_off[EDM_ROUND_MAX];             // where entry k's list of reaching predecessors starts
+  __shared__ int4 s_cells[EDM_ROUND_MAX];          // folded centre cell + ok of every planned entry
   __shared__ unsigned short s_ndep[EDM_ROUND_MAX]; // earlier entries that can reach entry k's corners
+  __shared__ int s_boff[65];                       // exchange blocks: first entry of each block
   const bool local = prm.b_tempering && prm.global_tempering < 0;
   const int W1 = DIM + 1;
+  const unsigned crank = cluster_cta_rank();
+  const int ctid = (int)crank * blockDim.x + threadIdx.x, cthreads = kPlanCtas * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int cwarp = ctid >> 5, cwarps = cthreads >> 5;
+  const size_t bw = 1 + (size_t)block_cap * DIM;
+
+  // ---- phase 0
   if (threadIdx.x == 0) {
-    // the planned list: the backlog slots [left, right) first (flush_bias_buffer drains them before
-    // any new hill, lib/edm_bias.cpp:432), then the accepted candidates
     const long long nb = st->right - st->left;
-    int mode = (!st->accepted_overflow && nb + st->n_accepted <= n_max) ? 1 : 0;
-    s_nb = (int)nb;
-    st->n_plan_b = (int)nb;
+    long long nacc = st->n_accepted;
+    int overflow = st->accepted_overflow;
+    if (blocks) {  // the rank-major concatenation is the candidate list; its order is the canonical order
+      nacc = 0;
+      for (int b = 0; b < nblocks; b++) {
+        s_boff[b] = (int)nacc;
+        nacc += (long long)blocks[(size_t)b * bw];
+      }
+      s_boff[nblocks] = (int)nacc;
+      if (nacc > prm.accepted_cap) overflow = 1;
+    }
+    int mode = (!overflow && nb + nacc <= n_max) ? 1 : 0;
     // a periodic window wider than the grid revisits its own points: concurrent hills (DIM > 1) and the plan's
     // one-term-per-predecessor corner patches (local tempering) both assume a single visit
     if (bias.dup_possible && (DIM > 1 || local)) mode = 0;
     if (local && bias.n_dup > 0) mode = 0;         // duplicate_boundary rewrites records between hills
     s_mode = mode;
-    st->round_mode = mode;
-    st->ticket = 0;
-    st->round_epoch++;
+    s_nb = (int)nb;
+    s_nacc = (int)(nacc > prm.accepted_cap ? prm.accepted_cap : nacc);
     double pf = prm.hill_prefactor;
     if (prm.global_tempering > 0) {  // T15: threshold tempering, lib/edm_bias.cpp:419-426
       double avg = st->cum_bias / prm.total_volume;
@@ -601,17 +639,56 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
     s_prefactor = pf;
   }
   __syncthreads();
-  if (s_mode == 0) {
-    if (threadIdx.x == 0) st->n_fast = 0;
-    return;
+  const int nb = s_nb, nacc = s_nacc, nall = nb + nacc;
+  const int mode0 = s_mode;
+  // every CTA has read the state words by now; only then may rank 0 change them
+  cluster_sync_all();
+  if (crank == 0 && threadIdx.x == 0) {
+    st->n_plan_b = nb;
+    st->round_mode = mode0;
+    st->ticket = 0;
+    st->int_done = 0;
+    st->round_epoch++;
+    st->n_fast = mode0 ? nall : 0;
+    if (blocks) {
+      st->n_accepted = s_boff[nblocks];
+      st->accepted_sorted = 1;  // keys are the positions in the rank-major concatenation
+      if (s_boff[nblocks] > prm.accepted_cap) st->accepted_overflow = 1;
+    }
   }
-  int nacc = st->n_accepted;
-  if (nacc > prm.accepted_cap) nacc = (int)prm.accepted_cap;
-  if (!st->accepted_sorted) cta_sort_accepted(acc, acc_tmp, nacc);  // packed / unpacked lists arrive in key order
-  const int nb = s_nb;
-  const int nall = nb + nacc;
+  if (blocks) {  // the unpack: the in-order kernel (and the next plan phases) read the accepted buffer
+    for (int i = ctid; i < nacc; i += cthreads) {
+      int b = 0;
+      while (b + 1 < nblocks && s_boff[b + 1] <= i) b++;
+      const double* src = blocks + (size_t)b * bw + 1 + (size_t)(i - s_boff[b]) * DIM;
+      HillAccepted a;
+      a.key = (unsigned long long)i;
+#pragma unroll
+      for (int d = 0; d < 3; d++) a.x[d] = d < DIM ? src[d] : 0.0;
+      acc[i] = a;
+    }
+  }
+  if (mode0 == 0) return;  // uniform across the cluster: the in-order kernel takes the whole round
+
+  // ---- phase 1: candidate order
+  if (!blocks) {
+    const bool sorted = st->accepted_sorted != 0;  // not modified by this kernel on this path
+    if (!sorted) {
+      for (int i = ctid; i < nacc; i += cthreads) {
+        const unsigned long long k = acc[i].key;
+        int rank = 0;
+        for (int j = 0; j < nacc; j++) rank += (acc[j].key < k);
+        acc_tmp[rank] = acc[i];
+      }
+      cluster_sync_all();
+      for (int i = ctid; i < nacc; i += cthreads) acc[i] = acc_tmp[i];
+    }
+  }
+  cluster_sync_all();
+
+  // ---- phase 2: one entry per thread
   const long long left = st->left;
-  for (int k = threadIdx.x; k < nall; k += blockDim.x) {
+  for (int k = ctid; k < nall; k += cthreads) {
     double pos[DIM];
     const bool slot = k < nb;  // a backlog slot: its height is what the slot holds
     const double* src = slot ? &st->overflow[(left + k) * W1] : acc[k - nb].x;
@@ -642,9 +719,9 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       p.ok = d_hill_prepare<DIM>(bias, pos, p.hg) ? 1 : 0;
       const int4 c = make_int4(p.hg.xi[0], p.hg.xi[DIM > 1 ? 1 : 0], p.hg.xi[DIM > 2 ? 2 : 0], p.ok);
       if (DIM > 1) cells[k] = c;
-      s_cells[k] = make_int4(d_fold(c.x, bias.n[0], bias.periodic[0] != 0),
-                             d_fold(c.y, bias.n[DIM > 1 ? 1 : 0], bias.periodic[DIM > 1 ? 1 : 0] != 0),
-                             d_fold(c.z, bias.n[DIM > 2 ? 2 : 0], bias.periodic[DIM > 2 ? 2 : 0] != 0), p.ok);
+      cells_folded[k] = make_int4(d_fold(c.x, bias.n[0], bias.periodic[0] != 0),
+                                  d_fold(c.y, bias.n[DIM > 1 ? 1 : 0], bias.periodic[DIM > 1 ? 1 : 0] != 0),
+                                  d_fold(c.z, bias.n[DIM > 2 ? 2 : 0], bias.periodic[DIM > 2 ? 2 : 0] != 0), p.ok);
       CellLoc<DIM> L;
       p.valid = d_locate<DIM>(bias, pos, L) ? 1 : 0;
       if (p.valid) {
@@ -655,33 +732,41 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
           p.X0[d] = L.X0[d];
         }
 #pragma unroll
-        for (int c = 0; c < NC; c++) RecLoad<W>::ld(bias.rec + (L.base + d_corner_shift<DIM>(L, c)) * W, p.rec[c]);
+        for (int c2 = 0; c2 < NC; c2++) RecLoad<W>::ld(bias.rec + (L.base + d_corner_shift<DIM>(L, c2)) * W, p.rec[c2]);
       }
     }
   }
-  if (threadIdx.x == 0) st->n_fast = nall;
   if (!local) return;
-  __syncthreads();
+  cluster_sync_all();
 
-  // hills nobody earlier can reach: heights from the start-of-round records, all at once
-  for (int k = nb + threadIdx.x; k < nall; k += blockDim.x) {
-    PlanHill<DIM>& p = plan[k];
+  // ---- phase 3: a warp per new hill counts the earlier entries that can reach its corners
+  for (int k = threadIdx.x; k < nall; k += blockDim.x) s_cells[k] = cells_folded[k];
+  __syncthreads();
+  for (int k = nb + cwarp; k < nall; k += cwarps) {
+    const PlanHill<DIM>& p = plan[k];
     int ndep = 0;
     if (p.valid) {
       int lo[DIM];
 #pragma unroll
       for (int d = 0; d < DIM; d++) lo[d] = p.lo[d];
-      for (int j = 0; j < k; j++) ndep += d_hill_near<DIM>(bias, s_cells[j], lo) ? 1 : 0;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        const bool near = j < k && d_hill_near<DIM>(bias, s_cells[j], lo);
+        ndep += __popc(__ballot_sync(0xffffffffu, near));
+      }
     }
-    s_ndep[k] = (unsigned short)ndep;
-    if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
+    if (lane == 0) {
+      ndep_g[k] = ndep;
+      // nobody earlier can reach it: height from the start-of-round records
+      if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
+    }
   }
-  __syncthreads();
+  cluster_sync_all();
 
-  // The others.  First, all warps at once: for every such hill k, the per-unit-height terms each earlier
-  // reaching hill j adds to k's corner records, listed in order j (they do not depend on any height).
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  if (warp == 0) {  // list offsets: exclusive scan of the counts
+  // ---- phase 4: list offsets (each CTA for itself), then the per-unit-height terms, a warp per dependent hill
+  for (int k = threadIdx.x; k < nall; k += blockDim.x) s_ndep[k] = k < nb ? (unsigned short)0 : (unsigned short)ndep_g[k];
+  __syncthreads();
+  if (threadIdx.x < 32) {
     int carry = 0;
     for (int base = nb; base < nall; base += 32) {
       const int k = base + lane;
@@ -695,17 +780,17 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       if (k < nall) s_off[k] = carry + inc - v;
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) {
-      s_total = carry;
-      if (carry > term_cap) {  // more interplay than the lists hold: the in-order kernel takes the round
-        st->round_mode = 0;
-        st->n_fast = 0;
-      }
-    }
+    if (lane == 0) s_total = carry;
   }
   __syncthreads();
-  if (s_total > term_cap) return;
-  for (int k = nb + warp; k < nall; k += nwarps) {
+  if (s_total > term_cap) {  // more interplay than the lists hold: the in-order kernel takes the round
+    if (crank == 0 && threadIdx.x == 0) {
+      st->round_mode = 0;
+      st->n_fast = 0;
+    }
+    return;  // uniform across the cluster: every CTA computed the same total
+  }
+  for (int k = nb + cwarp; k < nall; k += cwarps) {
     if (s_ndep[k] == 0) continue;
     const PlanHill<DIM>& p = plan[k];
     int lo[DIM], up[DIM];
@@ -750,10 +835,10 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
       pos += __popc(m);
     }
   }
-  __syncthreads();
-  if (warp != 0) return;
+  cluster_sync_all();
+  if (crank != 0 || threadIdx.x >= 32) return;
 
-  // Then one warp, in candidate order: corner records + sum over the list of h_j * term (the adds a
+  // ---- phase 5: one warp, in candidate order: corner records + sum over the list of h_j * term (the adds a
   // hill-by-hill deposit would have made to those records, in the same order), interpolate, scale.
   for (int k = nb; k < nall; k++) {
     const int cnt = s_ndep[k];
@@ -776,15 +861,21 @@ __global__ void __launch_bounds__(512) round_plan_kernel(GridDesc bias, GridDesc
   }
 }
 
-// add_value's integral of every planned hill, one CTA per hill (2-D/3-D)
 template <int DIM>
-__global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, const BiasDev* st,
+__device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasDev* st, const double* __restrict__ centres,
+                             const double* __restrict__ heights, const double* __restrict__ ba, edm_hill_event_t* log);
+
+// add_value's integral of every planned hill, one CTA per hill; the CTA that finishes last also takes the
+// decision (round_decide below) — one launch and one dependent round trip less than a separate kernel.
+template <int DIM>
+__global__ void __launch_bounds__(512, 2) round_integrals_kernel(GridDesc bias, GridDesc hist, RoundParams prm, BiasDev* st,
                                                               const double* __restrict__ centres,
                                                               const double* __restrict__ heights,
-                                                              double* __restrict__ ba) {
+                                                              double* __restrict__ ba, edm_hill_event_t* log) {
   __shared__ double red[33];
+  __shared__ int s_last;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
-  if (st->round_mode != 1) return;
+  if (st->round_mode != 1) return;  // uniform over the grid: written by the plan, an earlier launch
   const int n = st->n_fast;
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
     double pos[DIM];
@@ -794,6 +885,16 @@ __global__ void __launch_bounds__(512) round_integrals_kernel(GridDesc bias, con
     double tot = cta_window_pass<DIM, kPassIntegrate>(bias, pos, heights[k], red, dirty, s_axis);
     if (threadIdx.x == 0) ba[k] = tot;
   }
+  // last CTA out decides: every CTA publishes its integrals (fence) before it signs off
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&st->int_done, 1) == (int)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  round_decide<DIM>(hist, prm, st, centres, heights, ba, log);
 }
 
 // The deposit itself once the decision fell (round_mode 2 or 3: hills [0, n_fast)), 2-D/3-D.  CTAs take hills by ticket,
@@ -828,7 +929,7 @@ __device__ __forceinline__ bool d_windows_overlap(const GridDesc& g, const int4&
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasDev* st,
+__global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, BiasDev* st,
                                                             const double* __restrict__ centres,
                                                             const double* __restrict__ heights,
                                                             const int4* __restrict__ cells, int* flags) {
@@ -862,17 +963,12 @@ __global__ void __launch_bounds__(512) round_deposit_kernel(GridDesc bias, BiasD
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(512) round_decide_kernel(GridDesc hist, RoundParams prm, BiasDev* st,
-                                                           const double* __restrict__ centres,
-                                                           const double* __restrict__ heights,
-                                                           const double* __restrict__ ba, edm_hill_event_t* log) {
-  __shared__ int s_take, s_mode, s_nb;
-  if (threadIdx.x == 0) s_mode = st->round_mode;
-  __syncthreads();
-  if (s_mode != 1) return;
+__device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasDev* st, const double* __restrict__ centres,
+                             const double* __restrict__ heights, const double* __restrict__ ba, edm_hill_event_t* log) {
+  __shared__ int s_take, s_nb;
   const int n = st->n_fast;
   __shared__ double s_ba[EDM_ROUND_MAX];  // the scan below is one thread's: keep its operands next to it
-  for (int k = threadIdx.x; k < n; k += blockDim.x) s_ba[k] = ba[k];
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s_ba[k] = __ldcg(&ba[k]);  // other CTAs wrote them: read through L2
   __syncthreads();
   if (threadIdx.x == 0) {
     // Entries [0, take) of the planned list are plain full deposits.  Backlog slots first
@@ -1075,6 +1171,12 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
                             bool fast, cudaStream_t st) {
   HillAccepted* tmp = b->d_accepted + b->accepted_cap;
   const GridDesc& bias = b->bias->d;
+  const double* blocks = b->round_blocks;  // candidates arrive as exchange blocks (edm_bias_hills_commit_dev)
+  if (blocks && !fast) {                   // the in-order kernel reads the accepted buffer: unpack first
+    unpack_blocks_kernel<DIM><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, b->round_nblocks,
+                                                 b->round_block_cap);
+    count_launches(1);
+  }
   if (fast) {
     const long cap = b->accepted_cap;
     // the plan is sized for the usual few hundred hills; larger rounds take the sequential path
@@ -1085,7 +1187,9 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     // local tempering: (later hill, earlier reaching hill) pairs the plan can list
     const int term_cap = 16384;
     const size_t b_terms = (size_t)term_cap * (1 << DIM) * RecW<DIM>::value * sizeof(double);
-    EDM_TRY(b->fast.reserve(b_dbl + b_plan + b_cells + b_terms + (size_t)term_cap * sizeof(int)));
+    const size_t b_tj = ((size_t)term_cap * sizeof(int) + 15) / 16 * 16;
+    const size_t b_nd = ((size_t)n_max * sizeof(int) + 15) / 16 * 16;
+    EDM_TRY(b->fast.reserve(b_dbl + b_plan + 2 * b_cells + b_terms + b_tj + b_nd));
     double* centres = b->fast.as<double>();
     double* heights = centres + (size_t)DIM * cap;
     double* ba = heights + cap;
@@ -1093,13 +1197,16 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     int4* cells = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan);
     double* terms = reinterpret_cast<double*>(b->fast.as<char>() + b_dbl + b_plan + b_cells);
     int* term_j = reinterpret_cast<int*>(b->fast.as<char>() + b_dbl + b_plan + b_cells + b_terms);
-    round_plan_kernel<DIM><<<1, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp, centres,
-                                               heights, plan, cells, terms, term_j, term_cap);
+    int4* cells_folded = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan + b_cells + b_terms + b_tj);
+    int* ndep = reinterpret_cast<int*>(b->fast.as<char>() + b_dbl + b_plan + 2 * b_cells + b_terms + b_tj);
+    // one cluster of kPlanCtas CTAs (compile-time __cluster_dims__)
+    round_plan_kernel<DIM><<<kPlanCtas, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp,
+                                                       centres, heights, plan, cells, cells_folded, ndep, terms, term_j,
+                                                       term_cap, blocks, b->round_nblocks, b->round_block_cap);
     const long nsm4 = 4L * sm_count(b->device);
-    const int blocks = (int)(n_max < nsm4 ? n_max : nsm4);
-    round_integrals_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, ba);
-    round_decide_kernel<DIM><<<1, 512, 0, st>>>(hist, rp, b->d_state, centres, heights, ba, b->d_log);
-    count_launches(3);
+    const int nblk = (int)(n_max < nsm4 ? n_max : nsm4);
+    round_integrals_kernel<DIM><<<nblk, 512, 0, st>>>(bias, hist, rp, b->d_state, centres, heights, ba, b->d_log);
+    count_launches(2);
     // everything so far only read the grid; whoever else still reads it (this step's force update on
     // another stream) must be done before the first write
     if (b->round_after) {
@@ -1112,7 +1219,7 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
       EDM_TRY(deposit1d_stage(b->bias, centres, heights, nullptr, &b->d_state->n_fast, n_max, st));
       EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
     } else {
-      round_deposit_kernel<DIM><<<blocks, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
+      round_deposit_kernel<DIM><<<nblk, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
       count_launches(1);
       if (bias.n_dup) {
         EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
@@ -1195,6 +1302,10 @@ int edm_bias_create(edm_bias_t** out, edm_grid_t* bias, edm_grid_t* cv_hist, edm
   EDM_REQUIRE(out && bias && params, "NULL argument");
   EDM_REQUIRE(bias->d.is_gauss && bias->d.dim == params->dim, "bias must be a GaussGrid of params->dim dimensions");
   EDM_TRY(ensure_device(bias->device));
+  {  // experiment hook: EDM_L2_FETCH=32|64|128 sets the device's L2 fetch granularity hint (random-gather workloads)
+    static const char* l2f = getenv("EDM_L2_FETCH");
+    if (l2f) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(l2f));
+  }
   edm_bias* b = new edm_bias();
   b->device = bias->device;
   b->prm = *params;
@@ -1206,7 +1317,7 @@ int edm_bias_create(edm_bias_t** out, edm_grid_t* bias, edm_grid_t* cv_hist, edm
   EDM_CUDA(cudaMemset(b->d_state, 0, sizeof(BiasDev)));  // T19: the backlog storage starts zero-filled
   b->log_cap = 1 << 16;
   EDM_CUDA(cudaMalloc(&b->d_log, (size_t)b->log_cap * sizeof(edm_hill_event_t)));
-  b->n_partial = sm_count(b->device) * 8;
+  b->n_partial = sm_count(b->device) * 64;
   EDM_CUDA(cudaMalloc(&b->d_energy_partial, (size_t)b->n_partial * sizeof(double)));
   EDM_CUDA(cudaMalloc(&b->d_scalar, 8 * sizeof(double)));
   EDM_TRY(ensure_accepted(b, 4096));
@@ -1331,6 +1442,8 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
   EDM_REQUIRE(xstride >= b->prm.dim && fstride >= b->prm.dim, "stride < dim");
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
+  // short-lived CTAs (a handful of atoms per thread at most): the SM slots they release let the hill round's
+  // small kernels, which sit on a higher-priority stream, in while the force update is still running
   long long blocks = (n + 256 * EDM_FORCES_UNROLL - 1) / (256 * EDM_FORCES_UNROLL);
   if (blocks > b->n_partial) blocks = b->n_partial;
   if (blocks < 1) blocks = 1;
@@ -1342,8 +1455,12 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
     default: forces_kernel<3><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
   }
   EDM_CUDA(cudaGetLastError());
+  if (b->forces_event) {  // one-shot: "the force update has read the grid" (before the energy sum)
+    EDM_CUDA(cudaEventRecord(b->forces_event, st));
+    b->forces_event = nullptr;
+  }
   if (energy) {
-    sum_partials_kernel<<<1, 256, 0, st>>>((int)blocks, b->d_energy_partial, energy);
+    sum_partials_kernel<<<1, 1024, 0, st>>>((int)blocks, b->d_energy_partial, energy);
     EDM_CUDA(cudaGetLastError());
   }
   return EDM_OK;
@@ -1490,15 +1607,22 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   EDM_TRY(ensure_device(b->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (!b->st_side) {
-    EDM_CUDA(cudaStreamCreateWithFlags(&b->st_side, cudaStreamNonBlocking));
+    // highest priority: the round's kernels are tiny next to the force update and must not queue behind its CTAs
+    int prio_lo = 0, prio_hi = 0;
+    EDM_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    EDM_CUDA(cudaStreamCreateWithPriority(&b->st_side, cudaStreamNonBlocking, prio_hi));
     EDM_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     EDM_CUDA(cudaEventCreateWithFlags(&b->ev_forces, cudaEventDisableTiming));
     EDM_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   }
   EDM_CUDA(cudaEventRecord(b->ev_fork, st));
   EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
+  b->forces_event = b->ev_forces;
   if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream));
-  EDM_CUDA(cudaEventRecord(b->ev_forces, st));
+  if (b->forces_event) {  // nothing was launched
+    EDM_CUDA(cudaEventRecord(b->ev_forces, st));
+    b->forces_event = nullptr;
+  }
   const long long est = edm_job_est(b, n);
   EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
   EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
@@ -1683,16 +1807,16 @@ int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, 
                               void* stream) {
   EDM_REQUIRE(b && blocks && nblocks > 0 && cap > 0, "bad argument");
   EDM_TRY(ensure_device(b->device));
+  EDM_REQUIRE(nblocks <= 64, "at most 64 exchange blocks");
   cudaStream_t st = (cudaStream_t)stream;
   EDM_TRY(ensure_accepted(b, (long)nblocks * cap));
-  count_launches(1);
-  switch (b->prm.dim) {
-    case 1: unpack_blocks_kernel<1><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
-    case 2: unpack_blocks_kernel<2><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
-    default: unpack_blocks_kernel<3><<<1, 256, 0, st>>>(b->d_state, b->d_accepted, b->accepted_cap, blocks, nblocks, cap); break;
-  }
-  EDM_CUDA(cudaGetLastError());
-  return edm_bias_launch_round(b, est_hill_count, st, false);
+  // the round's plan reads the blocks itself (its first phase is the unpack)
+  b->round_blocks = blocks;
+  b->round_nblocks = nblocks;
+  b->round_block_cap = cap;
+  const int rc = edm_bias_launch_round(b, est_hill_count, st, false);
+  b->round_blocks = nullptr;
+  return rc;
 }
 
 int edm_bias_check(edm_bias_t* b) {

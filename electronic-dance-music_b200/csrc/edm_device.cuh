@@ -529,15 +529,18 @@ __device__ double cta_window_pass(const GridDesc& g, const double* x0, double h,
 #pragma unroll
     for (int d = 0; d < DIM; d++) inv_denom *= g.sqrtpi_sigma[d];
     inv_denom = 1.0 / inv_denom;
-    const int span0 = 2 * g.supp[0] + 1, span1 = 2 * g.supp[DIM > 1 ? 1 : 0] + 1;
-    for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+    // every span is at most kAxisMax here, so the window has fewer than 2^20 points: 32-bit index arithmetic
+    // (a 64-bit division by a run-time span costs more than the rest of the loop body)
+    const unsigned span0 = 2 * g.supp[0] + 1, span1 = 2 * g.supp[DIM > 1 ? 1 : 0] + 1;
+    const unsigned total32 = (unsigned)total;
+    for (unsigned w = threadIdx.x; w < total32; w += blockDim.x) {
       int o[3];
-      long long q = w;
-      o[0] = (int)(q % span0);
-      q /= span0;
+      unsigned q = w / span0;
+      o[0] = (int)(w - q * span0);
       if (DIM > 2) {
-        o[1] = (int)(q % span1);
-        o[2] = (int)(q / span1);
+        const unsigned q2 = q / span1;
+        o[1] = (int)(q - q2 * span1);
+        o[2] = (int)q2;
       } else {
         o[1] = (int)q;
         o[2] = 0;

@@ -98,6 +98,7 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int n_accepted_last;  // candidates the last finished round consumed
   int rounds_parallel, rounds_split, rounds_in_order;  // how the rounds so far ran (edm_bias_round_info)
   int ticket;      // next hill a CTA of the parallel deposit takes
+  int int_done;    // CTAs of round_integrals_kernel that signed off (the last one takes the decision)
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   unsigned long long n_pairs;
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
@@ -173,6 +174,11 @@ struct edm_bias {
   cudaStream_t st_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_forces = nullptr, ev_join = nullptr;
   cudaEvent_t round_after = nullptr;  // borrowed, one-shot: the next round's first grid write waits for it
+  cudaEvent_t forces_event = nullptr; // one-shot: recorded right after the next forces_kernel launch
+  // one-shot: the next round takes its candidates from these exchange blocks (the plan unpacks them itself)
+  const double* round_blocks = nullptr;
+  int round_nblocks = 0;
+  long round_block_cap = 0;
   cudaEvent_t ev_pair[3] = {nullptr, nullptr, nullptr};  // pair kernels: begin, end, between search and evaluation
 };
 

@@ -1266,6 +1266,10 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
     dt = b->io3.as<int>();
   }
   EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, b->st_main));
+  // the old forces follow the positions over the link (two concurrent uploads would share it and delay the
+  // positions, which the binning and the search are waiting for; the forces are not needed before the evaluation)
+  EDM_CUDA(cudaEventRecord(b->ev_f_final, b->st_main));  // reused here as "x is up"
+  EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_f_final, 0));
   if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[1], b->st_main));
   EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bx, cudaMemcpyHostToDevice, b->st_copy));
   EDM_CUDA(cudaEventRecord(b->ev_f_up, b->st_copy));

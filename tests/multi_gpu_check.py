@@ -123,7 +123,7 @@ def coord_check(tmp, rank, world, local, comm):
     edev = torch.zeros(1, dtype=torch.float64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     xs, us, es, fs = [], [], [], []
-    side = torch.cuda.Stream()
+    side = torch.cuda.Stream(priority=-1)
     ev_fork, ev_k1, ev_join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     for step in range(steps):
         rng = np.random.default_rng([77, rank, step])
