@@ -858,6 +858,7 @@ def run_coord(args, rank, local_rank, world):
             "step_breakdown_ms": {"update_forces": k1, "hill_round": rnd,
                                   "note": "measured back to back; in the timed step the round's selection, exchange, plan, "
                                           "integrals and decision run beside update_forces on a second stream"},
+            "round_stamps_us": [round(float(v), 2) for v in bias.round_times_us()],
             "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],
                       "rounds_split": info1["split"] - info0["split"],
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},

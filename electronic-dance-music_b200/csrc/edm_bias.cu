@@ -10,6 +10,12 @@
 
 namespace edm {
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ------------------------------------------------------------------ K1: update_forces
 
 // EDMBias::update_forces, lib/edm_bias.cpp:276-295: thread per atom, coalesced row loads,
@@ -81,6 +87,8 @@ __global__ void __launch_bounds__(256) select_kernel(long n, const double* __res
                                                      int apply_mask, double thresh, int accept_all, uint64_t key,
                                                      uint64_t first_counter, BiasDev* st, HillAccepted* acc,
                                                      long cap) {
+  pdl_trigger();
+  pdl_wait();
   long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (apply_mask >= 0 && !(apply_mask & mask[i])) continue;
@@ -241,9 +249,13 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ double s_prefactor;
   __shared__ RoundState rs;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
+  pdl_trigger();
+  pdl_wait();
   const int mode = st->round_mode;
+  if (threadIdx.x == 0) st->stamp[11] = global_ns();
   if (mode == 2) {  // the parallel round already committed this round
     if (threadIdx.x == 0) {
+      st->stamp[12] = global_ns();
       st->n_accepted_last = st->n_accepted;
       st->n_accepted = 0;  // the next selection starts a fresh candidate list
       st->accepted_sorted = 0;
@@ -462,6 +474,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
     st->n_accepted_last = st->n_accepted;
     st->n_accepted = 0;  // the next selection starts a fresh candidate list
     st->accepted_sorted = 0;
+    st->stamp[12] = global_ns();
   }
 }
 
@@ -559,6 +572,32 @@ __device__ __forceinline__ double d_local_height(const GridDesc& bias, const Rou
   return fmin(h, 1.0 * prm.bias_per_step);  // BIAS_CLAMP, lib/edm_bias.h:14
 }
 
+// The plan executes each of its phases once per round, on instruction caches the force update has just flushed:
+// with everything inlined it was 120 KB (2-D) to 213 KB (3-D) of straight-line code and spent most of its time
+// fetching it (sm__icc hit rate 76 %, 3.2 warps stalled on "no instruction" per issue).  The heavy device
+// functions are therefore called, not inlined, here: one copy each, shared by all call sites and corners.
+template <int DIM>
+__device__ __noinline__ bool plan_hill_prepare(const GridDesc& g, const double* x0, HillGeom<DIM>& hg) {
+  return d_hill_prepare<DIM>(g, x0, hg);
+}
+template <int DIM>
+__device__ __noinline__ bool plan_hill_term(const GridDesc& g, const HillGeom<DIM>& hg, const int* idx, double& etot,
+                                            double* force) {
+  bool cnz;
+  return d_hill_term<DIM>(g, hg, idx, etot, force, cnz);
+}
+template <int DIM>
+__device__ __noinline__ double plan_local_height(const GridDesc& bias, const RoundParams& prm, const double* X0,
+                                                 const double (*rec)[RecW<DIM>::value], bool valid, double hb) {
+  return d_local_height<DIM>(bias, prm, X0, rec, valid, hb);
+}
+template <int DIM> __device__ __noinline__ bool plan_locate(const GridDesc& g, const double* x, CellLoc<DIM>& L) {
+  return d_locate<DIM>(g, x, L);
+}
+template <int DIM> __device__ __noinline__ double plan_target_value(const GridDesc& target, const double* x) {
+  return d_get_value<DIM>(target, x);
+}
+
 // The plan runs as ONE thread-block cluster of kPlanCtas CTAs (hardware cluster barriers between its phases, all
 // exchange through global memory, which the barrier's release/acquire covers cluster-wide): as a single CTA it
 // was a latency chain of 62-108 us at 8 % warp occupancy (profiles/r01_k_plan_c3_ncu_selected.txt) and the
@@ -586,7 +625,8 @@ __device__ __forceinline__ unsigned cluster_cta_rank() {
 
 template <int DIM>
 __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
-    round_plan_kernel(GridDesc bias, GridDesc target, RoundParams prm, int n_max, BiasDev* st, HillAccepted* acc,
+    round_plan_kernel(const __grid_constant__ GridDesc bias, const __grid_constant__ GridDesc target,
+                      const __grid_constant__ RoundParams prm, int n_max, BiasDev* st, HillAccepted* acc,
                       HillAccepted* acc_tmp, double* __restrict__ centres, double* heights, PlanHill<DIM>* plan,
                       int4* __restrict__ cells, int4* __restrict__ cells_folded, int* __restrict__ ndep_g,
                       double* terms, int* term_j, int term_cap, const double* __restrict__ blocks, int nblocks,
@@ -595,11 +635,15 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
   constexpr int NC = 1 << DIM;
   __shared__ double s_prefactor;
   __shared__ int s_mode, s_nb, s_nacc, s_total;
-  __shared__ double s_rec[NC][W];
-  __shared__ int s_off[EDM_ROUND_MAX];             // where entry k's list of reaching predecessors starts
+  // where entry k's list of reaching predecessors starts (16 bits: lists hold at most term_cap <= 65535 entries,
+  // and a round with more bails out before any offset is used)
+  __shared__ unsigned short s_off[EDM_ROUND_MAX];
   __shared__ int4 s_cells[EDM_ROUND_MAX];          // folded centre cell + ok of every planned entry
   __shared__ unsigned short s_ndep[EDM_ROUND_MAX]; // earlier entries that can reach entry k's corners
   __shared__ int s_boff[65];                       // exchange blocks: first entry of each block
+  __shared__ unsigned char s_ready[EDM_ROUND_MAX]; // phase 5: hill k's height is final
+  __shared__ int s_ndeps;                          // phase 5: how many hills have predecessors
+  __shared__ double s_rec5[16][NC * W];            // phase 5: one patched corner block per warp
   const bool local = prm.b_tempering && prm.global_tempering < 0;
   const int W1 = DIM + 1;
   const unsigned crank = cluster_cta_rank();
@@ -608,6 +652,9 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
   const int cwarp = ctid >> 5, cwarps = cthreads >> 5;
   const size_t bw = 1 + (size_t)block_cap * DIM;
 
+  pdl_wait();  // the trigger is left to the exit: the successor's grid is large and would sit resident on every SM
+  const bool stamper = crank == 0 && threadIdx.x == 0;
+  if (stamper) st->stamp[0] = global_ns();
   // ---- phase 0
   if (threadIdx.x == 0) {
     const long long nb = st->right - st->left;
@@ -669,6 +716,7 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     }
   }
   if (mode0 == 0) return;  // uniform across the cluster: the in-order kernel takes the whole round
+  if (stamper) st->stamp[1] = global_ns();
 
   // ---- phase 1: candidate order
   if (!blocks) {
@@ -685,6 +733,7 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     }
   }
   cluster_sync_all();
+  if (stamper) st->stamp[2] = global_ns();
 
   // ---- phase 2: one entry per thread
   const long long left = st->left;
@@ -701,11 +750,12 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     if (slot)
       heights[k] = src[DIM];
     else if (prm.b_targeting)
-      h *= exp(d_get_value<DIM>(target, pos) - prm.expected_target);
-    if (DIM > 1 && !local) {  // centre cells for the deposit's overlap test
-      HillGeom<DIM> hg;
-      bool ok = d_hill_prepare<DIM>(bias, pos, hg);
-      cells[k] = make_int4(hg.xi[0], hg.xi[DIM > 1 ? 1 : 0], hg.xi[DIM > 2 ? 2 : 0], ok ? 1 : 0);
+      h *= exp(plan_target_value<DIM>(target, pos) - prm.expected_target);
+    HillGeom<DIM> hg;
+    bool ok = false;
+    if (DIM > 1 || local) {  // centre cells for the deposit's overlap test / the reach tests of local tempering
+      ok = plan_hill_prepare<DIM>(bias, pos, hg);
+      if (DIM > 1) cells[k] = make_int4(hg.xi[0], hg.xi[DIM > 1 ? 1 : 0], hg.xi[DIM > 2 ? 2 : 0], ok ? 1 : 0);
     }
     if (!local) {
       if (prm.hill_density < 0)
@@ -716,14 +766,14 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     } else {
       PlanHill<DIM>& p = plan[k];
       p.hb = h;
-      p.ok = d_hill_prepare<DIM>(bias, pos, p.hg) ? 1 : 0;
-      const int4 c = make_int4(p.hg.xi[0], p.hg.xi[DIM > 1 ? 1 : 0], p.hg.xi[DIM > 2 ? 2 : 0], p.ok);
-      if (DIM > 1) cells[k] = c;
+      p.ok = ok ? 1 : 0;
+      p.hg = hg;
+      const int4 c = make_int4(hg.xi[0], hg.xi[DIM > 1 ? 1 : 0], hg.xi[DIM > 2 ? 2 : 0], p.ok);
       cells_folded[k] = make_int4(d_fold(c.x, bias.n[0], bias.periodic[0] != 0),
                                   d_fold(c.y, bias.n[DIM > 1 ? 1 : 0], bias.periodic[DIM > 1 ? 1 : 0] != 0),
                                   d_fold(c.z, bias.n[DIM > 2 ? 2 : 0], bias.periodic[DIM > 2 ? 2 : 0] != 0), p.ok);
       CellLoc<DIM> L;
-      p.valid = d_locate<DIM>(bias, pos, L) ? 1 : 0;
+      p.valid = plan_locate<DIM>(bias, pos, L) ? 1 : 0;
       if (p.valid) {
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
@@ -736,8 +786,10 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
       }
     }
   }
+  if (stamper) st->stamp[3] = st->stamp[4] = st->stamp[5] = st->stamp[6] = global_ns();
   if (!local) return;
   cluster_sync_all();
+  if (stamper) st->stamp[3] = global_ns();
 
   // ---- phase 3: a warp per new hill counts the earlier entries that can reach its corners
   for (int k = threadIdx.x; k < nall; k += blockDim.x) s_cells[k] = cells_folded[k];
@@ -758,10 +810,11 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     if (lane == 0) {
       ndep_g[k] = ndep;
       // nobody earlier can reach it: height from the start-of-round records
-      if (ndep == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
+      if (ndep == 0) heights[k] = plan_local_height<DIM>(bias, prm, p.X0, p.rec, p.valid != 0, p.hb);
     }
   }
   cluster_sync_all();
+  if (stamper) st->stamp[4] = global_ns();
 
   // ---- phase 4: list offsets (each CTA for itself), then the per-unit-height terms, a warp per dependent hill
   for (int k = threadIdx.x; k < nall; k += blockDim.x) s_ndep[k] = k < nb ? (unsigned short)0 : (unsigned short)ndep_g[k];
@@ -777,7 +830,7 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
         const int u = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += u;
       }
-      if (k < nall) s_off[k] = carry + inc - v;
+      if (k < nall) s_off[k] = (unsigned short)(carry + inc - v);
       carry += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) s_total = carry;
@@ -808,20 +861,20 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
         const int slot = pos + __popc(m & ((1u << lane) - 1u));
         term_j[slot] = j;
         double* T = terms + (size_t)slot * (NC * W);
-#pragma unroll
+        const HillGeom<DIM> hgj = plan[j].hg;  // one bulk load instead of a dependent L2 round trip per field
+#pragma unroll 1
         for (int c = 0; c < NC; c++) {
           int idx[DIM];
           bool reach = true;
 #pragma unroll
           for (int d = 0; d < DIM; d++) {
             idx[d] = ((c >> d) & 1) ? up[d] : lo[d];
-            reach = reach && d_window_reaches(bias, d, plan[j].hg.xi[d], idx[d]);
+            reach = reach && d_window_reaches(bias, d, hgj.xi[d], idx[d]);
           }
           double etot = 0.0, force[DIM];
 #pragma unroll
           for (int d = 0; d < DIM; d++) force[d] = 0.0;
-          bool cnz;
-          if (reach && !d_hill_term<DIM>(bias, plan[j].hg, idx, etot, force, cnz)) {
+          if (reach && !plan_hill_term<DIM>(bias, hgj, idx, etot, force)) {
             etot = 0.0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) force[d] = 0.0;
@@ -836,29 +889,73 @@ __global__ void __cluster_dims__(kPlanCtas, 1, 1) __launch_bounds__(512)
     }
   }
   cluster_sync_all();
-  if (crank != 0 || threadIdx.x >= 32) return;
+  if (stamper) st->stamp[5] = global_ns();
+  if (crank != 0) return;
 
-  // ---- phase 5: one warp, in candidate order: corner records + sum over the list of h_j * term (the adds a
-  // hill-by-hill deposit would have made to those records, in the same order), interpolate, scale.
-  for (int k = nb; k < nall; k++) {
-    const int cnt = s_ndep[k];
-    if (cnt == 0) continue;
-    const PlanHill<DIM>& p = plan[k];
-    double accv = 0.0;
-    if (lane < NC * W) accv = p.rec[lane / W][lane % W];
-    const int first = s_off[k];
-#pragma unroll 4
-    for (int e = 0; e < cnt; e++) {
-      const double hj = heights[term_j[first + e]];
-      const double t = lane < NC * W ? terms[(size_t)(first + e) * (NC * W) + lane] : 0.0;
-      accv += hj * t;
+  // ---- phase 5 (rank 0): the dependent hills, each by one warp: corner records + sum over its list of
+  // h_j * term in list order (the adds a hill-by-hill deposit would have made to those records, in the same
+  // order), interpolate, scale.  A hill waits only for listed predecessors, which all have lower indices; a warp
+  // takes its hills in increasing order, so the lowest unfinished hill is always being worked on by its warp and
+  // never waits for an unfinished one: no deadlock, and sparse dependencies (2-D/3-D) resolve in parallel while a
+  // 1-D chain degrades to the order it must have anyway.
+  if (threadIdx.x == 0) s_ndeps = 0;
+  for (int k = threadIdx.x; k < nall; k += blockDim.x) s_ready[k] = (k < nb || s_ndep[k] == 0) ? 1 : 0;
+  __syncthreads();
+  // the dependent hills as a compact ascending list (rewriting s_ndep's tail is not possible: counts are needed),
+  // kept in the cells_folded scratch of this CTA's shared copy: s_cells is dead from here on
+  int* s_deplist = reinterpret_cast<int*>(s_cells);
+  if (threadIdx.x < 32) {
+    int base = 0;
+    for (int k0 = nb; k0 < nall; k0 += 32) {
+      const int k = k0 + lane;
+      const bool dep = k < nall && s_ndep[k] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, dep);
+      if (dep) s_deplist[base + __popc(m & ((1u << lane) - 1u))] = k;
+      base += __popc(m);
     }
-    if (lane < NC * W) s_rec[lane / W][lane % W] = accv;
-    __syncwarp();
-    if (lane == 0) heights[k] = d_local_height<DIM>(bias, prm, p.X0, s_rec, true, p.hb);
-    __threadfence_block();
-    __syncwarp();
+    if (lane == 0) s_ndeps = base;
   }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int ndeps = s_ndeps;
+    for (int i = warp; i < ndeps; i += nwarps) {  // the i-th dependent hill goes to warp i % nwarps, ascending
+      const int k = s_deplist[i];
+      const int cnt = s_ndep[k];
+      const PlanHill<DIM>& p = plan[k];
+      double accv = 0.0;
+      if (lane < NC * W) accv = p.rec[lane / W][lane % W];
+      const int first = s_off[k];
+      for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        double hj = 0.0;
+        if (e < cnt) {
+          const int j = term_j[first + e];
+          while (*(volatile unsigned char*)&s_ready[j] == 0) {
+          }
+          hj = __ldcg(&heights[j]);  // written by another warp of this CTA (or an earlier phase): read through L2
+        }
+        __syncwarp();
+        const int m = min(32, cnt - e0);
+        for (int q = 0; q < m; q++) {
+          const double h = __shfl_sync(0xffffffffu, hj, q);
+          const double t = lane < NC * W ? terms[(size_t)(first + e0 + q) * (NC * W) + lane] : 0.0;
+          accv += h * t;
+        }
+      }
+      double* myrec = &s_rec5[warp][0];
+      if (lane < NC * W) myrec[lane] = accv;
+      __syncwarp();
+      if (lane == 0) {
+        heights[k] = plan_local_height<DIM>(bias, prm, p.X0, reinterpret_cast<const double(*)[W]>(myrec), true, p.hb);
+        __threadfence_block();  // consumers inside this phase are warps of this CTA; later kernels see it anyway
+        *(volatile unsigned char*)&s_ready[k] = 1;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (stamper) st->stamp[6] = global_ns();
 }
 
 template <int DIM>
@@ -875,6 +972,8 @@ __global__ void __launch_bounds__(512, 2) round_integrals_kernel(GridDesc bias, 
   __shared__ double red[33];
   __shared__ int s_last;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
+  pdl_trigger();
+  pdl_wait();
   if (st->round_mode != 1) return;  // uniform over the grid: written by the plan, an earlier launch
   const int n = st->n_fast;
   for (int k = blockIdx.x; k < n; k += gridDim.x) {
@@ -894,7 +993,9 @@ __global__ void __launch_bounds__(512, 2) round_integrals_kernel(GridDesc bias, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (threadIdx.x == 0) st->stamp[7] = global_ns();
   round_decide<DIM>(hist, prm, st, centres, heights, ba, log);
+  if (threadIdx.x == 0) st->stamp[8] = global_ns();
 }
 
 // The deposit itself once the decision fell (round_mode 2 or 3: hills [0, n_fast)), 2-D/3-D.  CTAs take hills by ticket,
@@ -936,6 +1037,8 @@ __global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, Bi
   __shared__ double red[33];
   __shared__ int s_k;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
+  pdl_trigger();
+  pdl_wait();
   if (st->round_mode < 2) return;
   const int n = st->n_fast;
   const int epoch = st->round_epoch;
@@ -944,6 +1047,7 @@ __global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, Bi
     __syncthreads();
     const int k = s_k;
     if (k >= n) break;
+    if (k == 0 && threadIdx.x == 0) st->stamp[9] = global_ns();
     const int4 ck = cells[k];
     for (int j = threadIdx.x; j < k; j += blockDim.x)
       if (d_windows_overlap<DIM>(bias, cells[j], ck))
@@ -954,20 +1058,39 @@ __global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, Bi
 #pragma unroll
     for (int d = 0; d < DIM; d++) pos[d] = centres[(long)k * DIM + d];
     bool dirty;
-    cta_window_pass<DIM, kPassAtomic>(bias, pos, heights[k], red, dirty, s_axis);
+    // concurrent hills never overlap here (an overlapping later hill waits for this one's release): plain RMWs
+    cta_window_pass<DIM, kPassOrdered>(bias, pos, heights[k], red, dirty, s_axis);
     if (dirty) flags[0] = 1;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) st_release_gpu(&st->hill_done[k], epoch);
+    if (threadIdx.x == 0) {
+      if (k == n - 1) st->stamp[10] = global_ns();
+      st_release_gpu(&st->hill_done[k], epoch);
+    }
   }
 }
 
 template <int DIM>
 __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasDev* st, const double* __restrict__ centres,
                              const double* __restrict__ heights, const double* __restrict__ ba, edm_hill_event_t* log) {
-  __shared__ int s_take, s_nb;
-  const int n = st->n_fast;
+  // One CTA, a handful of dependent steps: every global load it needs is issued up front (the state words by
+  // thread 0 while all threads fetch the integrals), the running sum runs on shared memory, and nothing is read
+  // back from global memory afterwards — each dependent round trip here costs as much as the whole scan.
+  __shared__ int s_take, s_nb, s_base;
+  __shared__ double s_cov;
+  __shared__ long long s_steps;
   __shared__ double s_ba[EDM_ROUND_MAX];  // the scan below is one thread's: keep its operands next to it
+  const int n = st->n_fast;
+  int nb = 0, log_n = 0;
+  long long steps = 0, left = 0;
+  double cum_bias = 0.0;
+  if (threadIdx.x == 0) {
+    nb = st->n_plan_b;
+    log_n = st->log_n;
+    steps = st->steps;
+    left = st->left;
+    cum_bias = st->cum_bias;
+  }
   for (int k = threadIdx.x; k < n; k += blockDim.x) s_ba[k] = __ldcg(&ba[k]);  // other CTAs wrote them: read through L2
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -977,17 +1100,28 @@ __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasD
     // running sum, lib/edm_bias.cpp:465-474): plain while the sum stays below bias_per_step before
     // and after the hill.  The first entry that is not plain, and everything behind it, is the
     // in-order kernel's.
-    const int nb = st->n_plan_b;
     const double bps = prm.bias_per_step;
     double cum = 0.0;
     int take = 0;
     bool stop = false;
     while (!stop && take < n) {  // eight entries at a time: the loads and tests overlap, the sum stays serial
       const int cnt = n - take < 8 ? n - take : 8;
-      double c[9];
+      double c[9], lowest = 0.0;
       c[0] = cum;
 #pragma unroll
-      for (int i = 0; i < 8; i++) c[i + 1] = c[i] + (i < cnt ? s_ba[take + i] : 0.0);
+      for (int i = 0; i < 8; i++) {
+        const double v = i < cnt ? s_ba[take + i] : 0.0;
+        lowest = fmin(lowest, v);
+        c[i + 1] = c[i] + v;
+      }
+      // The usual chunk: no negative entry (undo remainders in drained slots are the only ones) and the sum
+      // still below bias_per_step after it — then every prefix is below it too and all eight entries are plain;
+      // only the serial adds remain on the critical path.  Any other chunk is examined entry by entry.
+      if (lowest >= 0.0 && c[8] < bps && c[0] < bps) {
+        cum = c[8];  // entries past cnt added 0.0
+        take += cnt;
+        continue;
+      }
       int first = cnt;
 #pragma unroll
       for (int i = 7; i >= 0; i--) {
@@ -1001,9 +1135,12 @@ __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasD
       take += first;
       stop = first < cnt;
     }
-    if (st->log_n + take > prm.log_cap) take = 0;
+    if (log_n + take > prm.log_cap) take = 0;
     s_take = take;
     s_nb = nb;
+    s_base = log_n;
+    s_steps = steps;
+    s_cov = cum_bias / prm.total_volume;
     if (take > 0) {
       st->temp_hill_cum = cum;
       st->hills_added = take;
@@ -1012,7 +1149,16 @@ __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasD
       if (take >= nb)
         st->left = st->right = 0;
       else
-        st->left += take;
+        st->left = left + take;
+      st->log_n = log_n + take;
+      if (take == n) {  // post_add_hill; otherwise the in-order kernel finishes the round
+        st->cum_bias = cum_bias + cum;
+        st->steps = steps + 1;
+        st->round_mode = 2;
+        st->rounds_parallel++;
+      } else {
+        st->round_mode = 3;
+      }
     } else {
       st->round_mode = 0;
       st->n_fast = 0;
@@ -1021,12 +1167,12 @@ __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasD
   __syncthreads();
   const int take = s_take;
   if (take == 0) return;
-  const double cov = st->cum_bias / prm.total_volume;
-  const int base = st->log_n;
-  const long long steps = st->steps;
+  const double cov = s_cov;
+  const int base = s_base;
+  const long long steps_now = s_steps;
   for (int k = threadIdx.x; k < take; k += blockDim.x) {
     edm_hill_event_t& e = log[base + k];
-    e.steps = steps;
+    e.steps = steps_now;
     e.type = k < s_nb ? 'b' : 'h';
     e.hills_added = k + 1;
     double pos[DIM];
@@ -1040,23 +1186,17 @@ __device__ void round_decide(const GridDesc& hist, const RoundParams& prm, BiasD
     e.cum_over_vol = cov;
     d_hist_bump<DIM, true>(hist, pos, 1.0);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    st->log_n = base + take;
-    if (take == n) {  // post_add_hill; otherwise the in-order kernel finishes the round
-      st->cum_bias += st->temp_hill_cum;
-      st->steps++;
-      st->round_mode = 2;
-      st->rounds_parallel++;
-    } else {
-      st->round_mode = 3;
-    }
-  }
 }
 
-__global__ void reset_mode_kernel(BiasDev* st) { st->round_mode = 0; }
+__global__ void reset_mode_kernel(BiasDev* st) {
+  pdl_trigger();
+  pdl_wait();
+  st->round_mode = 0;
+}
 
 __global__ void reset_accepted_kernel(BiasDev* st) {
+  pdl_trigger();
+  pdl_wait();
   st->n_accepted = 0;
   st->accepted_overflow = 0;
   st->accepted_sorted = 0;
@@ -1065,6 +1205,8 @@ __global__ void reset_accepted_kernel(BiasDev* st) {
 // hill exchange blocks: double[0] = count, then `count` centres of DIM doubles (key order)
 template <int DIM>
 __global__ void pack_block_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* tmp, double* block, long cap) {
+  pdl_trigger();
+  pdl_wait();
   int n = st->n_accepted;
   if (n > cap) {  // never drop hills silently: edm_bias_check / the next host-synchronising call reports it
     if (threadIdx.x == 0) st->accepted_overflow = 1;
@@ -1161,7 +1303,7 @@ int edm_bias_size_accepted(edm_bias* b, double candidates, long long est) {
 
 int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st) {
   count_launches(1);
-  reset_accepted_kernel<<<1, 1, 0, st>>>(b->d_state);
+  EDM_CUDA(launch_pdl(reset_accepted_kernel, dim3(1), dim3(1), 0, st, b->d_state));
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
@@ -1200,12 +1342,13 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     int4* cells_folded = reinterpret_cast<int4*>(b->fast.as<char>() + b_dbl + b_plan + b_cells + b_terms + b_tj);
     int* ndep = reinterpret_cast<int*>(b->fast.as<char>() + b_dbl + b_plan + 2 * b_cells + b_terms + b_tj);
     // one cluster of kPlanCtas CTAs (compile-time __cluster_dims__)
-    round_plan_kernel<DIM><<<kPlanCtas, 512, 0, st>>>(bias, target, rp, (int)n_max, b->d_state, b->d_accepted, tmp,
-                                                       centres, heights, plan, cells, cells_folded, ndep, terms, term_j,
-                                                       term_cap, blocks, b->round_nblocks, b->round_block_cap);
-    const long nsm4 = 4L * sm_count(b->device);
-    const int nblk = (int)(n_max < nsm4 ? n_max : nsm4);
-    round_integrals_kernel<DIM><<<nblk, 512, 0, st>>>(bias, hist, rp, b->d_state, centres, heights, ba, b->d_log);
+    EDM_CUDA(launch_pdl(round_plan_kernel<DIM>, dim3(kPlanCtas), dim3(512), 0, st, bias, target, rp, (int)n_max, b->d_state,
+                        b->d_accepted, tmp, centres, heights, plan, cells, cells_folded, ndep, terms, term_j, term_cap,
+                        blocks, b->round_nblocks, b->round_block_cap));
+    const long nsm2 = 2L * sm_count(b->device);  // two CTAs per SM are resident: more would only queue
+    const int nblk = (int)(n_max < nsm2 ? n_max : nsm2);
+    EDM_CUDA(launch_pdl(round_integrals_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, hist, rp, b->d_state,
+                        (const double*)centres, (const double*)heights, ba, b->d_log));
     count_launches(2);
     // everything so far only read the grid; whoever else still reads it (this step's force update on
     // another stream) must be done before the first write
@@ -1219,7 +1362,8 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
       EDM_TRY(deposit1d_stage(b->bias, centres, heights, nullptr, &b->d_state->n_fast, n_max, st));
       EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
     } else {
-      round_deposit_kernel<DIM><<<nblk, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
+      EDM_CUDA(launch_pdl(round_deposit_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, b->d_state, (const double*)centres,
+                          (const double*)heights, (const int4*)cells, b->bias->d_flags));
       count_launches(1);
       if (bias.n_dup) {
         EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
@@ -1227,7 +1371,7 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
       }
     }
   } else {
-    reset_mode_kernel<<<1, 1, 0, st>>>(b->d_state);
+    EDM_CUDA(launch_pdl(reset_mode_kernel, dim3(1), dim3(1), 0, st, b->d_state));
     count_launches(1);
   }
   count_launches(1);
@@ -1235,7 +1379,8 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
     b->round_after = nullptr;
   }
-  hill_round_kernel<DIM><<<1, 512, 0, st>>>(bias, hist, target, rp, b->d_state, b->d_accepted, tmp, b->d_log);
+  EDM_CUDA(launch_pdl(hill_round_kernel<DIM>, dim3(1), dim3(512), 0, st, bias, hist, target, rp, b->d_state, b->d_accepted,
+                      tmp, b->d_log));
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
@@ -1287,9 +1432,9 @@ static int select_launch(edm_bias* b, long n, const double* x, long xs, const do
   if (blocks > 8LL * sm_count(b->device)) blocks = 8LL * sm_count(b->device);
   count_launches(1);
   switch (p.dim) {
-    case 1: select_kernel<1><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
-    case 2: select_kernel<2><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
-    default: select_kernel<3><<<(int)blocks, 256, 0, st>>>(n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap); break;
+    case 1: EDM_CUDA(launch_pdl(select_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, st, n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap)); break;
+    case 2: EDM_CUDA(launch_pdl(select_kernel<2>, dim3((unsigned)blocks), dim3(256), 0, st, n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap)); break;
+    default: EDM_CUDA(launch_pdl(select_kernel<3>, dim3((unsigned)blocks), dim3(256), 0, st, n, x, xs, runiform, mask, apply_mask, thresh, accept_all, key, first_counter, b->d_state, b->d_accepted, b->accepted_cap)); break;
   }
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
@@ -1712,6 +1857,18 @@ int edm_bias_post_add_hill(edm_bias_t* b) {
   return edm_bias_check_round(b);
 }
 
+// %globaltimer stamps of the last hill round in microseconds relative to the plan's first instruction:
+// [0..6] plan phases (start, mode known, order known, entries planned, counts, lists, serial part done),
+// [7,8] decision begin/end, [9,10] first deposit taken / last deposit done, [11,12] in-order kernel begin/end.
+int edm_bias_round_times_us(edm_bias_t* b, double* out13) {
+  EDM_REQUIRE(b && out13, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 13; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
+  return EDM_OK;
+}
+
 int edm_bias_round_info(edm_bias_t* b, long long* parallel, long long* split, long long* in_order) {
   EDM_REQUIRE(b != nullptr, "NULL argument");
   EDM_TRY(ensure_device(b->device));
@@ -1795,9 +1952,9 @@ int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream
   HillAccepted* tmp = b->d_accepted + b->accepted_cap;
   count_launches(1);
   switch (b->prm.dim) {
-    case 1: pack_block_kernel<1><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
-    case 2: pack_block_kernel<2><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
-    default: pack_block_kernel<3><<<1, 512, 0, st>>>(b->d_state, b->d_accepted, tmp, block, cap); break;
+    case 1: EDM_CUDA(launch_pdl(pack_block_kernel<1>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, block, cap)); break;
+    case 2: EDM_CUDA(launch_pdl(pack_block_kernel<2>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, block, cap)); break;
+    default: EDM_CUDA(launch_pdl(pack_block_kernel<3>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, block, cap)); break;
   }
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;

@@ -350,6 +350,8 @@ template <int DIM> __global__ void remap_kernel(GridDesc g, double* x) {
 
 // duplicate_boundary, lib/gaussian_grid.h:571-630 (T13: values only)
 __global__ void dup_boundary_kernel(GridDesc g, int* flags, const int* __restrict__ gate, int want) {
+  pdl_trigger();
+  pdl_wait();
   if (gate && *gate < want) return;
   if (flags[0] == 0) return;
   for (int k = threadIdx.x; k < g.n_dup; k += blockDim.x)
@@ -395,6 +397,8 @@ struct Hill1D {
 __global__ void deposit1d_prepare_kernel(GridDesc g, long n, const int* __restrict__ n_dev,
                                          const double* __restrict__ centres, const double* __restrict__ heights,
                                          Hill1D* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   if (i >= n) return;
@@ -418,6 +422,8 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
                                                               const Hill1D* __restrict__ hills, long chunk, int nslot,
                                                               double* __restrict__ partial,
                                                               double* __restrict__ ba_slots, int* flags) {
+  pdl_trigger();
+  pdl_wait();
   if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
@@ -568,6 +574,8 @@ __global__ void __launch_bounds__(128) deposit1d_owner_kernel(GridDesc g, long n
 
 __global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* __restrict__ partial,
                                         const int* __restrict__ flag, int want) {
+  pdl_trigger();
+  pdl_wait();
   if (flag && *flag < want) return;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= g.n[0]) return;
@@ -587,6 +595,8 @@ __global__ void deposit1d_commit_kernel(GridDesc g, int nchunks, const double* _
 
 __global__ void deposit1d_ba_kernel(long n, const int* __restrict__ n_dev, int nslot,
                                     const double* __restrict__ ba_slots, double* __restrict__ ba) {
+  pdl_trigger();
+  pdl_wait();
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n_dev) n = (*n_dev < n) ? *n_dev : n;
   if (i >= n) return;
@@ -624,13 +634,16 @@ int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, d
   double* partial = reinterpret_cast<double*>(basep + b_h);
   double* slots = reinterpret_cast<double*>(basep + b_h + b_p);
   if (ba) EDM_CUDA(cudaMemsetAsync(slots, 0, b_s, st));
-  deposit1d_prepare_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(d, n_max, n_dev, centres, heights, hl);
+  EDM_CUDA(launch_pdl(deposit1d_prepare_kernel, dim3((unsigned)((n_max + 255) / 256)), dim3(256), 0, st, d, n_max, n_dev,
+                      centres, heights, hl));
   long chunk = (n_max + 31) / 32 * 32;
   dim3 grid((nwarps + 3) / 4, 1);
   if (d.periodic[0])
-    deposit1d_owner_kernel<true><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
+    EDM_CUDA(launch_pdl(deposit1d_owner_kernel<true>, grid, dim3(128), 0, st, d, n_max, n_dev, (const Hill1D*)hl, chunk, nslot,
+                        partial, slots, g->d_flags));
   else
-    deposit1d_owner_kernel<false><<<grid, 128, 0, st>>>(d, n_max, n_dev, hl, chunk, nslot, partial, slots, g->d_flags);
+    EDM_CUDA(launch_pdl(deposit1d_owner_kernel<false>, grid, dim3(128), 0, st, d, n_max, n_dev, (const Hill1D*)hl, chunk, nslot,
+                        partial, slots, g->d_flags));
   if (ba) deposit1d_ba_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, st>>>(n_max, n_dev, nslot, slots, ba);
   g->stage_partial = partial;
   count_launches(ba ? 3 : 2);
@@ -641,10 +654,11 @@ int deposit1d_stage(edm_grid* g, const double* centres, const double* heights, d
 int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st) {
   const GridDesc& d = g->d;
   const int npts = d.n[0];
-  deposit1d_commit_kernel<<<(npts + 255) / 256, 256, 0, st>>>(d, 1, g->stage_partial, flag, want);
+  EDM_CUDA(launch_pdl(deposit1d_commit_kernel, dim3((npts + 255) / 256), dim3(256), 0, st, d, 1, (const double*)g->stage_partial,
+                      flag, want));
   count_launches(1);
   if (d.n_dup) {
-    dup_boundary_kernel<<<1, 64, 0, st>>>(d, g->d_flags, flag, want);
+    EDM_CUDA(launch_pdl(dup_boundary_kernel, dim3(1), dim3(64), 0, st, d, g->d_flags, flag, want));
     count_launches(1);
   }
   EDM_CUDA(cudaGetLastError());

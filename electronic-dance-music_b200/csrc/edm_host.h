@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/edm_b200.h"
@@ -46,6 +47,26 @@ int deposit1d_commit_if(edm_grid* g, const int* flag, int want, cudaStream_t st)
 // duplicate_boundary (lib/gaussian_grid.h:571-630) after a batch of hills, only if *gate == want
 int edm_grid_dup_boundary_if(edm_grid* g, const int* gate, int want, cudaStream_t st);
 void count_launches(int n);
+
+// Programmatic dependent launch (sm_90+): the kernel may be scheduled while its predecessor in the stream is still
+// running and waits at pdl_wait() — the launch latency (several microseconds between the hill round's small
+// dependent kernels) overlaps with the predecessor instead of following it.  Kernels launched this way call
+// pdl_trigger() first thing (their own successor may be staged at once) and pdl_wait() before they touch anything
+// a predecessor wrote; both are no-ops under an ordinary <<<>>> launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // Device scratch that grows on demand and is reused across calls (no allocation on the steady
 // per-step path once sizes settle).
@@ -99,6 +120,8 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   int rounds_parallel, rounds_split, rounds_in_order;  // how the rounds so far ran (edm_bias_round_info)
   int ticket;      // next hill a CTA of the parallel deposit takes
   int int_done;    // CTAs of round_integrals_kernel that signed off (the last one takes the decision)
+  // %globaltimer stamps of the last round (ns): plan phases 0-6, decide begin/end, deposit first/last, in-order begin/end
+  unsigned long long stamp[16];
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   unsigned long long n_pairs;
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array

@@ -325,6 +325,11 @@ int edm_bias_profile_pair_ms(edm_bias_t* b, double* search_ms, double* eval_ms);
  * first copy to the later of the two ends.  Outputs may be NULL. */
 int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, double* f_down_ms, double* span_ms);
 
+/* Device-clock (%globaltimer) stamps of the last hill round, microseconds since the plan kernel began:
+ * [0..6] plan phases, [7,8] decision begin/end, [9,10] first deposit taken / last deposit done,
+ * [11,12] in-order kernel begin/end.  Synchronises on a small copy. */
+int edm_bias_round_times_us(edm_bias_t* b, double* out13);
+
 /* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
  * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,
  * the rest of the round hill by hill.  `in_order`: pre_add_hill / add_hill / post_add_hill walked
