@@ -766,10 +766,9 @@ def run_coord(args, rank, local_rank, world):
             sst = side.cuda_stream
             edm.check(L.edm_bias_select_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, est_total, seed, step,
                                             rank * n_atoms, sst))
-            edm.check(L.edm_bias_round_after(bias.h, ev_k1.cuda_event))   # the deposit waits for the force update
+            # the round's writers (deposit, tail) follow the force update on the main stream: nothing to join
+            edm.check(L.edm_bias_round_commit_on(bias.h, main.cuda_stream))
             edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, sst))
-            ev_join.record(side)
-        main.wait_event(ev_join)
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -792,6 +791,7 @@ def run_coord(args, rank, local_rank, world):
     barrier()
     launches = edm.launch_count() - launches0
     info1 = bias.round_info()
+    stamps_fused = bias.round_times_us()       # device-clock stamps of the last overlapped step
     total_ms = float(sum(e[0].elapsed_time(e[1]) for e in ev))
     # the two halves one after the other, for the breakdown only
     evb = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(5)]
@@ -858,7 +858,11 @@ def run_coord(args, rank, local_rank, world):
             "step_breakdown_ms": {"update_forces": k1, "hill_round": rnd,
                                   "note": "measured back to back; in the timed step the round's selection, exchange, plan, "
                                           "integrals and decision run beside update_forces on a second stream"},
-            "round_stamps_us": [round(float(v), 2) for v in bias.round_times_us()],
+            "round_stamps_us": {
+                "legend": "us since the plan began: [0-6] plan phases, [7,8] decision, [9,10] first deposit taken / last "
+                          "deposit done, [11,12] in-order kernel begin/end, [13] force update finished, [14] force update began",
+                "overlapped_step": [round(float(v), 2) for v in stamps_fused],
+                "back_to_back": [round(float(v), 2) for v in bias.round_times_us()]},
             "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],
                       "rounds_split": info1["split"] - info0["split"],
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},

@@ -65,6 +65,7 @@ HOST_LIB = os.path.join(LIBDIR, "libedm.so")
 HOST_TEST = os.path.join(LIBDIR, "edm_host_test")
 FIX_DRIVER = os.path.join(LIBDIR, "fix_driver_test")
 EXCHANGE_TEST = os.path.join(LIBDIR, "exchange_test")
+TEXT_IO_DRIVER = os.path.join(LIBDIR, "text_io_driver")
 CXX = "/usr/bin/g++"
 CXXFLAGS = ["-std=c++11", "-O2", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare"]
 
@@ -103,6 +104,12 @@ def build_host_tests(force=False):
     if force or _stale(EXCHANGE_TEST, [xt_src, HOST_LIB]):
         subprocess.check_call([CXX] + CXXFLAGS + ["-pthread", "-I" + HERE, "-o", EXCHANGE_TEST, xt_src,
                                                   "-L" + LIBDIR, "-ledm", "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
+    # the text-I/O driver against this repo's EDM:: classes (the same source is linked against the unmodified
+    # reference by oracle/Makefile `text` to produce the golden files)
+    td_src = os.path.join(HERE, "tests_host", "text_io_driver.cpp")
+    if force or _stale(TEXT_IO_DRIVER, [td_src, HOST_LIB]):
+        subprocess.check_call([CXX] + CXXFLAGS + ["-I" + edm_dir, "-o", TEXT_IO_DRIVER, td_src, "-L" + LIBDIR, "-ledm",
+                                                  "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_TEST
 
 

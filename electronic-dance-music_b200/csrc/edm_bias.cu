@@ -32,9 +32,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 template <int DIM>
 __global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) forces_kernel(GridDesc g, long n, const double* __restrict__ x, long xs,
                                                      double* __restrict__ f, long fs, const int* __restrict__ mask,
-                                                     int apply_mask, double* __restrict__ partial) {
+                                                     int apply_mask, double* __restrict__ partial, BiasDev* st) {
   __shared__ double red[33];
   constexpr int U = EDM_FORCES_UNROLL;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->stamp[14] = global_ns();  // measurement: when the force update began
   double e = 0.0;
   const long stride = (long)gridDim.x * blockDim.x;
   for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
@@ -68,8 +69,9 @@ __global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) forces_kernel(GridDes
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
-__global__ void sum_partials_kernel(int n, const double* __restrict__ partial, double* out) {
+__global__ void sum_partials_kernel(int n, const double* __restrict__ partial, double* out, BiasDev* st) {
   __shared__ double red[33];
+  if (st && threadIdx.x == 0) st->stamp[13] = global_ns();  // measurement: the force update has just finished
   double e = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) e += partial[i];
   double tot = block_sum(e, red);
@@ -1308,6 +1310,26 @@ int edm_bias_reset_accepted(edm_bias* b, cudaStream_t st) {
   return EDM_OK;
 }
 
+// One-shots set by edm_bias_round_commit_on / edm_bias_round_after: from here on the round writes the grid.
+static int round_switch_to_commit_stream(edm_bias* b, cudaStream_t& st, bool& moved) {
+  moved = false;
+  if (b->commit_stream_set) {
+    b->commit_stream_set = 0;
+    if (b->commit_stream != st) {
+      if (!b->ev_round_ready) EDM_CUDA(cudaEventCreateWithFlags(&b->ev_round_ready, cudaEventDisableTiming));
+      EDM_CUDA(cudaEventRecord(b->ev_round_ready, st));
+      EDM_CUDA(cudaStreamWaitEvent(b->commit_stream, b->ev_round_ready, 0));
+      st = b->commit_stream;
+      moved = true;
+    }
+  }
+  if (b->round_after) {
+    EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
+    b->round_after = nullptr;
+  }
+  return EDM_OK;
+}
+
 template <int DIM>
 static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& hist, const GridDesc& target,
                             bool fast, cudaStream_t st) {
@@ -1350,20 +1372,24 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     EDM_CUDA(launch_pdl(round_integrals_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, hist, rp, b->d_state,
                         (const double*)centres, (const double*)heights, ba, b->d_log));
     count_launches(2);
-    // everything so far only read the grid; whoever else still reads it (this step's force update on
-    // another stream) must be done before the first write
-    if (b->round_after) {
-      EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
-      b->round_after = nullptr;
-    }
-    if (DIM == 1 && deposit1d_eligible(b->bias)) {
-      // owner-computes deposit of hills [0, n_fast): staged from the stored values, written back if the
-      // round was committed (n_fast = 0 stages the stored values themselves)
-      EDM_TRY(deposit1d_stage(b->bias, centres, heights, nullptr, &b->d_state->n_fast, n_max, st));
+    const bool one_d = DIM == 1 && deposit1d_eligible(b->bias);
+    // owner-computes deposit of hills [0, n_fast) in 1-D: staged from the stored values into scratch (reads the
+    // grid only), written back below if the round was committed (n_fast = 0 stages the stored values themselves)
+    if (one_d) EDM_TRY(deposit1d_stage(b->bias, centres, heights, nullptr, &b->d_state->n_fast, n_max, st));
+    // Everything so far only read the grid.  What follows writes it, so whoever else still reads it (this step's
+    // force update) must be done first: either the writers move to the stream the force update runs on
+    // (commit_stream: they simply follow it there, no cross-stream wake-up on the critical path; the read-only
+    // part is linked in by an event that has long fired by then), or this stream waits for the caller's event.
+    bool moved = false;
+    EDM_TRY(round_switch_to_commit_stream(b, st, moved));
+    if (one_d) {
       EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
     } else {
-      EDM_CUDA(launch_pdl(round_deposit_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, b->d_state, (const double*)centres,
-                          (const double*)heights, (const int4*)cells, b->bias->d_flags));
+      if (moved)  // behind a long force update: launched plainly, or its whole grid would sit resident next to it
+        round_deposit_kernel<DIM><<<nblk, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
+      else
+        EDM_CUDA(launch_pdl(round_deposit_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, b->d_state,
+                            (const double*)centres, (const double*)heights, (const int4*)cells, b->bias->d_flags));
       count_launches(1);
       if (bias.n_dup) {
         EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
@@ -1375,9 +1401,9 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     count_launches(1);
   }
   count_launches(1);
-  if (b->round_after) {  // the in-order kernel writes the grid as well
-    EDM_CUDA(cudaStreamWaitEvent(st, b->round_after, 0));
-    b->round_after = nullptr;
+  {  // the in-order kernel writes the grid as well (a no-op if the fast branch above already switched)
+    bool moved = false;
+    EDM_TRY(round_switch_to_commit_stream(b, st, moved));
   }
   EDM_CUDA(launch_pdl(hill_round_kernel<DIM>, dim3(1), dim3(512), 0, st, bias, hist, target, rp, b->d_state, b->d_accepted,
                       tmp, b->d_log));
@@ -1490,6 +1516,7 @@ int edm_bias_destroy(edm_bias_t* b) {
   b->cand.release();
   if (b->h_pair_flags) cudaFreeHost((void*)b->h_pair_flags);
   if (b->ev_prev) cudaEventDestroy(b->ev_prev);
+  if (b->ev_round_ready) cudaEventDestroy(b->ev_round_ready);
   for (int i = 0; i < 5; i++)
     if (b->ev_e2e[i]) cudaEventDestroy(b->ev_e2e[i]);
   if (b->st_main) cudaStreamDestroy(b->st_main);
@@ -1595,9 +1622,9 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
   const GridDesc& g = b->bias->d;
   count_launches(energy ? 2 : 1);
   switch (b->prm.dim) {
-    case 1: forces_kernel<1><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
-    case 2: forces_kernel<2><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
-    default: forces_kernel<3><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial); break;
+    case 1: forces_kernel<1><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial, b->d_state); break;
+    case 2: forces_kernel<2><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial, b->d_state); break;
+    default: forces_kernel<3><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial, b->d_state); break;
   }
   EDM_CUDA(cudaGetLastError());
   if (b->forces_event) {  // one-shot: "the force update has read the grid" (before the energy sum)
@@ -1605,7 +1632,7 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
     b->forces_event = nullptr;
   }
   if (energy) {
-    sum_partials_kernel<<<1, 1024, 0, st>>>((int)blocks, b->d_energy_partial, energy);
+    sum_partials_kernel<<<1, 1024, 0, st>>>((int)blocks, b->d_energy_partial, energy, b->d_state);
     EDM_CUDA(cudaGetLastError());
   }
   return EDM_OK;
@@ -1734,6 +1761,13 @@ int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride,
   return edm_bias_launch_round(b, est, st);
 }
 
+int edm_bias_round_commit_on(edm_bias_t* b, void* stream) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  b->commit_stream = (cudaStream_t)stream;
+  b->commit_stream_set = 1;
+  return EDM_OK;
+}
+
 int edm_bias_round_after(edm_bias_t* b, void* event) {
   EDM_REQUIRE(b != nullptr, "NULL argument");
   b->round_after = (cudaEvent_t)event;
@@ -1772,10 +1806,10 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
   EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
   EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, est, seed, step, 0, b->st_side));
-  b->round_after = b->ev_forces;
+  // the round's writers (deposit, in-order tail) follow the force update on the caller's stream; nothing to join
+  b->commit_stream = st;
+  b->commit_stream_set = 1;
   EDM_TRY(edm_bias_launch_round(b, est, b->st_side));
-  EDM_CUDA(cudaEventRecord(b->ev_join, b->st_side));
-  EDM_CUDA(cudaStreamWaitEvent(st, b->ev_join, 0));
   return EDM_OK;
 }
 
@@ -1865,7 +1899,7 @@ int edm_bias_round_times_us(edm_bias_t* b, double* out13) {
   EDM_TRY(ensure_device(b->device));
   BiasDev hdr;
   EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 13; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
+  for (int i = 0; i < 15; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
   return EDM_OK;
 }
 

@@ -197,6 +197,10 @@ struct edm_bias {
   cudaStream_t st_side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_forces = nullptr, ev_join = nullptr;
   cudaEvent_t round_after = nullptr;  // borrowed, one-shot: the next round's first grid write waits for it
+  // one-shot (edm_bias_round_commit_on): the next round's grid-writing kernels go to this stream
+  cudaStream_t commit_stream = nullptr;
+  int commit_stream_set = 0;
+  cudaEvent_t ev_round_ready = nullptr;  // the round's read-only part is done
   cudaEvent_t forces_event = nullptr; // one-shot: recorded right after the next forces_kernel launch
   // one-shot: the next round takes its candidates from these exchange blocks (the plan unpacks them itself)
   const double* round_blocks = nullptr;

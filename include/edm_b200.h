@@ -258,6 +258,12 @@ int edm_pair_select_cells_dev(edm_bias_t* b, long natoms, const double* x, doubl
 int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream);
 int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, long cap,
                               long long est_hill_count, void* stream);
+/* One-shot, preferred over edm_bias_round_after: the next hill round launched for `b` puts its grid-WRITING
+ * kernels (deposit, in-order tail) on `stream` — behind whatever is already enqueued there, i.e. this step's
+ * force update — and only its read-only part (unpack, plan, integrals, decision) on the stream it was launched
+ * on; the two are linked by an internal event.  The round is complete when `stream` is: no join needed, and
+ * nothing wakes up across streams on the critical path force update -> deposit -> next force update. */
+int edm_bias_round_commit_on(edm_bias_t* b, void* stream);
 /* One-shot: the next hill round launched for `b` (add_hills_dev, hills_commit_dev, ...) waits for `event`
  * (a cudaEvent_t) right before its first write to the bias grid.  Lets a caller run selection, exchange
  * and the round's read-only kernels on a second stream while this step's force update, recorded by
@@ -327,8 +333,9 @@ int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, 
 
 /* Device-clock (%globaltimer) stamps of the last hill round, microseconds since the plan kernel began:
  * [0..6] plan phases, [7,8] decision begin/end, [9,10] first deposit taken / last deposit done,
- * [11,12] in-order kernel begin/end.  Synchronises on a small copy. */
-int edm_bias_round_times_us(edm_bias_t* b, double* out13);
+ * [11,12] in-order kernel begin/end, [13] the last force update finished, [14] the last force update began.
+ * out holds 15 doubles.  Synchronises on a small copy. */
+int edm_bias_round_times_us(edm_bias_t* b, double* out15);
 
 /* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
  * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,
