@@ -760,7 +760,7 @@ def run_coord(args, rank, local_rank, world):
         main = torch.cuda.current_stream()
         ev_fork.record(main)
         side.wait_event(ev_fork)
-        forces(step)
+        edm.check(L.edm_bias_update_forces_dev(bias.h, n_atoms, x.data_ptr(), D, f_dev.data_ptr(), D, None, -1, None, stream))
         ev_k1.record(main)
         with torch.cuda.stream(side):
             sst = side.cuda_stream
@@ -769,6 +769,7 @@ def run_coord(args, rank, local_rank, world):
             # the round's writers (deposit, tail) follow the force update on the main stream: nothing to join
             edm.check(L.edm_bias_round_commit_on(bias.h, main.cuda_stream))
             edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, sst))
+        edm.check(L.edm_bias_energy_dev(bias.h, energy_dev.data_ptr(), stream))   # behind the deposit, off the critical path
 
     clocks = ClockSampler(local_rank)
     clocks.start()

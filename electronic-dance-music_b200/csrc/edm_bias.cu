@@ -1620,7 +1620,7 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
   if (blocks > b->n_partial) blocks = b->n_partial;
   if (blocks < 1) blocks = 1;
   const GridDesc& g = b->bias->d;
-  count_launches(energy ? 2 : 1);
+  count_launches(1);
   switch (b->prm.dim) {
     case 1: forces_kernel<1><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial, b->d_state); break;
     case 2: forces_kernel<2><<<(int)blocks, 256, 0, st>>>(g, n, x, xstride, f, fstride, mask, apply_mask, b->d_energy_partial, b->d_state); break;
@@ -1631,10 +1631,25 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
     EDM_CUDA(cudaEventRecord(b->forces_event, st));
     b->forces_event = nullptr;
   }
+  b->last_partials = (int)blocks;
   if (energy) {
+    count_launches(1);
     sum_partials_kernel<<<1, 1024, 0, st>>>((int)blocks, b->d_energy_partial, energy, b->d_state);
     EDM_CUDA(cudaGetLastError());
   }
+  return EDM_OK;
+}
+
+// The energy of the last edm_bias_update_forces_dev call made with energy = NULL: the per-CTA partials summed in CTA
+// order by a one-CTA kernel.  Lets a caller put that kernel BEHIND the hill deposit instead of between the force update
+// and the deposit, where it would sit on the step's critical path.
+int edm_bias_energy_dev(edm_bias_t* b, double* energy, void* stream) {
+  EDM_REQUIRE(b && energy, "NULL argument");
+  EDM_REQUIRE(b->last_partials > 0, "no force update on record");
+  EDM_TRY(ensure_device(b->device));
+  count_launches(1);
+  sum_partials_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b->last_partials, b->d_energy_partial, energy, nullptr);
+  EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
 
@@ -1797,7 +1812,8 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   EDM_CUDA(cudaEventRecord(b->ev_fork, st));
   EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
   b->forces_event = b->ev_forces;
-  if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, energy, stream));
+  // the energy sum (a one-CTA kernel) goes behind the round's deposit, not between it and the force update
+  if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, nullptr, stream));
   if (b->forces_event) {  // nothing was launched
     EDM_CUDA(cudaEventRecord(b->ev_forces, st));
     b->forces_event = nullptr;
@@ -1810,6 +1826,7 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   b->commit_stream = st;
   b->commit_stream_set = 1;
   EDM_TRY(edm_bias_launch_round(b, est, b->st_side));
+  if (energy && n > 0) EDM_TRY(edm_bias_energy_dev(b, energy, stream));
   return EDM_OK;
 }
 

@@ -932,7 +932,11 @@ static int eval_launch(const edm_grid* g, long n, const double* x, long xs, doub
                        cudaStream_t st) {
   if (n <= 0) return EDM_OK;
   count_launches(1);
-  const GridDesc& d = g->d;
+  GridDesc d = g->d;
+  if (mode == 2) {  // the plain grid inside a GaussGrid: no boundary test, no remap (lib/grid.h:390-446 only)
+    d.is_gauss = 0;
+    mode = 0;
+  }
   int blocks = launch_blocks(n, 256);
   switch (d.dim) {
     case 1: eval_kernel<1><<<blocks, 256, 0, st>>>(d, n, x, xs, val, der, mode); break;
@@ -975,6 +979,9 @@ int edm_grid_eval(const edm_grid_t* g, long n, const double* x, long xstride, do
 }
 int edm_grid_get_value(const edm_grid_t* g, long n, const double* x, long xstride, double* value) {
   return eval_host(g, n, x, xstride, value, nullptr, 1);
+}
+int edm_grid_eval_plain(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der) {
+  return eval_host(g, n, x, xstride, value, der, 2);
 }
 
 int edm_grid_hist_add(edm_grid_t* g, long n, const double* x, long xs, const double* v) {

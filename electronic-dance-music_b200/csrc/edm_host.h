@@ -124,6 +124,7 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   unsigned long long stamp[16];
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   unsigned long long n_pairs;
+  unsigned long long n_pairs_ghost;  // of those, pairs with one ghost atom (one hill proposal instead of two)
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
   int hill_done[EDM_ROUND_MAX];          // parallel deposit: hill k finished in round hill_done[k]
 };
@@ -156,6 +157,7 @@ struct edm_bias {
   long log_cap = 0;
   double* d_energy_partial = nullptr;  // per-CTA energy partials
   int n_partial = 0;
+  int last_partials = 0;               // CTAs (= partials) of the last force update
   double* d_scalar = nullptr;          // [0] energy
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels

@@ -13,7 +13,9 @@ namespace edm {
 struct CellGrid {
   int nc[3];
   double cs[3];
-  double box[3];
+  double box[3];   // extent of the cell grid per dimension (the period, in periodic dimensions)
+  double lo[3];    // its lower corner
+  int periodic[3]; // 0: the cell grid ends there — whatever lies beyond reaches this rank as ghost atoms
   int ncell;
 };
 
@@ -28,6 +30,7 @@ struct PairParams {
   double rc2;
   float rc2m;  // fp32 prefilter radius^2: cutoff^2 enlarged by 1e-4 (the fp32 error is ~1e-5 absolute)
   long natoms;
+  long nlocal;  // atoms [nlocal, natoms) are ghosts: no force, one hill proposal, ghost-ghost pairs skipped
   long acc_cap;
 };
 
@@ -40,9 +43,9 @@ __global__ void cell_count_kernel(long n, const double* __restrict__ x, CellGrid
                                   int* __restrict__ count) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int cx = cell_coord(x[3 * i + 0], cg.cs[0], cg.nc[0]);
-  int cy = cell_coord(x[3 * i + 1], cg.cs[1], cg.nc[1]);
-  int cz = cell_coord(x[3 * i + 2], cg.cs[2], cg.nc[2]);
+  int cx = cell_coord(x[3 * i + 0] - cg.lo[0], cg.cs[0], cg.nc[0]);
+  int cy = cell_coord(x[3 * i + 1] - cg.lo[1], cg.cs[1], cg.nc[1]);
+  int cz = cell_coord(x[3 * i + 2] - cg.lo[2], cg.cs[2], cg.nc[2]);
   int c = (cz * cg.nc[1] + cy) * cg.nc[0] + cx;
   cell_of[i] = c;
   atomicAdd(&count[c], 1);
@@ -167,10 +170,10 @@ __device__ __forceinline__ double pair_eval_fast(const GridDesc& g, const double
 
 // hill proposals of one pair; the exactly rounded sqrt is taken only for an accepted proposal
 __device__ __forceinline__ void propose_hills_d2(const PairParams& pp, unsigned long long pairkey, double d2,
-                                                 BiasDev* st, HillAccepted* acc) {
+                                                 BiasDev* st, HillAccepted* acc, int nprop = 2) {
   const uint64_t bits = pair_bits(pp.key, pairkey);
   const bool t0 = pp.accept_all || (bits >> 32) < pp.thresh_bits;
-  const bool t1 = pp.accept_all || (bits & 0xffffffffULL) < pp.thresh_bits;
+  const bool t1 = nprop > 1 && (pp.accept_all || (bits & 0xffffffffULL) < pp.thresh_bits);
   if (t0 || t1) {
     const double r = sqrt(d2);
 #pragma unroll
@@ -222,8 +225,8 @@ __global__ void cell_rank_gather_kernel(long n, CellGrid cg, const int* __restri
   for (int a = lo; a < hi; a++) rank += (order[a] < (int)i);
   const long s = lo + rank;
   const double px = x[3 * i + 0], py = x[3 * i + 1], pz = x[3 * i + 2];
-  const double cx = (c % cg.nc[0]) * cg.cs[0], cy = ((c / cg.nc[0]) % cg.nc[1]) * cg.cs[1];
-  const double cz = (c / (cg.nc[0] * cg.nc[1])) * cg.cs[2];
+  const double cx = cg.lo[0] + (c % cg.nc[0]) * cg.cs[0], cy = cg.lo[1] + ((c / cg.nc[0]) % cg.nc[1]) * cg.cs[1];
+  const double cz = cg.lo[2] + (c / (cg.nc[0] * cg.nc[1])) * cg.cs[2];
   AtomRec r;
   r.x = px;
   r.y = py;
@@ -297,6 +300,10 @@ __device__ __forceinline__ bool pair_exact(const PairCtx& c, const AtomRec& ri, 
   }
   const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
   if (!(d2 < c.pp.rc2)) return false;
+  // lammps/fix_edm_pair.cpp:177 loops over LOCAL atoms i only: a pair of two ghosts is not in the list; a pair with
+  // one ghost is, once (from its local atom): no force on the ghost (:223), one hill proposal instead of two (:233)
+  const bool gi = (ri.tag & 0xffffffffLL) >= c.pp.nlocal, gj = (rj.tag & 0xffffffffLL) >= c.pp.nlocal;
+  if (gi && gj) return false;
   const double rinv = rsqrt(d2);
   const double r = d2 * rinv;  // within 2 ulp of sqrt(d2): enough for V(r); hills take the exact root
   double force;
@@ -305,10 +312,11 @@ __device__ __forceinline__ bool pair_exact(const PairCtx& c, const AtomRec& ri, 
   px = dx * s;
   py = dy * s;
   pz = dz * s;
+  if (gi || gj) atomicAdd(&c.st->n_pairs_ghost, 1ULL);  // rare (halo pairs only)
   if (c.pp.do_hills) {
     const unsigned long long oi = (unsigned long long)(ri.tag & 0xffffffffLL), oj = (unsigned long long)(rj.tag & 0xffffffffLL);
     const unsigned long long lo = oi < oj ? oi : oj, hi = oi < oj ? oj : oi;
-    propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc);
+    propose_hills_d2(c.pp, lo * (unsigned long long)c.pp.natoms + hi, d2, c.st, c.acc, (gi || gj) ? 1 : 2);
   }
   return true;
 }
@@ -359,9 +367,10 @@ __global__ void __launch_bounds__(128) pair_direct_kernel(const __grid_constant_
     const AtomRec ri = c.arec[a];
     const int ti = __float_as_int(c.xs32[a].w);
     if (pp.use_types && ti != pp.itype && ti != pp.jtype) continue;
-    const int cx = cell_coord(ri.x, cg.cs[0], cg.nc[0]);
-    const int cy = cell_coord(ri.y, cg.cs[1], cg.nc[1]);
-    const int cz = cell_coord(ri.z, cg.cs[2], cg.nc[2]);
+    const int cx = cell_coord(ri.x - cg.lo[0], cg.cs[0], cg.nc[0]);
+    const int cy = cell_coord(ri.y - cg.lo[1], cg.cs[1], cg.nc[1]);
+    const int cz = cell_coord(ri.z - cg.lo[2], cg.cs[2], cg.nc[2]);
+    const bool ghost_i = (ri.tag & 0xffffffffLL) >= pp.nlocal;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for (int nb = 0; nb < 14; nb++) {
       // nb 0 = own cell; 1..13 = offsets with (dz,dy,dx) lexicographically positive
@@ -370,6 +379,8 @@ __global__ void __launch_bounds__(128) pair_direct_kernel(const __grid_constant_
       if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
       if (qy >= cg.nc[1]) { qy -= cg.nc[1]; code |= 4; } else if (qy < 0) { qy += cg.nc[1]; code |= 8; }
       if (qz >= cg.nc[2]) { qz -= cg.nc[2]; code |= 16; } else if (qz < 0) { qz += cg.nc[2]; code |= 32; }
+      // beyond a non-periodic end of the cell grid there is nothing (ghost atoms already sit inside it)
+      if (((code & 3) && !cg.periodic[0]) || ((code & 12) && !cg.periodic[1]) || ((code & 48) && !cg.periodic[2])) continue;
       const int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
       long jlo = c.start[q];
       const long jhi = c.start[q + 1];
@@ -386,14 +397,18 @@ __global__ void __launch_bounds__(128) pair_direct_kernel(const __grid_constant_
         fx += px;
         fy += py;
         fz += pz;
-        atomicAdd(&c.f[3 * rj.tag + 0], -px);
-        atomicAdd(&c.f[3 * rj.tag + 1], -py);
-        atomicAdd(&c.f[3 * rj.tag + 2], -pz);
+        if ((rj.tag & 0xffffffffLL) < pp.nlocal) {
+          atomicAdd(&c.f[3 * rj.tag + 0], -px);
+          atomicAdd(&c.f[3 * rj.tag + 1], -py);
+          atomicAdd(&c.f[3 * rj.tag + 2], -pz);
+        }
       }
     }
-    atomicAdd(&c.f[3 * ri.tag + 0], fx);
-    atomicAdd(&c.f[3 * ri.tag + 1], fy);
-    atomicAdd(&c.f[3 * ri.tag + 2], fz);
+    if (!ghost_i) {
+      atomicAdd(&c.f[3 * ri.tag + 0], fx);
+      atomicAdd(&c.f[3 * ri.tag + 1], fy);
+      atomicAdd(&c.f[3 * ri.tag + 2], fz);
+    }
   }
   double tot = block_sum(e, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
@@ -473,10 +488,12 @@ __device__ __forceinline__ bool region_setup(const CellGrid& cg, const BlockGeom
     if (qx >= cg.nc[0]) { qx -= cg.nc[0]; code |= 1; } else if (qx < 0) { qx += cg.nc[0]; code |= 2; }
     if (qy >= cg.nc[1]) { qy -= cg.nc[1]; code |= 4; } else if (qy < 0) { qy += cg.nc[1]; code |= 8; }
     if (qz >= cg.nc[2]) { qz -= cg.nc[2]; code |= 16; }
+    // beyond a non-periodic end of the cell grid: an empty cell (ghost atoms already sit inside the grid)
+    const bool beyond = ((code & 3) && !cg.periodic[0]) || ((code & 12) && !cg.periodic[1]) || ((code & 48) && !cg.periodic[2]);
     const int q = (qz * cg.nc[1] + qy) * cg.nc[0] + qx;
     const int s0 = start[q];
     R.cslot[rc] = s0;
-    R.cstart[rc] = start[q + 1] - s0;  // count for now
+    R.cstart[rc] = beyond ? 0 : start[q + 1] - s0;  // count for now
     R.ccode[rc] = (unsigned char)code;
   }
   __syncthreads();
@@ -778,8 +795,9 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
     long long q[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) q[k] = ((long long)S.hi[k][l] << 32) + (long long)S.lo[k][l];
-    if (q[0] | q[1] | q[2]) {
-      const long long o = 3 * (__double_as_longlong(S.pb[l].y) & 0xffffffffLL);
+    const long long tag = __double_as_longlong(S.pb[l].y) & 0xffffffffLL;
+    if ((q[0] | q[1] | q[2]) && tag < c.pp.nlocal) {  // a ghost takes no force here: its owner computes the pair too
+      const long long o = 3 * tag;
       atomicAdd(&c.f[o + 0], (double)q[0] * inv_scale);
       atomicAdd(&c.f[o + 1], (double)q[1] * inv_scale);
       atomicAdd(&c.f[o + 2], (double)q[2] * inv_scale);
@@ -810,6 +828,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2) block_eval_kernel(const __gri
 
 __global__ void pair_reset_kernel(BiasDev* st, int* fallback, int fallback_init, unsigned long long* fmax_bits) {
   st->n_pairs = 0;
+  st->n_pairs_ghost = 0;
   *fallback = fallback_init;
   fmax_bits[0] = 0ull;
   fmax_bits[1] = 0ull;
@@ -923,6 +942,7 @@ __global__ void add_forces_kernel(long n, const double* __restrict__ d, double* 
 
 __global__ void reset_pairs_kernel(BiasDev* st, unsigned long long* ncalls) {
   st->n_pairs = 0;
+  st->n_pairs_ghost = 0;
   if (ncalls) *ncalls = 0;
 }
 
@@ -947,7 +967,7 @@ __global__ void step_report_kernel(const BiasDev* st, const double* energy, cons
                                    HostReport* rep) {
   rep->energy = energy ? *energy : 0.0;
   rep->n_pairs = st->n_pairs;
-  rep->n_calls = ncalls ? *ncalls : 2ULL * st->n_pairs;
+  rep->n_calls = ncalls ? *ncalls : 2ULL * st->n_pairs - st->n_pairs_ghost;
   rep->backlog_full = st->backlog_full;
   rep->accepted_overflow = st->accepted_overflow;
   __threadfence_system();
@@ -1028,6 +1048,7 @@ static PairParams pair_params(const edm_bias* b, const int* type, int itype, int
   pp.rc2 = cutoff * cutoff;
   pp.rc2m = (float)(pp.rc2 * 1.0001) + 1e-6f;
   pp.natoms = natoms;
+  pp.nlocal = natoms;  // every atom local unless the caller says otherwise
   pp.acc_cap = b->accepted_cap;
   return pp;
 }
@@ -1071,7 +1092,10 @@ static bool choose_bricks(const CellGrid& cg, long natoms, double cutoff, double
 static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* f, const int* type, int itype,
                              int jtype, const double* box, double cutoff, int do_hills, long long est, uint64_t seed,
                              uint64_t step, double* energy_dev, cudaStream_t st, cudaEvent_t forces_ready = nullptr,
-                             cudaEvent_t forces_done = nullptr) {
+                             cudaEvent_t forces_done = nullptr, const edm_pair_domain_t* dom = nullptr) {
+  // dom == NULL: a periodic box [0, box)^3 with every atom local.  Otherwise one rank's share of a larger system
+  // (LAMMPS' picture): local atoms first, then ghosts, inside [lo, hi); dimensions flagged periodic are wrapped here,
+  // the others end at lo / hi and whatever lies beyond has been handed over as ghost atoms.
   // forces_ready: waited for before the first kernel that touches f (the search before it only reads
   // x); forces_done: recorded once f is final (before any hill work the caller appends)
   EDM_REQUIRE(b->prm.dim == 1, "Pairwise distance must be 1 dimension in EDM input file");  // fix_edm_pair.cpp:52-53
@@ -1082,10 +1106,16 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   CellGrid cg;
   long long ncell = 1;
   for (int d = 0; d < 3; d++) {
-    cg.box[d] = box[d];
-    cg.nc[d] = (int)floor(box[d] / cutoff);
-    EDM_REQUIRE(cg.nc[d] >= 3, "box must hold at least 3 cutoffs per side for the half-shell cell search");
-    cg.cs[d] = box[d] / cg.nc[d];
+    cg.lo[d] = dom ? dom->lo[d] : 0.0;
+    cg.periodic[d] = dom ? (dom->periodic[d] != 0) : 1;
+    cg.box[d] = dom ? dom->hi[d] - dom->lo[d] : box[d];
+    EDM_REQUIRE(cg.box[d] > 0, "empty domain");
+    cg.nc[d] = (int)floor(cg.box[d] / cutoff);
+    if (cg.periodic[d])
+      EDM_REQUIRE(cg.nc[d] >= 3, "box must hold at least 3 cutoffs per side for the half-shell cell search");
+    else if (cg.nc[d] < 1)
+      cg.nc[d] = 1;
+    cg.cs[d] = cg.box[d] / cg.nc[d];
     ncell *= cg.nc[d];
   }
   EDM_REQUIRE(ncell < 2000000000LL, "too many cells");
@@ -1154,6 +1184,10 @@ static int pair_cells_launch(edm_bias* b, long natoms, const double* x, double* 
   ctx.g = b->bias->d;
   ctx.cg = cg;
   ctx.pp = pair_params(b, type, itype, jtype, do_hills, est, seed, step, cutoff, natoms);
+  if (dom) {
+    EDM_REQUIRE(dom->nlocal >= 0 && dom->nlocal <= natoms, "nlocal out of range");
+    ctx.pp.nlocal = dom->nlocal;
+  }
   ctx.start = start;
   ctx.arec = arec;
   ctx.xs32 = xs32;
@@ -1201,7 +1235,9 @@ static int read_pair_result(edm_bias* b, edm_pair_result_t* result, const unsign
   EDM_CUDA(cudaMemcpy(&np, &b->d_state->n_pairs, sizeof(np), cudaMemcpyDeviceToHost));
   result->energy = e;
   result->n_pairs = (long long)np;
-  result->n_calls = 2 * (long long)np;
+  unsigned long long ng = 0;
+  EDM_CUDA(cudaMemcpy(&ng, &b->d_state->n_pairs_ghost, sizeof(ng), cudaMemcpyDeviceToHost));
+  result->n_calls = 2 * (long long)np - (long long)ng;  // a pair with a ghost proposes once, fix_edm_pair.cpp:233
   if (ncalls_dev) {
     unsigned long long nc;
     EDM_CUDA(cudaMemcpy(&nc, ncalls_dev, sizeof(nc), cudaMemcpyDeviceToHost));
@@ -1285,6 +1321,76 @@ int edm_pair_step_cells(edm_bias_t* b, long natoms, const double* x, double* f, 
   count_launches(1);
   if (prof) EDM_CUDA(cudaEventRecord(b->ev_e2e[2], b->st_main));
   b->e2e_valid = prof ? 1 : 0;
+  EDM_CUDA(cudaStreamSynchronize(b->st_main));
+  const int rc = pair_host_result(b, result, do_hills);
+  EDM_CUDA(cudaStreamSynchronize(b->st_copy));
+  return rc;
+}
+
+// ---- one rank's share of a larger system: local atoms + ghosts inside a sub-box (LAMMPS' own picture) ----
+
+int edm_pair_select_cells_domain_dev(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype,
+                                     int jtype, const edm_pair_domain_t* dom, double cutoff, long long est_hill_count,
+                                     uint64_t seed, uint64_t step, double* energy_dev, void* stream) {
+  EDM_REQUIRE(b && x && f && dom, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  EDM_TRY(edm_bias_reset_accepted(b, st));
+  return pair_cells_launch(b, nall, x, f, type, itype, jtype, nullptr, cutoff, 1, est_hill_count, seed, step,
+                           energy_dev ? energy_dev : b->d_scalar, st, nullptr, nullptr, dom);
+}
+
+int edm_pair_step_cells_domain_dev(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype,
+                                   int jtype, const edm_pair_domain_t* dom, double cutoff, int do_hills,
+                                   long long est_hill_count, uint64_t seed, uint64_t step, edm_pair_result_t* result,
+                                   void* stream) {
+  EDM_REQUIRE(b && x && f && dom, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  est_hill_count = edm_job_est(b, est_hill_count);
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, st));
+  EDM_TRY(pair_cells_launch(b, nall, x, f, type, itype, jtype, nullptr, cutoff, do_hills, est_hill_count, seed, step,
+                            b->d_scalar, st, nullptr, nullptr, dom));
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, st));
+  if (result) {
+    EDM_CUDA(cudaStreamSynchronize(st));
+    EDM_TRY(read_pair_result(b, result, nullptr));
+    if (do_hills) EDM_TRY(edm_bias_check_round(b));
+  }
+  return EDM_OK;
+}
+
+int edm_pair_step_cells_domain(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype, int jtype,
+                               const edm_pair_domain_t* dom, double cutoff, int do_hills, long long est_hill_count,
+                               uint64_t seed, uint64_t step, edm_pair_result_t* result) {
+  EDM_REQUIRE(b && x && f && dom && nall > 0, "bad argument");
+  EDM_TRY(ensure_device(b->device));
+  est_hill_count = edm_job_est(b, est_hill_count);
+  EDM_TRY(pair_host_streams(b));
+  const size_t bx = (size_t)nall * 3 * sizeof(double);
+  const size_t bl = (size_t)dom->nlocal * 3 * sizeof(double);  // forces travel for the local atoms only
+  EDM_TRY(b->io.reserve(bx));
+  EDM_TRY(b->io2.reserve(bx));
+  const int* dt = nullptr;
+  if (type) {
+    EDM_TRY(b->io3.reserve((size_t)nall * sizeof(int)));
+    EDM_CUDA(cudaMemcpyAsync(b->io3.p, type, (size_t)nall * sizeof(int), cudaMemcpyHostToDevice, b->st_main));
+    dt = b->io3.as<int>();
+  }
+  EDM_CUDA(cudaMemcpyAsync(b->io.p, x, bx, cudaMemcpyHostToDevice, b->st_main));
+  EDM_CUDA(cudaEventRecord(b->ev_f_final, b->st_main));  // "x is up": the forces follow the positions over the link
+  EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_f_final, 0));
+  if (bl) EDM_CUDA(cudaMemcpyAsync(b->io2.p, f, bl, cudaMemcpyHostToDevice, b->st_copy));
+  EDM_CUDA(cudaEventRecord(b->ev_f_up, b->st_copy));
+  if (do_hills) EDM_TRY(edm_bias_reset_accepted(b, b->st_main));
+  EDM_TRY(pair_cells_launch(b, nall, b->io.as<double>(), b->io2.as<double>(), dt, itype, jtype, nullptr, cutoff, do_hills,
+                            est_hill_count, seed, step, b->d_scalar, b->st_main, b->ev_f_up, b->ev_f_final, dom));
+  EDM_CUDA(cudaStreamWaitEvent(b->st_copy, b->ev_f_final, 0));
+  if (bl) EDM_CUDA(cudaMemcpyAsync(f, b->io2.p, bl, cudaMemcpyDeviceToHost, b->st_copy));
+  if (do_hills) EDM_TRY(edm_bias_launch_round(b, est_hill_count, b->st_main));
+  step_report_kernel<<<1, 1, 0, b->st_main>>>(b->d_state, b->d_scalar, nullptr, reinterpret_cast<HostReport*>(b->d_pair_flags));
+  count_launches(1);
+  b->e2e_valid = 0;
   EDM_CUDA(cudaStreamSynchronize(b->st_main));
   const int rc = pair_host_result(b, result, do_hills);
   EDM_CUDA(cudaStreamSynchronize(b->st_copy));

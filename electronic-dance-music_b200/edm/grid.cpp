@@ -358,7 +358,10 @@ void DimmedGrid<DIM>::multi_write(const std::string& filename, const double* box
       pts[p * DIM + j] = k * dx_[j] + box_min[j];
     }
   }
-  get_value_deriv_batch((long)total, pts.data(), (long)DIM, val.data(), der.data());
+  // the reference evaluates DimmedGrid::get_value_deriv here (lib/grid.h:650-653): the plain grid, even when this
+  // grid sits inside a GaussGrid whose boundary test would return 0 at the upper wall
+  store_.to_device();
+  edm_check(edm_grid_eval_plain(dev_, (long)total, pts.data(), (long)DIM, val.data(), der.data()), "grid.h:multi_write");
   ofstream out(filename.c_str());
   if (!b_lammps_format) {
     out << "#! FORCE " << b_derivatives_ << endl << "#! NVAR " << DIM << endl << "#! TYPE ";

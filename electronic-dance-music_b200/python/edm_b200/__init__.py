@@ -38,6 +38,10 @@ class BiasState(C.Structure):
                 ("backlog_right", C.c_long), ("n_accepted", C.c_long), ("log_dropped", C.c_long)]
 
 
+class PairDomain(C.Structure):
+    _fields_ = [("lo", C.c_double * 3), ("hi", C.c_double * 3), ("periodic", C.c_int * 3), ("nlocal", C.c_long)]
+
+
 class PairResult(C.Structure):
     _fields_ = [("energy", C.c_double), ("n_pairs", C.c_longlong), ("n_calls", C.c_longlong)]
 
@@ -68,6 +72,7 @@ EXPORTS = {
     "edm_grid_clear": (C.c_int, [vp]),
     "edm_grid_eval": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_dp]),
     "edm_grid_eval_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, vp, vp]),
+    "edm_grid_eval_plain": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_dp]),
     "edm_grid_get_value": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp]),
     "edm_grid_hist_add": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp]),
     "edm_grid_add": (C.c_int, [vp, vp, C.c_double, C.c_double]),
@@ -88,6 +93,7 @@ EXPORTS = {
     "edm_bias_step_coords_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, C.c_int, vp,
                                            C.c_uint64, C.c_uint64, vp, vp]),
     "edm_bias_round_after": (C.c_int, [vp, vp]),
+    "edm_bias_energy_dev": (C.c_int, [vp, vp, vp]),
     "edm_bias_round_commit_on": (C.c_int, [vp, vp]),
     "edm_bias_update_forces_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, vp, vp]),
     "edm_bias_add_hills": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_ip, C.c_int, C.c_uint64, C.c_uint64]),
@@ -99,6 +105,13 @@ EXPORTS = {
                                       C.c_longlong, C.c_uint64, C.c_uint64, C.POINTER(PairResult)]),
     "edm_pair_step_cells_dev": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_int, C.c_int, c_dp, C.c_double, C.c_int,
                                           C.c_longlong, C.c_uint64, C.c_uint64, C.POINTER(PairResult), vp]),
+    "edm_pair_step_cells_domain": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_int, C.c_int, C.POINTER(PairDomain), C.c_double,
+                                             C.c_int, C.c_longlong, C.c_uint64, C.c_uint64, C.POINTER(PairResult)]),
+    "edm_pair_step_cells_domain_dev": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_int, C.c_int, C.POINTER(PairDomain),
+                                                 C.c_double, C.c_int, C.c_longlong, C.c_uint64, C.c_uint64,
+                                                 C.POINTER(PairResult), vp]),
+    "edm_pair_select_cells_domain_dev": (C.c_int, [vp, C.c_long, vp, vp, vp, C.c_int, C.c_int, C.POINTER(PairDomain),
+                                                   C.c_double, C.c_longlong, C.c_uint64, C.c_uint64, vp, vp]),
     "edm_pair_step_list": (C.c_int, [vp, C.c_long, C.c_long, c_dp, c_dp, c_ip, C.c_int, C.c_int, C.c_long, c_ip,
                                      c_lp, c_ip, C.c_int, C.c_longlong, c_dp, C.c_uint64, C.c_uint64,
                                      C.POINTER(PairResult)]),
@@ -454,6 +467,18 @@ class Bias:
         check(self.L.edm_pair_step_cells(self.h, x.shape[0], _dp(x), _dp(f), _ip(t) if t is not None else None, itype,
                                          jtype, _dp(_d(box)), float(cutoff), int(do_hills), int(est), seed, step,
                                          C.byref(r)))
+        return dict(energy=r.energy, n_pairs=r.n_pairs, n_calls=r.n_calls)
+
+    def pair_step_cells_domain(self, x, f, lo, hi, periodic, nlocal, cutoff, do_hills=False, est=0, seed=0, step=0,
+                               types=None, itype=0, jtype=0):
+        """One rank's share: x has nall rows (local atoms first, then ghosts), f has nlocal rows."""
+        assert x.flags.c_contiguous and f.flags.c_contiguous and x.shape[1] == 3 and f.shape == (nlocal, 3)
+        dom = PairDomain((C.c_double * 3)(*lo), (C.c_double * 3)(*hi), (C.c_int * 3)(*[int(p) for p in periodic]), nlocal)
+        r = PairResult()
+        t = _i(types) if types is not None else None
+        check(self.L.edm_pair_step_cells_domain(self.h, x.shape[0], _dp(x), _dp(f), _ip(t) if t is not None else None,
+                                                itype, jtype, C.byref(dom), float(cutoff), int(do_hills), int(est), seed,
+                                                step, C.byref(r)))
         return dict(energy=r.energy, n_pairs=r.n_pairs, n_calls=r.n_calls)
 
     def pair_search_info(self):

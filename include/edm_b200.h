@@ -94,6 +94,10 @@ int edm_grid_clear(edm_grid_t* g);
 int edm_grid_eval(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der);
 int edm_grid_eval_dev(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der,
                       void* stream);
+/* DimmedGrid::get_value_deriv of the grid INSIDE a GaussGrid (lib/grid.h:390-446 alone, without the boundary test
+ * and remap of lib/gaussian_grid.h:118-138): what grid_.multi_write evaluates, lib/grid.h:650-653.  On a plain
+ * grid the same as edm_grid_eval. */
+int edm_grid_eval_plain(const edm_grid_t* g, long n, const double* x, long xstride, double* value, double* der);
 /* Grid::get_value batched, lib/grid.h:343-365 / lib/gaussian_grid.h:99-116 */
 int edm_grid_get_value(const edm_grid_t* g, long n, const double* x, long xstride, double* value);
 /* DimmedGrid::add_value (histogram bump), lib/grid.h:370-385; fails on interpolated grids */
@@ -167,6 +171,11 @@ int edm_bias_update_forces(edm_bias_t* b, long n, const double* x, long xstride,
 int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstride, double* f, long fstride,
                                const int* mask, int apply_mask, double* energy, void* stream);
 
+/* The energy of the last edm_bias_update_forces_dev call made with energy = NULL (a one-CTA sum of the per-CTA
+ * partials, in CTA order).  For callers that overlap a hill round with the force update: issuing it after the
+ * round keeps it off the path force update -> deposit. */
+int edm_bias_energy_dev(edm_bias_t* b, double* energy, void* stream);
+
 /* FixEDM::post_force, lammps/fix_edm.cpp:134-162, as ONE call on host buffers: update_forces over every
  * atom and, if do_hills (ntimestep % stride == 0, fix_edm.cpp:142), add_hills over the same atoms.  The
  * coordinates are uploaded once and the atoms stream through in chunks, so both PCIe directions and
@@ -219,6 +228,31 @@ int edm_pair_step_cells_dev(edm_bias_t* b, long natoms, const double* x, double*
                             int jtype, const double* box, double cutoff, int do_hills,
                             long long est_hill_count, uint64_t seed, uint64_t step, edm_pair_result_t* result,
                             void* stream);
+/* The same step for ONE RANK'S SHARE of a larger system, in LAMMPS' own picture (lammps/fix_edm_pair.cpp:177-236 with
+ * newton off): the nall atoms handed over are the rank's nlocal local atoms followed by its ghosts (images and
+ * neighbours' atoms within the cutoff of the sub-box, coordinates already shifted), all inside [lo, hi).  Dimensions
+ * flagged periodic are wrapped by this rank itself (it holds the whole period); the others end at lo / hi.  As in
+ * the reference: the loop runs over local atoms, so a pair of two ghosts is skipped; a pair with one ghost is
+ * evaluated (its energy counted) but puts no force on the ghost (:223) and proposes ONE hill (:233) — the rank that
+ * owns the ghost evaluates the pair too.  f holds nlocal rows (host form) / nall rows (device form, ghost rows
+ * untouched).  With every dimension periodic and nlocal = nall this is edm_pair_step_cells. */
+typedef struct edm_pair_domain {
+  double lo[3], hi[3];
+  int periodic[3];
+  long nlocal;
+} edm_pair_domain_t;
+int edm_pair_step_cells_domain(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype,
+                               int jtype, const edm_pair_domain_t* dom, double cutoff, int do_hills,
+                               long long est_hill_count, uint64_t seed, uint64_t step, edm_pair_result_t* result);
+int edm_pair_step_cells_domain_dev(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype,
+                                   int jtype, const edm_pair_domain_t* dom, double cutoff, int do_hills,
+                                   long long est_hill_count, uint64_t seed, uint64_t step, edm_pair_result_t* result,
+                                   void* stream);
+/* selection only (evaluation + proposals, no round): the first half of the multi-GPU step, see below */
+int edm_pair_select_cells_domain_dev(edm_bias_t* b, long nall, const double* x, double* f, const int* type, int itype,
+                                     int jtype, const edm_pair_domain_t* dom, double cutoff, long long est_hill_count,
+                                     uint64_t seed, uint64_t step, double* energy_dev, void* stream);
+
 /* Same loop over a caller-supplied half neighbour list in LAMMPS NeighList form flattened to CSR
  * (ilist[inum], first[inum+1] offsets into jlist[]; j already masked with NEIGHMASK; j >= nlocal
  * are ghosts whose force is not updated, fix_edm_pair.cpp:223).  runiform (2 per listed pair, in

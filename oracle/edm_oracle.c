@@ -951,6 +951,66 @@ double orc_pair_step(void* p, long npairs, const int* pi, const int* pj, const d
   return energy;
 }
 
+/* The same with ghost atoms, as one rank of a decomposed LAMMPS run sees it (lammps/fix_edm_pair.cpp:177-236, newton
+ * off): every listed pair has a LOCAL first atom i (< nlocal); j may be a ghost (>= nlocal): then no force on j (:223)
+ * and one hill proposal instead of two (:233).  uniforms still holds two per pair; the second is unused for a ghost.
+ * Lib-level order as above.  ncalls_out = hill proposals made (the caller's next last_calls, :245). */
+double orc_pair_step_ghost(void* p, long npairs, const int* pi, const int* pj, const double* x, double* f,
+                           const double* shift, long nlocal, int do_hills, int est, const double* uniforms,
+                           double* r_out, long* ncalls_out) {
+  orc_bias* b = (orc_bias*)p;
+  double energy = 0;
+  long ncalls = 0;
+  double* rr = (double*)malloc(sizeof(double) * (size_t)(npairs > 0 ? npairs : 1));
+  for (long k = 0; k < npairs; k++) {
+    int i = pi[k], j = pj[k];
+    double delx = x[3 * i + 0] - x[3 * j + 0];
+    double dely = x[3 * i + 1] - x[3 * j + 1];
+    double delz = x[3 * i + 2] - x[3 * j + 2];
+    if (shift) {
+      delx -= shift[3 * k + 0];
+      dely -= shift[3 * k + 1];
+      delz -= shift[3 * k + 2];
+    }
+    double r = sqrt(delx * delx + dely * dely + delz * delz);
+    double rinv = 1.0 / r;
+    delx *= rinv;
+    dely *= rinv;
+    delz *= rinv;
+    double der[3] = {0, 0, 0};
+    double edm_force = 0;
+    if (!b->b_outofbounds) {
+      energy += gauss_get_value_deriv(b->bias, &r, der);
+      edm_force -= der[0];
+    }
+    f[3 * i + 0] += delx * edm_force;
+    f[3 * i + 1] += dely * edm_force;
+    f[3 * i + 2] += delz * edm_force;
+    if (j < nlocal) {
+      f[3 * j + 0] -= delx * edm_force;
+      f[3 * j + 1] -= dely * edm_force;
+      f[3 * j + 2] -= delz * edm_force;
+    }
+    rr[k] = r;
+    if (r_out) r_out[k] = r;
+  }
+  if (do_hills) {
+    orc_bias_pre_add_hill(b, est);
+    for (long k = 0; k < npairs; k++) {
+      bias_add_hill(b, &rr[k], uniforms[2 * k]);
+      ncalls++;
+      if (pj[k] < nlocal) {
+        bias_add_hill(b, &rr[k], uniforms[2 * k + 1]);
+        ncalls++;
+      }
+    }
+    orc_bias_post_add_hill(b);
+  }
+  free(rr);
+  if (ncalls_out) *ncalls_out = ncalls;
+  return energy;
+}
+
 /* Stand-in for the LAMMPS half neighbour list (not part of the reference tree): all i<j with
  * minimum-image distance < cutoff, ordered by (i, j).  shift[k] is the image vector s such that
  * the pair separation is x[i] - x[j] - s (a ghost atom in LAMMPS terms). */

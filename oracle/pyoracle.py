@@ -107,6 +107,7 @@ class _Lib:
             "bias_add_hill_many": (None, [vp, l, c_dp, c_dp]),
             "bias_post_add_hill": (None, [vp]),
             "pair_step": (d, [vp, l, c_ip, c_ip, c_dp, c_dp, c_dp, i, i, c_dp, c_dp]),
+            "pair_step_ghost": (d, [vp, l, c_ip, c_ip, c_dp, c_dp, c_dp, l, i, i, c_dp, c_dp, C.POINTER(l)]),
             "time_pair_eval": (d, [vp, l, c_dp, i]),
             "time_add_values": (d, [vp, l, c_dp, c_dp]),
             "time_fix_pair": (d, [vp, l, c_ip, c_ip, C.POINTER(C.c_byte), c_dp, c_dp, c_dp, i, i, C.c_ulonglong,
@@ -418,6 +419,18 @@ class Bias:
         un = _dp(_d(uniforms)) if uniforms is not None else None
         e = self.L.pair_step(self.h, npairs, _ip(pi), _ip(pj), _dp(x), _dp(f), sh, int(do_hills), int(est), un, _dp(r))
         return float(e), r
+
+    def pair_step_ghost(self, pi, pj, x, f, nlocal, shift=None, do_hills=False, est=0, uniforms=None):
+        """pair_step for one rank of a decomposed system: atoms >= nlocal are ghosts (no force, one proposal)."""
+        pi, pj = _i(pi), _i(pj)
+        npairs = pi.size
+        r = np.zeros(max(npairs, 1))
+        nc = C.c_long(0)
+        sh = _dp(_d(shift).ravel()) if shift is not None else None
+        un = _dp(_d(uniforms)) if uniforms is not None else None
+        e = self.L.pair_step_ghost(self.h, npairs, _ip(pi), _ip(pj), _dp(x), _dp(f), sh, int(nlocal), int(do_hills),
+                                   int(est), un, _dp(r), C.byref(nc))
+        return float(e), r[:npairs], nc.value
 
     def time_fix_pair(self, pi, pj, img, box, x, f, do_hills, est, seed=0, step=0):
         """The reference's own pair loop (lammps/fix_edm_pair.cpp:173-247, evaluation and hill proposals interleaved)

@@ -380,6 +380,59 @@ double ref_pair_step(void* p, long npairs, const int* pi, const int* pj, const d
   return energy;
 }
 
+// The same with ghost atoms (lammps/fix_edm_pair.cpp:223, 233): i is local, j may be a ghost (>= nlocal): no force on
+// it, one proposal instead of two.
+double ref_pair_step_ghost(void* p, long npairs, const int* pi, const int* pj, const double* x, double* f,
+                           const double* shift, long nlocal, int do_hills, int est, const double* uniforms,
+                           double* r_out, long* ncalls_out) {
+  EDMBias* b = ((BiasHandle*)p)->b;
+  double energy = 0;
+  long ncalls = 0;
+  std::vector<double> rr(npairs);
+  for (long k = 0; k < npairs; k++) {
+    int i = pi[k], j = pj[k];
+    double delx = x[3 * i + 0] - x[3 * j + 0];
+    double dely = x[3 * i + 1] - x[3 * j + 1];
+    double delz = x[3 * i + 2] - x[3 * j + 2];
+    if (shift) {
+      delx -= shift[3 * k + 0];
+      dely -= shift[3 * k + 1];
+      delz -= shift[3 * k + 2];
+    }
+    double r = sqrt(delx * delx + dely * dely + delz * delz);
+    double rinv = 1.0 / r;
+    delx *= rinv;
+    dely *= rinv;
+    delz *= rinv;
+    double edm_force[1] = {0};
+    energy += b->update_force(&r, edm_force);
+    f[3 * i + 0] += delx * edm_force[0];
+    f[3 * i + 1] += dely * edm_force[0];
+    f[3 * i + 2] += delz * edm_force[0];
+    if (j < nlocal) {
+      f[3 * j + 0] -= delx * edm_force[0];
+      f[3 * j + 1] -= dely * edm_force[0];
+      f[3 * j + 2] -= delz * edm_force[0];
+    }
+    rr[k] = r;
+    if (r_out) r_out[k] = r;
+  }
+  if (do_hills) {
+    b->pre_add_hill(est);
+    for (long k = 0; k < npairs; k++) {
+      b->add_hill(&rr[k], uniforms[2 * k]);
+      ncalls++;
+      if (pj[k] < nlocal) {
+        b->add_hill(&rr[k], uniforms[2 * k + 1]);
+        ncalls++;
+      }
+    }
+    b->post_add_hill();
+  }
+  if (ncalls_out) *ncalls_out = ncalls;
+  return energy;
+}
+
 // ------------------------------------------------------------------ timing helpers (CPU baseline)
 // Timed inside C++ so that ctypes/array marshalling stays outside the measured region.
 double ref_time_pair_eval(void* p, long npairs, const double* r, int repeats) {
