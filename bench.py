@@ -84,6 +84,31 @@ def c2_config(workload, world, pairs_per_step):
             "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world}
 
 
+ONE_BOX_ATOMS = 8_000_000   # c2_one_box: ONE periodic system of this many atoms, cut into z-slabs over the ranks
+
+
+def one_box_slab(rank, world):
+    """This rank's share of the single 8e6-atom box (number density 0.1, the same coordinates on every rank):
+    local atoms of the slab z in [zlo, zhi) first, then the ghost atoms within the cutoff of its two faces
+    (periodic images shifted), as LAMMPS hands them to fix edm_pair.  Returns (x, nlocal, lo, hi, periodic)."""
+    L = (ONE_BOX_ATOMS / DENSITY) ** (1.0 / 3.0)
+    x = np.random.default_rng(1234 + 7).uniform(0, L, size=(ONE_BOX_ATOMS, 3))
+    if world == 1:
+        return np.ascontiguousarray(x), ONE_BOX_ATOMS, [0.0] * 3, [L] * 3, [1, 1, 1]
+    zlo, zhi = rank * L / world, (rank + 1) * L / world
+    z = x[:, 2]
+    rows = [x[(z >= zlo) & (z < zhi)]]
+    nlocal = rows[0].shape[0]
+    for shift in (-L, 0.0, L):
+        zs = z + shift
+        g = ((zs >= zlo - CUTOFF) & (zs < zlo)) | ((zs >= zhi) & (zs < zhi + CUTOFF))
+        if g.any():
+            xg = x[g].copy()
+            xg[:, 2] += shift
+            rows.append(xg)
+    return np.ascontiguousarray(np.concatenate(rows)), nlocal, [0.0, 0.0, zlo - CUTOFF], [L, L, zhi + CUTOFF], [1, 1, 0]
+
+
 def c2_positions(rank, n_sets):
     """Synthetic coordinates of one rank: uniform in a periodic cube at number density 0.1."""
     box_len = (N_ATOMS / DENSITY) ** (1.0 / 3.0)
@@ -466,26 +491,43 @@ def run_gpu(args, rank, local_rank, world):
     bias.bias_grid.add_values(*warm)
     edm.check(L.edm_bias_set_profiling(bias.h, 1))
 
-    n_sets = 3                               # rotate position sets; L2 is flushed between steps anyway
-    box_len, sets = c2_positions(rank, n_sets)
+    one_box = args.workload == "c2_one_box"
+    dom = None
+    if one_box:
+        # ONE system over all ranks: z-slabs with ghost atoms (strong scaling of a fixed 8e6-atom box)
+        n_sets = 1
+        xs, nlocal, dlo, dhi, dper = one_box_slab(rank, world)
+        sets = [xs]
+        n_rows = xs.shape[0]
+        box_len = dhi[0] - dlo[0]
+        dom = edm.PairDomain((C.c_double * 3)(*dlo), (C.c_double * 3)(*dhi), (C.c_int * 3)(*dper), nlocal)
+    else:
+        n_sets = 3                           # rotate position sets; L2 is flushed between steps anyway
+        box_len, sets = c2_positions(rank, n_sets)
+        n_rows = nlocal = N_ATOMS
     box = np.array([box_len] * 3)
     xs_host = [torch.from_numpy(x).pin_memory() for x in sets]
     xs_dev = [x.cuda(non_blocking=True) for x in xs_host]
-    f_dev = torch.zeros((N_ATOMS, 3), dtype=torch.float64, device="cuda")
-    f_host = torch.zeros((N_ATOMS, 3), dtype=torch.float64).pin_memory()
+    f_dev = torch.zeros((n_rows, 3), dtype=torch.float64, device="cuda")
+    f_host = torch.zeros((nlocal, 3), dtype=torch.float64).pin_memory()
     energy_dev = torch.zeros(1, dtype=torch.float64, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     boxp = box.ctypes.data_as(C.POINTER(C.c_double))
-    expected_pairs = N_ATOMS * (4.0 / 3.0) * np.pi * CUTOFF ** 3 * DENSITY / 2
+    expected_pairs = nlocal * (4.0 / 3.0) * np.pi * CUTOFF ** 3 * DENSITY / 2
     est_local = int(2 * expected_pairs)
     seed = SEED
 
     def step_resident(step):
         x = xs_dev[step % n_sets]
         est_total = est_local * world
-        edm.check(L.edm_pair_select_cells_dev(bias.h, N_ATOMS, x.data_ptr(), f_dev.data_ptr(), None, 0, 0, boxp,
-                                              CUTOFF, est_total, seed + rank, step, energy_dev.data_ptr(), stream))
+        if one_box:
+            edm.check(L.edm_pair_select_cells_domain_dev(bias.h, n_rows, x.data_ptr(), f_dev.data_ptr(), None, 0, 0,
+                                                         C.byref(dom), CUTOFF, est_total, seed + rank, step,
+                                                         energy_dev.data_ptr(), stream))
+        else:
+            edm.check(L.edm_pair_select_cells_dev(bias.h, N_ATOMS, x.data_ptr(), f_dev.data_ptr(), None, 0, 0, boxp,
+                                                  CUTOFF, est_total, seed + rank, step, energy_dev.data_ptr(), stream))
         # pack -> ncclAllGather -> commit inside the library (one rank: pack -> commit)
         edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, stream))
 
@@ -536,8 +578,12 @@ def run_gpu(args, rank, local_rank, world):
     def step_e2e(step):
         xh = xs_host[step % n_sets]
         r = edm.PairResult()
-        edm.check(L.edm_pair_step_cells(bias.h, N_ATOMS, xh.data_ptr(), f_host.data_ptr(), None, 0, 0, boxp, CUTOFF,
-                                        1, est_local, seed + rank, step, C.byref(r)))
+        if one_box:
+            edm.check(L.edm_pair_step_cells_domain(bias.h, n_rows, xh.data_ptr(), f_host.data_ptr(), None, 0, 0,
+                                                   C.byref(dom), CUTOFF, 1, est_local, seed + rank, step, C.byref(r)))
+        else:
+            edm.check(L.edm_pair_step_cells(bias.h, N_ATOMS, xh.data_ptr(), f_host.data_ptr(), None, 0, 0, boxp, CUTOFF,
+                                            1, est_local, seed + rank, step, C.byref(r)))
         return r
 
     r0 = step_e2e(step_no)
@@ -561,9 +607,10 @@ def run_gpu(args, rank, local_rank, world):
     for k in range(3):                        # the device-side split, outside the timed loop (event queries synchronise)
         step_e2e(step_no)
         step_no += 1
-        v = [C.c_double(0) for _ in range(4)]
-        edm.check(L.edm_bias_profile_e2e_ms(bias.h, *[C.byref(t) for t in v]))
-        split += np.array([t.value for t in v]) / 3.0
+        if not one_box:                       # the domain entry point is not instrumented
+            v = [C.c_double(0) for _ in range(4)]
+            edm.check(L.edm_bias_profile_e2e_ms(bias.h, *[C.byref(t) for t in v]))
+            split += np.array([t.value for t in v]) / 3.0
     bias.set_comm(None)
 
     pairs_timed = sum(pairs_per_step[(st0["steps"] + k) % n_sets] for k in range(args.steps))
@@ -610,17 +657,24 @@ def run_gpu(args, rank, local_rank, world):
         peak, peak_src = measured_peak()
         value = pairs_all / (total_ms * 1e-3)
         kernel_ms = float(np.mean(eval_ms)) if np.mean(eval_ms) > 0 else float(np.mean(pair_ms))
-        alg_bytes = ALG_BYTES_PER_ATOM * N_ATOMS
+        alg_bytes = ALG_BYTES_PER_ATOM * n_rows
         info = bias.pair_search_info()
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         st_hills = st1["steps"] - st0["steps"]
         traffic, binding, traffic_src = ncu_roofline(args.workload, "block_eval_kernel")
-        h2d, d2h = 2 * N_ATOMS * 24, N_ATOMS * 24
+        h2d, d2h = (n_rows + nlocal) * 24, nlocal * 24
+        config = c2_config(args.workload, world, pairs_per_step[0])
+        if one_box:
+            config.update({"atoms_total": ONE_BOX_ATOMS, "atoms_per_gpu": nlocal, "rows_per_gpu_with_ghosts": n_rows,
+                           "parallelism": "ONE periodic box cut into %d z-slabs, ghost atoms within the cutoff of the "
+                                          "faces (newton off: a pair across a face is evaluated on both sides), grid "
+                                          "replicated, hills all-gathered" % world})
         out = {
             "metric": "CV bias+force evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": c2_config(args.workload, world, pairs_per_step[0]),
+            "higher_is_better": True, "scaling": "strong" if one_box else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": config,
             "timing": {"hill_rounds_timed": st_hills,
                        "l2": "flushed between timed steps (512 MiB memset outside the per-step CUDA-event pair)",
                        "exchange": "edm_bias_exchange_dev: pack -> ncclAllGather -> commit, NCCL called by the library"},
@@ -655,7 +709,7 @@ def run_gpu(args, rank, local_rank, world):
             "gpu_launches": int(launches_all),
             "clocks": clk,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "c2_pair_rdf":
             kind, kind_name = oracle_kind()
             cores = len(os.sched_getaffinity(0))
             crng = np.random.default_rng(4321)
@@ -898,7 +952,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--csrc-hash", action="store_true", help="print the hash of the csrc/ tree and exit")
     ap.add_argument("--workload", default="c2_pair_rdf",
-                    choices=["c2_pair_rdf", "c5_pair_rdf_backlog", "c2_pair_rdf_local_tempering"] + sorted(COORD_WORKLOADS),
+                    choices=["c2_pair_rdf", "c5_pair_rdf_backlog", "c2_pair_rdf_local_tempering", "c2_one_box"] +
+                    sorted(COORD_WORKLOADS),
                     help="c2_pair_rdf is the benchmark (BASELINE.json configs[1]); the others are the remaining configs")
     args = ap.parse_args()
     if args.csrc_hash:
