@@ -771,7 +771,26 @@ def run_coord(args, rank, local_rank, world):
     n_atoms = cfg["atoms"] // world          # strong split of the config's atom count: BASELINE names the total
     rng = np.random.default_rng(1234 + 3 + 1000 * rank)
     n_sets = 2
-    xs_host = [torch.from_numpy(rng.uniform(cfg["lo"][0], cfg["hi"][0], size=(n_atoms, D))).pin_memory()
+
+    def ordered(x):
+        """--input-order: how the caller's atom array is ordered.  random = as drawn (the default, the hard case);
+        cell = sorted by grid cell, row-major (what an MD code with spatial sorting hands over); strip = sorted only
+        by a coarse strip of the slowest dimension whose records fit L2 (what a device-side binning pass would buy)."""
+        if args.input_order == "random":
+            return x
+        dx = np.array(geo["dx"][:D])
+        cell = np.floor((x - np.array(cfg["lo"])) / dx).astype(np.int64)
+        n = np.array(geo["n"][:D], dtype=np.int64)
+        if args.input_order == "cell":
+            key = cell[:, D - 1]
+            for d in range(D - 2, -1, -1):
+                key = key * n[d] + cell[:, d]
+        else:
+            rows_per_strip = max(1, int((48 << 20) // (32 * np.prod(n[:D - 1]))))   # ~48 MB of records per strip
+            key = cell[:, D - 1] // rows_per_strip
+        return np.ascontiguousarray(x[np.argsort(key, kind="stable")])
+
+    xs_host = [torch.from_numpy(ordered(rng.uniform(cfg["lo"][0], cfg["hi"][0], size=(n_atoms, D)))).pin_memory()
                for _ in range(n_sets)]
     xs_dev = [x.cuda(non_blocking=True) for x in xs_host]
     f_dev = torch.zeros((n_atoms, D), dtype=torch.float64, device="cuda")
@@ -822,8 +841,8 @@ def run_coord(args, rank, local_rank, world):
                                             rank * n_atoms, sst))
             # the round's writers (deposit, tail) follow the force update on the main stream: nothing to join
             edm.check(L.edm_bias_round_commit_on(bias.h, main.cuda_stream))
+            edm.check(L.edm_bias_energy_with_round(bias.h, energy_dev.data_ptr()))   # summed by an idle deposit CTA
             edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, sst))
-        edm.check(L.edm_bias_energy_dev(bias.h, energy_dev.data_ptr(), stream))   # behind the deposit, off the critical path
 
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -883,6 +902,28 @@ def run_coord(args, rank, local_rank, world):
             step_no += 1
         torch.cuda.synchronize()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    # ---- batched deposit throughput (GaussGrid::add_value equivalents per second) on a scratch replica
+    dep_hills_per_s = None
+    if world == 1:
+        nb = 1 << 17
+        dgrid = edm.GaussGrid(D, cfg["lo"], cfg["hi"], list(geo["dx"][:D]), [1] * D, 1,
+                              [float(v) for v in cfg["text"].split("bias_sigma")[1].split()[:D]], device=local_rank)
+        drng = np.random.default_rng(77)
+        dc = torch.from_numpy(drng.uniform(cfg["lo"][0], cfg["hi"][0], size=(nb, D))).cuda()
+        dh = torch.full((nb,), 1e-6, dtype=torch.float64, device="cuda")
+        dba = torch.zeros(nb, dtype=torch.float64, device="cuda")
+        edm.check(L.edm_gauss_deposit_dev(dgrid.h, nb, dc.data_ptr(), dh.data_ptr(), dba.data_ptr(), stream))
+        torch.cuda.synchronize()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(2):
+            edm.check(L.edm_gauss_deposit_dev(dgrid.h, nb, dc.data_ptr(), dh.data_ptr(), dba.data_ptr(), stream))
+        d1.record()
+        torch.cuda.synchronize()
+        dep_ms = d0.elapsed_time(d1) / 2
+        dep_hills_per_s = {"batched_deposit_hills_per_s": nb / (dep_ms * 1e-3), "batch": nb, "ms_per_batch": dep_ms,
+                           "note": "edm_gauss_deposit_dev: n pre-selected hills in list order, one CTA per hill"}
+        del dgrid
     clk = clocks.stop()
 
     stats = torch.tensor([total_ms, float(np.mean(k1_ms)), float(np.mean(round_ms)), float(launches)],
@@ -906,7 +947,8 @@ def run_coord(args, rank, local_rank, world):
             "metric": "CV bias+force evals/sec", "value": evals / (total_ms * 1e-3), "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "atoms_total": n_atoms * world, "atoms_per_gpu": n_atoms,
+            "config": {"workload": args.workload, "input_order": args.input_order, "atoms_total": n_atoms * world,
+                       "atoms_per_gpu": n_atoms,
                        "grid_points": n_pts, "grid_bytes_in_hbm": n_pts * (2 if D == 1 else 4) * 8, "hill_density": 250,
                        "l2": "flushed between timed steps (512 MiB memset outside the CUDA-event pairs)",
                        "parallelism": "atoms sharded %d-way, grid replicated, hills all-gathered" % world},
@@ -915,9 +957,10 @@ def run_coord(args, rank, local_rank, world):
                                           "integrals and decision run beside update_forces on a second stream"},
             "round_stamps_us": {
                 "legend": "us since the plan began: [0-6] plan phases, [7,8] decision, [9,10] first deposit taken / last "
-                          "deposit done, [11,12] in-order kernel begin/end, [13] force update finished, [14] force update began",
+                          "deposit done, [11,12] in-order kernel begin/end, [13] last deposit CTA left, [14] force update began, [15] in-order kernel resident",
                 "overlapped_step": [round(float(v), 2) for v in stamps_fused],
                 "back_to_back": [round(float(v), 2) for v in bias.round_times_us()]},
+            "batched_deposit": dep_hills_per_s,
             "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],
                       "rounds_split": info1["split"] - info0["split"],
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},
@@ -951,6 +994,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--csrc-hash", action="store_true", help="print the hash of the csrc/ tree and exit")
+    ap.add_argument("--input-order", default="random", choices=["random", "cell", "strip"],
+                    help="coordinate workloads: order of the caller's atom array (see run_coord.ordered)")
     ap.add_argument("--workload", default="c2_pair_rdf",
                     choices=["c2_pair_rdf", "c5_pair_rdf_backlog", "c2_pair_rdf_local_tempering", "c2_one_box"] +
                     sorted(COORD_WORKLOADS),

@@ -252,6 +252,7 @@ __global__ void __launch_bounds__(512) hill_round_kernel(GridDesc bias, GridDesc
   __shared__ RoundState rs;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
   pdl_trigger();
+  if (threadIdx.x == 0) st->stamp[15] = global_ns();  // measurement: resident, about to wait for the predecessor
   pdl_wait();
   const int mode = st->round_mode;
   if (threadIdx.x == 0) st->stamp[11] = global_ns();
@@ -1035,7 +1036,9 @@ template <int DIM>
 __global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, BiasDev* st,
                                                             const double* __restrict__ centres,
                                                             const double* __restrict__ heights,
-                                                            const int4* __restrict__ cells, int* flags) {
+                                                            const int4* __restrict__ cells, int* flags,
+                                                            const double* __restrict__ energy_partial, int n_partials,
+                                                            double* energy_out) {
   __shared__ double red[33];
   __shared__ int s_k;
   __shared__ AxisEntry s_axis[DIM > 1 ? DIM * kAxisMax : 1];
@@ -1048,7 +1051,18 @@ __global__ void __launch_bounds__(512, 2) round_deposit_kernel(GridDesc bias, Bi
     if (threadIdx.x == 0) s_k = atomicAdd(&st->ticket, 1);
     __syncthreads();
     const int k = s_k;
-    if (k >= n) break;
+    if (k >= n) {
+      if (threadIdx.x == 0 && k == n + (int)gridDim.x - 1) st->stamp[13] = global_ns();  // measurement: last CTA leaves
+      // The first CTA left without a hill adds up the energy partials of this step's force update (CTA order, so
+      // run-to-run deterministic): that sum rides along here instead of a one-CTA kernel of its own in the stream.
+      if (k == n && energy_out) {
+        double e = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) e += energy_partial[i];
+        e = block_sum(e, red);
+        if (threadIdx.x == 0) energy_out[0] = e;
+      }
+      break;
+    }
     if (k == 0 && threadIdx.x == 0) st->stamp[9] = global_ns();
     const int4 ck = cells[k];
     for (int j = threadIdx.x; j < k; j += blockDim.x)
@@ -1385,11 +1399,16 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
     if (one_d) {
       EDM_TRY(deposit1d_commit_if(b->bias, &b->d_state->round_mode, 2, st));
     } else {
+      // one-shot (edm_bias_energy_with_round): the energy sum of the last force update rides in this kernel
+      double* e_out = b->energy_with_round;
+      b->energy_with_round = nullptr;
       if (moved)  // behind a long force update: launched plainly, or its whole grid would sit resident next to it
-        round_deposit_kernel<DIM><<<nblk, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags);
+        round_deposit_kernel<DIM><<<nblk, 512, 0, st>>>(bias, b->d_state, centres, heights, cells, b->bias->d_flags,
+                                                         b->d_energy_partial, b->last_partials, e_out);
       else
         EDM_CUDA(launch_pdl(round_deposit_kernel<DIM>, dim3(nblk), dim3(512), 0, st, bias, b->d_state,
-                            (const double*)centres, (const double*)heights, (const int4*)cells, b->bias->d_flags));
+                            (const double*)centres, (const double*)heights, (const int4*)cells, b->bias->d_flags,
+                            (const double*)b->d_energy_partial, b->last_partials, e_out));
       count_launches(1);
       if (bias.n_dup) {
         EDM_TRY(edm_grid_dup_boundary_if(b->bias, &b->d_state->round_mode, 2, st));
@@ -1408,6 +1427,11 @@ static int launch_round_dim(edm_bias* b, const RoundParams& rp, const GridDesc& 
   EDM_CUDA(launch_pdl(hill_round_kernel<DIM>, dim3(1), dim3(512), 0, st, bias, hist, target, rp, b->d_state, b->d_accepted,
                       tmp, b->d_log));
   EDM_CUDA(cudaGetLastError());
+  if (b->energy_with_round) {  // no deposit kernel took it along (1-D owner-computes path, in-order round)
+    double* e_out = b->energy_with_round;
+    b->energy_with_round = nullptr;
+    EDM_TRY(edm_bias_energy_dev(b, e_out, st));
+  }
   return EDM_OK;
 }
 
@@ -1776,6 +1800,12 @@ int edm_bias_add_hills_dev(edm_bias_t* b, long n, const double* x, long xstride,
   return edm_bias_launch_round(b, est, st);
 }
 
+int edm_bias_energy_with_round(edm_bias_t* b, double* energy) {
+  EDM_REQUIRE(b != nullptr, "NULL argument");
+  b->energy_with_round = energy;
+  return EDM_OK;
+}
+
 int edm_bias_round_commit_on(edm_bias_t* b, void* stream) {
   EDM_REQUIRE(b != nullptr, "NULL argument");
   b->commit_stream = (cudaStream_t)stream;
@@ -1825,8 +1855,8 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   // the round's writers (deposit, in-order tail) follow the force update on the caller's stream; nothing to join
   b->commit_stream = st;
   b->commit_stream_set = 1;
+  if (energy && n > 0) b->energy_with_round = energy;  // summed inside the deposit kernel (or right after the round)
   EDM_TRY(edm_bias_launch_round(b, est, b->st_side));
-  if (energy && n > 0) EDM_TRY(edm_bias_energy_dev(b, energy, stream));
   return EDM_OK;
 }
 
@@ -1916,7 +1946,7 @@ int edm_bias_round_times_us(edm_bias_t* b, double* out13) {
   EDM_TRY(ensure_device(b->device));
   BiasDev hdr;
   EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < 15; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
+  for (int i = 0; i < 16; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
   return EDM_OK;
 }
 

@@ -158,6 +158,7 @@ struct edm_bias {
   double* d_energy_partial = nullptr;  // per-CTA energy partials
   int n_partial = 0;
   int last_partials = 0;               // CTAs (= partials) of the last force update
+  double* energy_with_round = nullptr; // one-shot: the next round also sums those partials into this device double
   double* d_scalar = nullptr;          // [0] energy
   edm::Scratch io, io2, io3, io4;      // host<->device staging for the host-pointer entry points
   edm::Scratch cells;                  // cell-list scratch of the pair kernels

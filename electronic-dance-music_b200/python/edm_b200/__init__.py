@@ -94,6 +94,7 @@ EXPORTS = {
                                            C.c_uint64, C.c_uint64, vp, vp]),
     "edm_bias_round_after": (C.c_int, [vp, vp]),
     "edm_bias_energy_dev": (C.c_int, [vp, vp, vp]),
+    "edm_bias_energy_with_round": (C.c_int, [vp, vp]),
     "edm_bias_round_commit_on": (C.c_int, [vp, vp]),
     "edm_bias_update_forces_dev": (C.c_int, [vp, C.c_long, vp, C.c_long, vp, C.c_long, vp, C.c_int, vp, vp]),
     "edm_bias_add_hills": (C.c_int, [vp, C.c_long, c_dp, C.c_long, c_dp, c_ip, C.c_int, C.c_uint64, C.c_uint64]),
@@ -512,7 +513,7 @@ class Bias:
         check(self.L.edm_bias_check(self.h))
 
     def round_times_us(self):
-        out = np.zeros(15)
+        out = np.zeros(16)
         check(self.L.edm_bias_round_times_us(self.h, _dp(out)))
         return out
 

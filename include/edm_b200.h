@@ -176,6 +176,10 @@ int edm_bias_update_forces_dev(edm_bias_t* b, long n, const double* x, long xstr
  * round keeps it off the path force update -> deposit. */
 int edm_bias_energy_dev(edm_bias_t* b, double* energy, void* stream);
 
+/* One-shot: the next hill round launched for `b` also writes that energy to `energy` (device pointer): an idle CTA
+ * of its deposit kernel adds the partials up, so the sum costs no launch of its own on the critical path. */
+int edm_bias_energy_with_round(edm_bias_t* b, double* energy);
+
 /* FixEDM::post_force, lammps/fix_edm.cpp:134-162, as ONE call on host buffers: update_forces over every
  * atom and, if do_hills (ntimestep % stride == 0, fix_edm.cpp:142), add_hills over the same atoms.  The
  * coordinates are uploaded once and the atoms stream through in chunks, so both PCIe directions and
@@ -367,9 +371,10 @@ int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, 
 
 /* Device-clock (%globaltimer) stamps of the last hill round, microseconds since the plan kernel began:
  * [0..6] plan phases, [7,8] decision begin/end, [9,10] first deposit taken / last deposit done,
- * [11,12] in-order kernel begin/end, [13] the last force update finished, [14] the last force update began.
- * out holds 15 doubles.  Synchronises on a small copy. */
-int edm_bias_round_times_us(edm_bias_t* b, double* out15);
+ * [11,12] in-order kernel begin/end, [13] the deposit grid's last CTA left, [14] the last force update began,
+ * [15] the in-order kernel became resident (before it waits for its predecessor).
+ * out holds 16 doubles.  Synchronises on a small copy. */
+int edm_bias_round_times_us(edm_bias_t* b, double* out16);
 
 /* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
  * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,
