@@ -105,7 +105,7 @@ def build_host_tests(force=False):
         subprocess.check_call([CXX] + CXXFLAGS + ["-pthread", "-I" + HERE, "-o", EXCHANGE_TEST, xt_src,
                                                   "-L" + LIBDIR, "-ledm", "-ledm_b200", "-Wl,-rpath,$ORIGIN"])
     # the text-I/O driver against this repo's EDM:: classes (the same source is linked against the unmodified
-    # reference by oracle/Makefile `text` to produce the golden files)
+    # reference by the checker's Makefile target `text` to produce the golden files)
     td_src = os.path.join(HERE, "tests_host", "text_io_driver.cpp")
     if force or _stale(TEXT_IO_DRIVER, [td_src, HOST_LIB]):
         subprocess.check_call([CXX] + CXXFLAGS + ["-I" + edm_dir, "-o", TEXT_IO_DRIVER, td_src, "-L" + LIBDIR, "-ledm",

@@ -1,6 +1,6 @@
 // One driver, two builds: the on-disk formats either side of the hot path.
 //
-//   - against the UNMODIFIED reference library (oracle/Makefile `text`, headers from /root/reference/lib, the
+//   - against the UNMODIFIED reference library (the checker's Makefile target `text`, headers from /root/reference/lib, the
 //     single-rank stub mpi.h): produces the golden texts committed under tests/golden/text/
 //     (tests/golden/make_text_golden.py);
 //   - against this repo's EDM:: mirror over the CUDA library (build.py): produces the same files from the GPU
