@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "edm_host.h"
@@ -23,9 +24,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Random coordinates make every evaluation a chain of dependent DRAM round trips (x -> corner
 // records -> f): the old force is loaded together with the coordinate, before the grid walk, and
 // the register budget is set for the occupancy that measured fastest on B200 (C3: 3 CTAs/SM
-// 0.70 ms vs 0.81 / 0.86 ms at 2 / 4; C4: 2 CTAs/SM).  Two or four points per thread did not help:
-// ncu shows DRAM at ~4.4 TB/s of mostly half-used 64 B bursts (a 32 B record per corner), i.e. the
-// gather is DRAM-bound on real traffic, 3.5x the algorithmic bytes.
+// 0.70 ms vs 0.81 / 0.86 ms at 2 / 4; C4: 2 CTAs/SM).  d_interp_cell issues all 2^DIM corner loads
+// before it blends (spatially ordered atoms: C3 0.36 -> 0.31 ms, C4 1.15 -> 0.86 ms; unordered atoms
+// are bound by the DRAM random-access rate either way: ~4.9 TB/s of mostly half-used 64 B bursts).
+// Measured and rejected (tools/experiments/k1_variants.sh): two atoms per thread, a software pipeline
+// with L2 prefetch of the next atom's corners (unordered 0.67 -> 1.14 ms), 64-register builds.
 #ifndef EDM_FORCES_UNROLL
 #define EDM_FORCES_UNROLL 1
 #endif
@@ -1027,7 +1030,7 @@ __device__ __forceinline__ bool d_windows_overlap(const GridDesc& g, const int4&
       dist %= g.n[d];
       dist = min(dist, g.n[d] - dist);
     }
-    if (dist > 2 * g.minisize[d]) return false;
+    if (dist > 2 * g.supp[d]) return false;  // a deposit pass touches supp cells either side of its centre cell, no more
   }
   return true;
 }

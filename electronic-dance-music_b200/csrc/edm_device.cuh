@@ -148,7 +148,11 @@ __device__ __forceinline__ bool d_locate(const GridDesc& g, const double* xin, C
     double xi = x[d];
     if (g.periodic[d]) xi = d_wrap(xi, g.min[d], g.len[d]);
     double t = __dsub_rn(xi, g.min[d]);
-    long long idx = (long long)floor(__ddiv_rn(t, g.dx[d]));  // T5: a true division
+    // T5: the reference floors a true quotient.  t * (1/dx) is within 2 ulp of it, so its floor is the same unless
+    // it lies that close to an integer; only then is the exactly rounded division paid for.
+    double q = t * g.inv_dx[d];
+    if (fabs(q - rint(q)) <= 8e-16 * fabs(q)) q = __ddiv_rn(t, g.dx[d]);
+    long long idx = (long long)floor(q);
     int nd = g.n[d];
     long long hi = g.periodic[d] ? nd - 1 : nd - 2;
     idx = idx < 0 ? 0 : (idx > hi ? hi : idx);  // rounding can land one past the last cell; clamp
@@ -178,14 +182,15 @@ template <int DIM> __device__ __forceinline__ long long d_corner_shift(const Cel
 template <int DIM, typename Load>
 __device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double* X0, double* der, Load load) {
   constexpr int W = RecW<DIM>::value;
+  constexpr int NC = 1 << DIM;
   double f = 0.0;
+  if (DIM == 1) {
 #pragma unroll
-  for (int c = 0; c < (1 << DIM); c++) {
-    double r[W];
-    load(c, r);
-    double tabf = r[0];
-    bool nz = !(fabs(tabf) < kInterpZero);  // T6
-    if (DIM == 1) {
+    for (int c = 0; c < NC; c++) {
+      double r[W];
+      load(c, r);
+      double tabf = r[0];
+      bool nz = !(fabs(tabf) < kInterpZero);  // T6
       int b = c & 1;
       double X = fabs(X0[0] - (double)b);
       double s = b ? -1.0 : 1.0;
@@ -197,31 +202,76 @@ __device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double*
       double td = nz ? r[1] : 0.0;
       f += tabf * a + s * td * bp * g.dx[0];
       der[0] += tabf * ap * s * g.inv_dx[0] + td * cc;
+    }
+    return f;
+  }
+  // 2-D / 3-D: every corner record first (the loads are in flight together), then ONE reciprocal per four corners:
+  // 1/t_c = (product of the other three) / (product of all four).  Corners the reference treats as zero (T6) enter
+  // as 1.  |t| >= 1e-7 for the others, so the product stays a normal number for any bias below 1e70; outside that
+  // range each corner gets its own division.
+  double r[NC][W], rinv[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) load(c, r[c]);
+#pragma unroll
+  for (int q = 0; q < NC; q += 4) {
+    bool nz[4];
+    double t[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      nz[c] = !(fabs(r[q + c][0]) < kInterpZero);  // T6
+      t[c] = nz[c] ? r[q + c][0] : 1.0;
+    }
+    const double p01 = t[0] * t[1], p23 = t[2] * t[3];
+    const double all = p01 * p23, mag = fabs(all);
+    if (mag > 1e-280 && mag < 1e280) {
+      const double inv = 1.0 / all;
+      const double i01 = inv * p23, i23 = inv * p01;  // 1/(t0 t1), 1/(t2 t3)
+      rinv[q + 0] = nz[0] ? i01 * t[1] : 0.0;
+      rinv[q + 1] = nz[1] ? i01 * t[0] : 0.0;
+      rinv[q + 2] = nz[2] ? i23 * t[3] : 0.0;
+      rinv[q + 3] = nz[3] ? i23 * t[2] : 0.0;
     } else {
-      double rinv = nz ? 1.0 / tabf : 0.0;
-      double C[DIM], D[DIM];
 #pragma unroll
-      for (int d = 0; d < DIM; d++) {
-        int b = (c >> d) & 1;
-        double X = fabs(X0[d] - (double)b);
-        double s = b ? -1.0 : 1.0;
-        double X2 = X * X, X3 = X2 * X;
-        double qq = -r[1 + d] * rinv;
-        C[d] = (1.0 - 3.0 * X2 + 2.0 * X3) - s * qq * (X - 2.0 * X2 + X3) * g.dx[d];
-        D[d] = ((-6.0 * X + 6.0 * X2) - s * qq * (1.0 - 4.0 * X + 3.0 * X2) * g.dx[d]) * s * g.inv_dx[d];
-      }
-      double ff = 1.0;
+      for (int c = 0; c < 4; c++) rinv[q + c] = nz[c] ? 1.0 / t[c] : 0.0;
+    }
+  }
+  // the Hermite factors depend on (dimension, side) only
+  double A[DIM][2], B[DIM][2], AP[DIM][2], CP[DIM][2];
 #pragma unroll
-      for (int d = 0; d < DIM; d++) ff *= C[d];
-      f += tabf * ff;
+  for (int d = 0; d < DIM; d++) {
 #pragma unroll
-      for (int d = 0; d < DIM; d++) {
-        double fd = D[d];
+    for (int b = 0; b < 2; b++) {
+      double X = fabs(X0[d] - (double)b);
+      double s = b ? -1.0 : 1.0;
+      double X2 = X * X, X3 = X2 * X;
+      A[d][b] = 1.0 - 3.0 * X2 + 2.0 * X3;
+      B[d][b] = s * (X - 2.0 * X2 + X3) * g.dx[d];
+      AP[d][b] = (-6.0 * X + 6.0 * X2) * s * g.inv_dx[d];
+      CP[d][b] = (1.0 - 4.0 * X + 3.0 * X2);  // * s * dx * s / dx
+    }
+  }
 #pragma unroll
-        for (int e = 0; e < DIM; e++)
-          if (e != d) fd *= C[e];
-        der[d] += tabf * fd;
-      }
+  for (int c = 0; c < NC; c++) {
+    const double tabf = r[c][0];
+    double C[DIM], D[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const int b = (c >> d) & 1;
+      const double qq = -r[c][1 + d] * rinv[c];
+      C[d] = A[d][b] - qq * B[d][b];
+      D[d] = AP[d][b] - qq * CP[d][b];
+    }
+    double ff = 1.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) ff *= C[d];
+    f += tabf * ff;
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      double fd = D[d];
+#pragma unroll
+      for (int e = 0; e < DIM; e++)
+        if (e != d) fd *= C[e];
+      der[d] += tabf * fd;
     }
   }
   return f;

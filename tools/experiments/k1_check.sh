@@ -1,0 +1,16 @@
+O=gpurun_out
+T=${1:-r2u}
+python -m pytest tests -m gpu -x -q > $O/${T}_tests.log 2>&1
+tail -3 $O/${T}_tests.log
+for w in c3_coord_2d c4_coord_3d; do for ord in random cell strip; do
+  python bench.py --workload $w --input-order $ord --steps 10 --no-cpu-baseline > $O/${T}_${w}_${ord}.json 2>> $O/${T}_err.log
+done; done
+python bench.py --steps 10 --no-cpu-baseline > $O/${T}_c2.json 2>> $O/${T}_err.log
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("gpurun_out/${T}_*.json")):
+    l=[x for x in open(f) if x.startswith("{")]
+    if not l: print(f,"EMPTY"); continue
+    d=json.loads(l[-1]); print(f.split("/")[-1], "%.4f ms"%d["ms_per_step"], "kernel %.4f"%d["roofline"]["kernel_ms"], d.get("step_breakdown_ms"))
+PY
+tail -3 $O/${T}_err.log
