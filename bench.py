@@ -677,7 +677,10 @@ def run_gpu(args, rank, local_rank, world):
             "config": config,
             "timing": {"hill_rounds_timed": st_hills,
                        "l2": "flushed between timed steps (512 MiB memset outside the per-step CUDA-event pair)",
-                       "exchange": "edm_bias_exchange_dev: pack -> ncclAllGather -> commit, NCCL called by the library"},
+                       "exchange": ("edm_bias_exchange_dev inside the library: " +
+                                    ("one kernel stores the accepted hills into every rank's NVLink peer window and "
+                                     "waits for theirs -> commit" if (world > 1 and comm.peer_windows()) else
+                                     "pack -> ncclAllGather -> commit" if world > 1 else "single rank, nothing travels"))},
             "hills_per_s": hills_all,
             "hills": {"batched_deposit_hills_per_s": hills_all, "batch": DEPOSIT_BATCH, "ms_per_batch": dep_ms,
                       "in_situ_hill_events": int(hills_timed),

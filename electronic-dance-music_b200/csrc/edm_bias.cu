@@ -1240,6 +1240,59 @@ __global__ void pack_block_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* 
     for (int d = 0; d < DIM; d++) block[1 + (long)i * DIM + d] = acc[i].x[d];
 }
 
+// The exchange over NVLink peer windows: pack_block_kernel's block goes straight into slot [parity][rank] of EVERY
+// rank's window (this one included) with plain stores through the peer mappings, a system-scope release of
+// flag[parity][rank] = epoch on each peer publishes it, and the kernel then waits (system-scope acquire) until the
+// local window holds every rank's block of this epoch.  When it ends, the local window is the rank-major
+// concatenation an all-gather would have produced.  Only `count` records travel, not the block's capacity.
+// Two parities suffice: a rank can only be one exchange ahead of the slowest, because finishing exchange e needs
+// every rank's block e, which a rank sends after it has consumed exchange e-1 (stream order).
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) pack_push_kernel(BiasDev* st, HillAccepted* acc, HillAccepted* tmp, long cap,
+                                                        char* const* __restrict__ peer, int nranks, int rank,
+                                                        int parity, int epoch, unsigned long long timeout_ns) {
+  pdl_trigger();
+  pdl_wait();
+  int n = st->n_accepted;
+  if (n > cap) {
+    if (threadIdx.x == 0) st->accepted_overflow = 1;
+    n = (int)cap;
+  }
+  if (!st->accepted_sorted) cta_sort_accepted(acc, tmp, n);
+  if (threadIdx.x == 0) st->accepted_sorted = 1;
+  const size_t bw = 1 + (size_t)cap * DIM;  // the block stride the round's unpack uses
+  const size_t slot = ((size_t)parity * nranks + rank) * bw;
+  for (int p = 0; p < nranks; p++) {
+    double* dst = reinterpret_cast<double*>(peer[p] + EDM_PEER_FLAG_BYTES) + slot;
+    if (threadIdx.x == 0) dst[0] = (double)n;
+    for (int i = threadIdx.x; i < n * DIM; i += blockDim.x) dst[1 + i] = acc[i / DIM].x[i % DIM];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < nranks)
+    st_release_sys(reinterpret_cast<int*>(peer[threadIdx.x]) + parity * EDM_PEER_MAX_RANKS + rank, epoch);
+  if ((int)threadIdx.x < nranks) {
+    const int* fl = reinterpret_cast<const int*>(peer[rank]) + parity * EDM_PEER_MAX_RANKS + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(fl) != epoch) {
+      if (global_ns() - t0 > timeout_ns) {  // a peer died or fell out of step: report instead of hanging the GPU
+        st->exchange_timeout = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int DIM>
 __global__ void unpack_blocks_kernel(BiasDev* st, HillAccepted* acc, long acc_cap, const double* blocks, int nblocks,
                                      long cap) {
@@ -1469,6 +1522,10 @@ int edm_bias_check_round(edm_bias* b) {
   if (hdr.accepted_overflow) {
     set_error("accepted-hill buffer exhausted");
     return EDM_ERR_CAPACITY;
+  }
+  if (hdr.exchange_timeout) {
+    set_error("hill exchange: a peer's block did not arrive within EDM_B200_PEER_TIMEOUT seconds");
+    return EDM_ERR_COMM;
   }
   return EDM_OK;
 }
@@ -2043,6 +2100,30 @@ int edm_bias_hills_pack_dev(edm_bias_t* b, double* block, long cap, void* stream
   EDM_CUDA(cudaGetLastError());
   return EDM_OK;
 }
+
+}  // extern "C"
+
+// Internal (edm_comm.cu): the peer-window exchange of this rank's accepted hills; *blocks_out = the rank-major
+// concatenation in the local window once the kernel has finished.
+int edm_bias_hills_push_dev(edm_bias* b, edm_comm* c, long cap, cudaStream_t st, const double** blocks_out) {
+  const int parity = c->epoch & 1;
+  const int epoch = ++c->epoch;
+  HillAccepted* tmp = b->d_accepted + b->accepted_cap;
+  static const double timeout_s = getenv("EDM_B200_PEER_TIMEOUT") ? atof(getenv("EDM_B200_PEER_TIMEOUT")) : 10.0;
+  const unsigned long long timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  count_launches(1);
+  switch (b->prm.dim) {
+    case 1: EDM_CUDA(launch_pdl(pack_push_kernel<1>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, cap, (char* const*)c->d_peer, c->nranks, c->rank, parity, epoch, timeout_ns)); break;
+    case 2: EDM_CUDA(launch_pdl(pack_push_kernel<2>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, cap, (char* const*)c->d_peer, c->nranks, c->rank, parity, epoch, timeout_ns)); break;
+    default: EDM_CUDA(launch_pdl(pack_push_kernel<3>, dim3(1), dim3(512), 0, st, b->d_state, b->d_accepted, tmp, cap, (char* const*)c->d_peer, c->nranks, c->rank, parity, epoch, timeout_ns)); break;
+  }
+  EDM_CUDA(cudaGetLastError());
+  const size_t bw = edm_hill_block_doubles(b->prm.dim, cap);
+  *blocks_out = reinterpret_cast<const double*>(c->win + EDM_PEER_FLAG_BYTES) + (size_t)parity * c->nranks * bw;
+  return EDM_OK;
+}
+
+extern "C" {
 
 int edm_bias_hills_commit_dev(edm_bias_t* b, const double* blocks, int nblocks, long cap, long long est_hill_count,
                               void* stream) {

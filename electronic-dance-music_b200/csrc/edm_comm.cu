@@ -19,6 +19,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "edm_host.h"
 
@@ -95,6 +96,142 @@ static int nccl_fail(const NcclApi* a, ncclResult_t r, const char* what) {
     if (r__ != ncclSuccess) return nccl_fail((api), r__, #call);     \
   } while (0)
 
+// ---- NVLink peer windows -------------------------------------------------------------------------------------
+// What every rank tells the others about its window.  Same pid: the ranks share a process (threads driving one
+// device each) and use the raw pointer after cudaDeviceEnablePeerAccess; other pid, same host: CUDA IPC.
+struct PeerCard {
+  cudaIpcMemHandle_t handle;
+  unsigned long long ptr;
+  long long pid;
+  unsigned long long host;  // hash of the host name: ranks on another node cannot be reached this way
+  int device, ok;
+};
+
+static size_t peer_window_bytes(int nranks) {
+  return EDM_PEER_FLAG_BYTES + 2 * (size_t)nranks * EDM_PEER_SLOT_DOUBLES * sizeof(double);
+}
+
+static unsigned long long host_hash() {
+  char name[256] = {0};
+  gethostname(name, sizeof(name) - 1);
+  unsigned long long h = 1469598103934665603ULL;
+  for (const char* p = name; *p; p++) h = (h ^ (unsigned char)*p) * 1099511628211ULL;
+  return h;
+}
+
+static void peer_release(edm_comm* c) {
+  cudaSetDevice(c->device);
+  for (int r = 0; r < EDM_PEER_MAX_RANKS; r++)
+    if (c->opened[r]) {
+      cudaIpcCloseMemHandle(c->opened[r]);
+      c->opened[r] = nullptr;
+    }
+  if (c->d_peer) cudaFree(c->d_peer);
+  if (c->win) cudaFree(c->win);
+  c->d_peer = nullptr;
+  c->win = nullptr;
+  c->p2p = 0;
+}
+
+static bool peer_disabled_by_env() {
+  const char* e = getenv("EDM_B200_NO_P2P");
+  return e && atoi(e) != 0;
+}
+
+// Maps the windows described by cards[0..nranks) into this rank's device; false if any cannot be reached.
+static bool peer_map(edm_comm* c, const PeerCard* cards, char** peers) {
+  const long long me = (long long)getpid();
+  const unsigned long long host = cards[c->rank].host;
+  for (int r = 0; r < c->nranks; r++) {
+    if (!cards[r].ok || cards[r].host != host) return false;
+    if (r == c->rank) {
+      peers[r] = c->win;
+    } else if (cards[r].pid == me) {
+      if (cards[r].device != c->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, cards[r].device) != cudaSuccess || !can) return false;
+        cudaError_t e = cudaDeviceEnablePeerAccess(cards[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          return false;
+        }
+        cudaGetLastError();
+      }
+      peers[r] = reinterpret_cast<char*>(cards[r].ptr);
+    } else {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, cards[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      c->opened[r] = p;
+      peers[r] = static_cast<char*>(p);
+    }
+  }
+  return true;
+}
+
+static bool peer_alloc(edm_comm* c, PeerCard* card) {
+  memset(card, 0, sizeof(*card));
+  card->pid = (long long)getpid();
+  card->host = host_hash();
+  card->device = c->device;
+  if (c->nranks > EDM_PEER_MAX_RANKS || peer_disabled_by_env()) return false;
+  if (cudaSetDevice(c->device) != cudaSuccess) return false;
+  const size_t bytes = peer_window_bytes(c->nranks);
+  if (cudaMalloc(&c->win, bytes) != cudaSuccess || cudaMemset(c->win, 0, bytes) != cudaSuccess ||
+      cudaDeviceSynchronize() != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  card->ptr = reinterpret_cast<unsigned long long>(c->win);
+  if (cudaIpcGetMemHandle(&card->handle, c->win) != cudaSuccess) {
+    cudaGetLastError();  // no IPC on this platform: still usable between devices of one process
+    memset(&card->handle, 0, sizeof(card->handle));
+  }
+  card->ok = 1;
+  return true;
+}
+
+static bool peer_finish(edm_comm* c, char** peers) {
+  if (cudaMalloc(&c->d_peer, c->nranks * sizeof(char*)) != cudaSuccess) return false;
+  if (cudaMemcpy(c->d_peer, peers, c->nranks * sizeof(char*), cudaMemcpyHostToDevice) != cudaSuccess) return false;
+  c->p2p = 1;
+  return true;
+}
+
+// One rank per process (edm_comm_init_rank, edm_comm_from_nccl): the cards travel over the communicator itself, and
+// so does the verdict -- the window is used only if EVERY rank mapped every peer.  Collective.
+static void peer_setup_collective(edm_comm* c, const NcclApi* a) {
+  if (c->nranks < 2 || c->nranks > EDM_PEER_MAX_RANKS) return;
+  PeerCard mine;
+  peer_alloc(c, &mine);
+  std::vector<PeerCard> cards(c->nranks);
+  PeerCard* d_cards = nullptr;
+  int* d_ok = nullptr;
+  int ok = 0;
+  bool comm_fine = cudaMalloc(&d_cards, (c->nranks + 1) * sizeof(PeerCard)) == cudaSuccess &&
+                   cudaMalloc(&d_ok, sizeof(int)) == cudaSuccess;
+  if (comm_fine) {
+    cudaMemcpy(d_cards + c->nranks, &mine, sizeof(PeerCard), cudaMemcpyHostToDevice);
+    comm_fine = a->AllGather(d_cards + c->nranks, d_cards, sizeof(PeerCard), ncclChar, (ncclComm_t)c->nccl, 0) == ncclSuccess &&
+                cudaStreamSynchronize(0) == cudaSuccess;
+  }
+  if (comm_fine) {
+    cudaMemcpy(cards.data(), d_cards, c->nranks * sizeof(PeerCard), cudaMemcpyDeviceToHost);
+    char* peers[EDM_PEER_MAX_RANKS];
+    ok = mine.ok && peer_map(c, cards.data(), peers) && peer_finish(c, peers) ? 1 : 0;
+    cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    comm_fine = a->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, (ncclComm_t)c->nccl, 0) == ncclSuccess &&
+                cudaStreamSynchronize(0) == cudaSuccess;
+    if (comm_fine) cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  if (d_cards) cudaFree(d_cards);
+  if (d_ok) cudaFree(d_ok);
+  cudaGetLastError();
+  if (!comm_fine || !ok) peer_release(c);  // the all-gather path remains
+}
+
 }  // namespace edm
 
 using namespace edm;
@@ -102,6 +239,8 @@ using namespace edm;
 // pack -> all-gather; leaves the rank-major concatenation in b->xchg (gathered part) and returns it
 static int exchange_gather(edm_bias* b, edm_comm* c, long cap, cudaStream_t st, const double** blocks_out) {
   const size_t bw = edm_hill_block_doubles(b->prm.dim, cap);
+  if (c->p2p && c->nranks > 1 && bw <= (size_t)EDM_PEER_SLOT_DOUBLES)  // the blocks fit the peer window's slots
+    return edm_bias_hills_push_dev(b, c, cap, st, blocks_out);
   EDM_TRY(b->xchg.reserve((size_t)(c->nranks + 1) * bw * sizeof(double)));
   double* block = b->xchg.as<double>();
   double* gathered = block + bw;
@@ -166,6 +305,7 @@ int edm_comm_init_rank(edm_comm_t** out, const unsigned char* id, int nranks, in
       return nccl_fail(a, r, "ncclCommInitRank");
     }
     c->owned = 1;
+    peer_setup_collective(c, a);
   }
   *out = c;
   return EDM_OK;
@@ -242,6 +382,19 @@ int edm_comm_init_all(edm_comm_t** out, int ndev, const int* devices) {
     c->owned = ndev > 1;
     out[i] = c;
   }
+  if (ndev > 1 && ndev <= EDM_PEER_MAX_RANKS) {  // one process: the windows are mapped through peer access
+    std::vector<PeerCard> cards(ndev);
+    bool ok = true;
+    for (int i = 0; i < ndev; i++) ok = peer_alloc(out[i], &cards[i]) && ok;
+    for (int i = 0; i < ndev && ok; i++) {
+      char* peers[EDM_PEER_MAX_RANKS];
+      cudaSetDevice(out[i]->device);
+      ok = peer_map(out[i], cards.data(), peers) && peer_finish(out[i], peers);
+    }
+    if (!ok)
+      for (int i = 0; i < ndev; i++) peer_release(out[i]);
+    cudaGetLastError();
+  }
   return EDM_OK;
 }
 
@@ -254,12 +407,18 @@ int edm_comm_from_nccl(edm_comm_t** out, void* nccl_comm, int nranks, int rank, 
   c->rank = rank;
   c->device = device;
   c->owned = 0;
+  if (nranks > 1) {
+    EDM_TRY(ensure_device(device));
+    const NcclApi* a = nccl_api();
+    if (a) peer_setup_collective(c, a);
+  }
   *out = c;
   return EDM_OK;
 }
 
 int edm_comm_destroy(edm_comm_t* c) {
   if (!c) return EDM_OK;
+  peer_release(c);
   if (c->owned && c->nccl) {
     const NcclApi* a = nccl_api();
     if (a) {
@@ -276,6 +435,14 @@ int edm_comm_info(const edm_comm_t* c, int* nranks, int* rank, int* device) {
   if (nranks) *nranks = c->nranks;
   if (rank) *rank = c->rank;
   if (device) *device = c->device;
+  return EDM_OK;
+}
+
+// 1 when the hill exchange of this communicator runs over NVLink peer windows (every rank reached every other
+// rank's window), 0 when it is one ncclAllGather per exchange.  EDM_B200_NO_P2P=1 forces the latter.
+int edm_comm_peer_windows(const edm_comm_t* c, int* enabled) {
+  EDM_REQUIRE(c && enabled, "NULL argument");
+  *enabled = c->p2p;
   return EDM_OK;
 }
 

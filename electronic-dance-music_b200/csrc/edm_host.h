@@ -123,6 +123,7 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   // %globaltimer stamps of the last round (ns): plan phases 0-6, decide begin/end, deposit first/last, in-order begin/end
   unsigned long long stamp[16];
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
+  int exchange_timeout;  // a peer's hill block did not arrive in time (edm_bias_check reports EDM_ERR_COMM)
   unsigned long long n_pairs;
   unsigned long long n_pairs_ghost;  // of those, pairs with one ghost atom (one hill proposal instead of two)
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array
@@ -138,10 +139,24 @@ struct HostReport {
   unsigned long long n_pairs, n_calls;
 };
 
+// Peer window of the hill exchange (edm_comm.cu): a small buffer on every rank that every other rank of the node can
+// store into over NVLink (CUDA IPC between processes, peer access inside one).  Layout: 2 x 64 int flags
+// (flag[parity][source rank] = epoch of the block that source last delivered), then 2 x nranks block slots.
+#define EDM_PEER_MAX_RANKS 64
+#define EDM_PEER_FLAG_BYTES (2 * EDM_PEER_MAX_RANKS * sizeof(int))
+#define EDM_PEER_SLOT_DOUBLES (1 + 4096 * 3)  // one block of the default capacity in 3-D
+
 struct edm_comm {  // one rank's end of the hill exchange (edm_comm.cu)
   void* nccl = nullptr;  // ncclComm_t
   int nranks = 1, rank = 0, device = 0;
   int owned = 0;         // the ncclComm_t is destroyed with the handle
+  // NVLink peer window (p2p != 0): the exchange is one kernel that stores this rank's hills into every peer's window
+  // and waits for theirs -- no collective launch on the step's critical path
+  int p2p = 0;
+  char* win = nullptr;            // this rank's window
+  char** d_peer = nullptr;        // device array [nranks]: every rank's window as seen from this device
+  void* opened[EDM_PEER_MAX_RANKS] = {};  // IPC mappings to close
+  int epoch = 0;                  // exchanges issued so far (the same on every rank)
 };
 
 struct edm_bias {
@@ -220,6 +235,7 @@ int edm_bias_size_accepted(edm_bias* b, double candidates, long long est);
 // exchange = true the accepted hills of all ranks are gathered first (edm_bias_exchange_round)
 int edm_bias_launch_round(edm_bias* b, long long est, cudaStream_t st, bool exchange = true);
 int edm_bias_exchange_round(edm_bias* b, long long est, cudaStream_t st);
+int edm_bias_hills_push_dev(edm_bias* b, edm_comm* c, long cap, cudaStream_t st, const double** blocks_out);
 int edm_bias_check_round(edm_bias* b);
 int edm_host_report_ensure(edm_bias* b);
 inline long long edm_job_est(const edm_bias* b, long long est) {

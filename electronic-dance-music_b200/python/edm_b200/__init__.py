@@ -144,6 +144,7 @@ EXPORTS = {
     "edm_comm_from_nccl": (C.c_int, [C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int]),
     "edm_comm_destroy": (C.c_int, [vp]),
     "edm_comm_info": (C.c_int, [vp, c_ip, c_ip, c_ip]),
+    "edm_comm_peer_windows": (C.c_int, [vp, c_ip]),
     "edm_comm_group_start": (C.c_int, []),
     "edm_comm_group_end": (C.c_int, []),
     "edm_comm_allreduce_sum_dev": (C.c_int, [vp, vp, C.c_long, vp]),
@@ -249,6 +250,12 @@ class Comm:
         n, r, d = C.c_int(0), C.c_int(0), C.c_int(0)
         check(self.L.edm_comm_info(self.h, C.byref(n), C.byref(r), C.byref(d)))
         return dict(nranks=n.value, rank=r.value, device=d.value)
+
+    def peer_windows(self):
+        """True when the exchange runs over NVLink peer windows (one kernel), False when it is an ncclAllGather."""
+        e = C.c_int(0)
+        check(self.L.edm_comm_peer_windows(self.h, C.byref(e)))
+        return bool(e.value)
 
     def destroy(self):
         if self.h:

@@ -327,12 +327,22 @@ int edm_comm_init_all(edm_comm_t** out /* [ndev] */, int ndev, const int* device
 int edm_comm_from_nccl(edm_comm_t** out, void* nccl_comm, int nranks, int rank, int device);
 int edm_comm_destroy(edm_comm_t* comm);
 int edm_comm_info(const edm_comm_t* comm, int* nranks, int* rank, int* device);
+/* How the exchange of this communicator travels.  When every rank of the job sits on one node and can map the
+ * others' memory (CUDA IPC between processes, peer access inside one process), communicator creation also sets up
+ * an NVLink peer window per rank, and an exchange is ONE kernel: it stores this rank's accepted hills into every
+ * peer's window, publishes them with a system-scope release flag and waits for the peers' flags -- only the hills
+ * that exist travel, and no collective is launched on the step's critical path (*enabled = 1).  Otherwise, or with
+ * EDM_B200_NO_P2P=1 in the environment, it is pack -> one ncclAllGather of fixed-capacity blocks (*enabled = 0).
+ * The choice is job-wide (agreed by an all-reduce at creation), the result bit-identical either way.  A peer that
+ * never delivers raises EDM_ERR_COMM at the next edm_bias_check-style call after EDM_B200_PEER_TIMEOUT seconds
+ * (default 10) instead of hanging the GPU. */
+int edm_comm_peer_windows(const edm_comm_t* comm, int* enabled);
 int edm_comm_group_start(void);
 int edm_comm_group_end(void);
 /* in-place sum over ranks of n doubles on the device (the bias energy, when a job-wide scalar is wanted;
  * replaces the MPI_Allreduce of lib/edm_bias.cpp:925 for callers that need one) */
 int edm_comm_allreduce_sum_dev(edm_comm_t* comm, double* buf, long n, void* stream);
-/* pack -> ncclAllGather -> commit in one call, on `stream`, never synchronising the host: what
+/* pack -> all-gather (peer windows or ncclAllGather, see edm_comm_peer_windows) -> commit in one call, on `stream`, never synchronising the host: what
  * post_add_hill does between the local add_hill calls and update_height.  est_total = the job-wide
  * est_hill_count (the same on every rank); cap = records per rank in the block (the same on every rank;
  * a rank that accepted more raises EDM_ERR_CAPACITY at the next edm_bias_state-style check instead of

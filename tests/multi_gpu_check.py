@@ -1,6 +1,7 @@
 """Run under torchrun on N GPUs: every rank evaluates its own atoms' pairs, selects hills locally,
-and calls the library's own exchange (edm_bias_exchange_dev: pack -> ncclAllGather -> commit, NCCL
-called from C++ on a communicator bootstrapped with edm_comm_init_rank; torch.distributed only ships
+and calls the library's own exchange (edm_bias_exchange_dev on a communicator bootstrapped with
+edm_comm_init_rank: over NVLink peer windows -- one kernel stores the hills into every peer and waits for
+theirs -- or, with EDM_B200_NO_P2P=1, pack -> ncclAllGather -> commit; torch.distributed only ships
 the 128-byte id and compares the replicas afterwards).  Checks:
 replicas bit-identical across ranks; rank 0 equal (1e-10) to a single-rank oracle that sees the
 rank-major concatenation of all ranks' pairs."""
@@ -32,6 +33,8 @@ def main():
     dist.broadcast_object_list(uid, 0)
     comm = edm.Comm.init_rank(uid[0], world, rank, local)
     assert comm.info() == dict(nranks=world, rank=rank, device=local)
+    if rank == 0:  # how the hills travel: NVLink peer windows (one kernel) or ncclAllGather (EDM_B200_NO_P2P=1)
+        print("PEER_WINDOWS=%d" % int(comm.peer_windows()))
     d = os.path.join(tmp, "r%d" % rank)
     os.makedirs(d, exist_ok=True)
     f = os.path.join(d, "c.edm")

@@ -110,15 +110,21 @@ def test_block_layout_round_trip():
 
 
 @pytest.mark.gpu
-def test_two_gpu_replicas_match_single_rank_oracle(tmp_path):
+@pytest.mark.parametrize("transport", ["peer_windows", "nccl_allgather"])
+def test_two_gpu_replicas_match_single_rank_oracle(tmp_path, transport):
+    """Both transports of the hill exchange against the single-rank oracle: NVLink peer windows (the default on one
+    node) and the ncclAllGather path (EDM_B200_NO_P2P=1)."""
     import edm_b200
     if edm_b200.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     script = os.path.join(ROOT, "tests", "multi_gpu_check.py")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), script, str(tmp_path)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    env = dict(os.environ, EDM_B200_NO_P2P="1" if transport == "nccl_allgather" else "0", EDM_B200_PEER_TIMEOUT="20")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0
     assert "MULTI_GPU_CHECK_OK" in r.stdout
     assert "MULTI_GPU_COORD_CHECK_OK" in r.stdout
+    if transport == "nccl_allgather":
+        assert "PEER_WINDOWS=0" in r.stdout
