@@ -28,7 +28,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // before it blends (spatially ordered atoms: C3 0.36 -> 0.31 ms, C4 1.15 -> 0.86 ms; unordered atoms
 // are bound by the DRAM random-access rate either way: ~4.9 TB/s of mostly half-used 64 B bursts).
 // Measured and rejected (tools/experiments/k1_variants.sh): two atoms per thread, a software pipeline
-// with L2 prefetch of the next atom's corners (unordered 0.67 -> 1.14 ms), 64-register builds.
+// with L2 prefetch of the next atom's corners (unordered 0.67 -> 1.14 ms), 64-register builds, loading the
+// next trip's coordinates and old force one trip ahead (ordered C3 -3 %, C4 +5 %: spills).
 #ifndef EDM_FORCES_UNROLL
 #define EDM_FORCES_UNROLL 1
 #endif
@@ -37,10 +38,10 @@ __global__ void __launch_bounds__(256, (DIM == 3) ? 2 : 3) forces_kernel(GridDes
                                                      double* __restrict__ f, long fs, const int* __restrict__ mask,
                                                      int apply_mask, double* __restrict__ partial, BiasDev* st) {
   __shared__ double red[33];
-  constexpr int U = EDM_FORCES_UNROLL;
   if (blockIdx.x == 0 && threadIdx.x == 0) st->stamp[14] = global_ns();  // measurement: when the force update began
   double e = 0.0;
   const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = EDM_FORCES_UNROLL;
   for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
     double xi[U][DIM], fo[U][DIM], der[U][DIM];
     bool on[U];

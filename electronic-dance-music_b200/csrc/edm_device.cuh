@@ -184,7 +184,7 @@ __device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double*
   constexpr int W = RecW<DIM>::value;
   constexpr int NC = 1 << DIM;
   double f = 0.0;
-  if (DIM == 1) {
+  if constexpr (DIM == 1) {
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       double r[W];
@@ -204,7 +204,7 @@ __device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double*
       der[0] += tabf * ap * s * g.inv_dx[0] + td * cc;
     }
     return f;
-  }
+  } else {
   // 2-D / 3-D: every corner record first (the loads are in flight together), then ONE reciprocal per four corners:
   // 1/t_c = (product of the other three) / (product of all four).  Corners the reference treats as zero (T6) enter
   // as 1.  |t| >= 1e-7 for the others, so the product stays a normal number for any bias below 1e70; outside that
@@ -275,6 +275,7 @@ __device__ __forceinline__ double d_interp_cell(const GridDesc& g, const double*
     }
   }
   return f;
+  }
 }
 
 template <int DIM>

@@ -11,7 +11,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(os.path.dirname(HERE))
-LIB_PATH = os.path.join(PKG, "lib", "libedm_b200.so")
+# EDM_B200_LIB: another build of the same library (A/B measurements of kernel variants, tools/experiments/)
+LIB_PATH = os.environ.get("EDM_B200_LIB") or os.path.join(PKG, "lib", "libedm_b200.so")
 
 EDM_BUFFER_DBLS = 8192
 
