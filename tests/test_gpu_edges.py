@@ -274,3 +274,70 @@ def test_pair_step_on_a_periodic_cv_grid_takes_the_general_interpolation(edm, po
     res = bd.pair_step_list(x, fd, n, np.arange(n, dtype=np.int32), first, pj, do_hills=False)
     assert abs(res["energy"] - eo) <= RTOL * abs(eo)
     assert_close(fd, fo, "list forces on a periodic CV grid")
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_interpolation_with_extreme_and_near_zero_corner_values(edm, port, dim):
+    """K1's blend takes ONE reciprocal per four corners (product / product).  Corner values under the reference's
+    1e-7 zero threshold (T6, lib/grid.h:113) must drop out exactly as they do there, and values whose product leaves
+    the normal range (1e75^4) must take the per-corner division: the result stays the oracle's either way."""
+    rng = np.random.default_rng(100 + dim)
+    lo, hi, dx = [0.0] * dim, [4.0] * dim, [0.25] * dim
+    per = [1] + [0] * (dim - 1)
+    gd = edm.Grid(dim, lo, hi, dx, per, 1, 1)
+    go = port.Grid("port", dim, lo, hi, dx, per, 1, 1)
+    v0, d0 = go.get_arrays()
+    n = v0.size
+    mags = np.array([1e-9, 5e-8, 1.0000001e-7, 1e-6, 1e-3, 1.0, 1e3, 1e60, 1e75, 1e80])
+    v = mags[rng.integers(0, mags.size, n)] * rng.choice([-1.0, 1.0], n) * rng.uniform(1.0, 2.0, n)
+    d = (rng.uniform(-1, 1, size=d0.shape) * np.abs(v).reshape(-1, 1)).reshape(d0.shape)
+    go.set_arrays(v, d)
+    gd.set_arrays(v, d)
+    x = rng.uniform(0.0, 3.999, size=(40000, dim))
+    val_d, der_d = gd.eval(x)
+    val_o, der_o = go.eval(x)
+    assert np.array_equal(val_d == 0.0, val_o == 0.0)
+    # cells mix magnitudes 80 orders apart, so the yardstick is per point: the largest corner of the point's own cell
+    nn = gd.info()["n"]
+    idx = np.floor(x / 0.25).astype(np.int64)
+    stride = np.concatenate([[1], np.cumprod(nn[:-1])]).astype(np.int64)
+    corner_mag = np.zeros(x.shape[0])
+    mag = np.abs(v) + np.abs(d).max(axis=1) * 0.25
+    for c in range(1 << dim):
+        lin = np.zeros(x.shape[0], np.int64)
+        for k in range(dim):
+            i = idx[:, k] + ((c >> k) & 1)
+            if per[k]:
+                i = i % nn[k]
+            lin += i * stride[k]
+        corner_mag = np.maximum(corner_mag, mag[lin])
+    assert np.all(np.abs(val_d - val_o) <= 1e-10 * corner_mag)
+    assert np.all(np.abs(der_d - der_o).max(axis=1) <= 1e-10 * corner_mag / 0.25 * 8)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_points_on_grid_lines_land_in_the_reference_cell(edm, port, dim):
+    """The cell index is floor((x - min) / dx) with a true division in the reference (lib/grid.h:315-325, T5).  The
+    device multiplies by 1/dx and only divides when the product is within rounding of an integer: points exactly on
+    grid lines, one ulp either side, and just inside the upper edge are where that matters."""
+    rng = np.random.default_rng(7 + dim)
+    lo, hi = [0.3] * dim, [3.5] * dim
+    dx = [0.1, 0.05, 0.2][:dim]
+    per = [0] * dim
+    gd = edm.Grid(dim, lo, hi, dx, per, 1, 1)
+    go = port.Grid("port", dim, lo, hi, dx, per, 1, 1)
+    v0, d0 = go.get_arrays()
+    v = rng.uniform(0.5, 2.0, v0.size)
+    d = rng.uniform(-1, 1, size=d0.shape)
+    go.set_arrays(v, d)
+    gd.set_arrays(v, d)
+    k = rng.integers(0, 30, size=(6000, dim))
+    x = np.array(lo) + k * np.array(dx)
+    x[2000:4000] = np.nextafter(x[2000:4000], 10.0)
+    x[4000:] = np.nextafter(x[4000:], -10.0)
+    x = np.vstack([x, np.nextafter(np.array(hi), -10.0)[None, :], np.array(lo)[None, :]])
+    val_d, der_d = gd.eval(x)
+    val_o, der_o = go.eval(x)
+    assert np.array_equal(val_d == 0.0, val_o == 0.0)
+    assert_close(val_d, val_o, "value on grid lines")
+    assert_close(der_d, der_o, "derivative on grid lines")
