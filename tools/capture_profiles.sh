@@ -1,7 +1,7 @@
 #!/bin/bash
 # Evidence run on the GPU box (gpurun -- bash tools/capture_profiles.sh TAG): bench lines first (never under a
 # profiler), then ncu launch lists, then one `ncu --set full` capture per kernel of interest.  Everything lands in
-# gpurun_out/; tools/ncu_summary.py condenses the .ncu-rep files into profiles/ back in the container.
+# gpurun_out/; tools/condense_profiles.sh TAG condenses them into profiles/ back in the container.
 TAG=${1:-r02}
 O=gpurun_out
 mkdir -p $O
@@ -30,6 +30,7 @@ $NCU -k regex:block_find_kernel -s 6 -c 1 -o $O/${TAG}_block_find -f python benc
 $NCU -k regex:forces_kernel -s 6 -c 1 -o $O/${TAG}_forces_c3 -f python bench.py --workload c3_coord_2d --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:forces_kernel -s 6 -c 1 -o $O/${TAG}_forces_c3_cell -f python bench.py --workload c3_coord_2d --input-order cell --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:forces_kernel -s 6 -c 1 -o $O/${TAG}_forces_c4 -f python bench.py --workload c4_coord_3d --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+$NCU -k regex:forces_kernel -s 6 -c 1 -o $O/${TAG}_forces_c4_cell -f python bench.py --workload c4_coord_3d --input-order cell --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:round_plan_kernel -s 6 -c 1 -o $O/${TAG}_plan_c3 -f python bench.py --workload c3_coord_2d --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:round_integrals_kernel -s 6 -c 1 -o $O/${TAG}_integrals_c4 -f python bench.py --workload c4_coord_3d --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 $NCU -k regex:round_deposit_kernel -s 6 -c 1 -o $O/${TAG}_deposit_c4 -f python bench.py --workload c4_coord_3d --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1

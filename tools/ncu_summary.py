@@ -19,7 +19,8 @@ WANT = [
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active", "gpu__time_duration.sum",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
+    "dram__bytes_write.sum.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
@@ -48,10 +49,13 @@ def record_roofline(hdr, units, vals, workload, kernel, csrc, source):
         "lsu": get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")[0],
         "issue": get("smsp__issue_active.avg.pct_of_peak_sustained_active")[0],
         "fp64": get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")[0],
-        "dram": get("dram__throughput.avg.pct_of_peak_sustained_elapsed")[0],
+        "dram": None,
         "l2": get("lts__throughput.avg.pct_of_peak_sustained_elapsed")[0],
     }
     pct = {k: float(v.replace(",", "")) for k, v in pct.items() if v not in (None, "")}
+    rdp, wrp = get("dram__bytes_read.sum.pct_of_peak_sustained_elapsed")[0], get("dram__bytes_write.sum.pct_of_peak_sustained_elapsed")[0]
+    if rdp not in (None, "") and wrp not in (None, ""):  # read + write share the same pins: their percentages add
+        pct["dram"] = float(rdp.replace(",", "")) + float(wrp.replace(",", ""))
     names = {"lsu": "L1/shared-memory data pipe (l1tex LSU wavefronts)", "issue": "warp issue slots",
              "fp64": "fp64 pipe", "dram": "HBM (dram throughput)", "l2": "L2 (lts throughput)"}
     top = max(pct, key=pct.get)
@@ -61,7 +65,8 @@ def record_roofline(hdr, units, vals, workload, kernel, csrc, source):
         "csrc_hash": csrc, "source": source,
         "dram_bytes_per_launch": int(to_bytes(*rd) + to_bytes(*wr)),
         "dram_bytes_read": int(to_bytes(*rd)), "dram_bytes_write": int(to_bytes(*wr)),
-        "gpu_time_us": float(get("gpu__time_duration.sum")[0].replace(",", "")),
+        "gpu_time_us": float(get("gpu__time_duration.sum")[0].replace(",", "")) *
+                       {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(get("gpu__time_duration.sum")[1].strip(), 1.0),
         "binding": {"bound": {"dram": "hbm"}.get(top, top), "name": names[top], "pct_of_peak": pct[top],
                     "all_pct": pct, "source": source},
     }
