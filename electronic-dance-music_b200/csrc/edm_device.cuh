@@ -150,8 +150,15 @@ __device__ __forceinline__ bool d_locate(const GridDesc& g, const double* xin, C
     double t = __dsub_rn(xi, g.min[d]);
     // T5: the reference floors a true quotient.  t * (1/dx) is within 2 ulp of it, so its floor is the same unless
     // it lies that close to an integer; only then is the exactly rounded division paid for.
-    double q = t * g.inv_dx[d];
-    if (fabs(q - rint(q)) <= 8e-16 * fabs(q)) q = __ddiv_rn(t, g.dx[d]);
+    // (1-D keeps the plain division: its callers are not bound by it, and the generic 1-D routine is also the
+    // out-of-line slow path of the pair kernels, whose register budget it must not disturb.)
+    double q;
+    if constexpr (DIM == 1) {
+      q = __ddiv_rn(t, g.dx[d]);
+    } else {
+      q = t * g.inv_dx[d];
+      if (fabs(q - rint(q)) <= 8e-16 * fabs(q)) q = __ddiv_rn(t, g.dx[d]);
+    }
     long long idx = (long long)floor(q);
     int nd = g.n[d];
     long long hi = g.periodic[d] ? nd - 1 : nd - 2;

@@ -124,3 +124,40 @@ def test_nccl_is_resolved_at_run_time_and_the_exchange_needs_a_gpu(edm):
     if edm.device_count() == 0:
         with pytest.raises(edm.EdmError, match="no CUDA device"):
             edm.Comm.init_rank(uid, 1, 0, 0)
+
+
+def test_hot_kernels_keep_their_register_budget(edm):
+    """The pair kernels sit at a register cliff (64 registers for 2 CTAs/SM of 512 threads): an unrelated edit to a
+    shared device function once cost block_eval_kernel 3.4 % through 8 extra bytes of spills.  Pin what was measured."""
+    import shutil
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "-res-usage", edm.LIB_PATH], capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+
+    def find(fragment):
+        hits = [v for k, v in usage.items() if fragment in k]
+        assert hits, fragment
+        return hits[0]
+
+    budget = {  # mangled-name fragment -> (max registers, max stack bytes)
+        "17block_eval_kernel": (64, 8),
+        "17block_find_kernelILb0": (64, 32),
+        "13forces_kernelILi2": (80, 0),
+        "13forces_kernelILi3": (128, 72),
+        "22deposit1d_owner_kernelILb0": (56, 0),
+        "20round_deposit_kernelILi3": (64, 120),
+    }
+    for frag, (reg, stack) in budget.items():
+        r, s = find(frag)
+        assert r <= reg and s <= stack, "%s: %d registers, %d bytes of stack (budget %d / %d)" % (frag, r, s, reg, stack)
