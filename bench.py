@@ -836,12 +836,13 @@ def run_coord(args, rank, local_rank, world):
         main = torch.cuda.current_stream()
         ev_fork.record(main)
         side.wait_event(ev_fork)
-        edm.check(L.edm_bias_update_forces_dev(bias.h, n_atoms, x.data_ptr(), D, f_dev.data_ptr(), D, None, -1, None, stream))
-        ev_k1.record(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side):     # the selection first: launched behind the force update it waits for SM slots
             sst = side.cuda_stream
             edm.check(L.edm_bias_select_dev(bias.h, n_atoms, x.data_ptr(), D, None, None, -1, est_total, seed, step,
                                             rank * n_atoms, sst))
+        edm.check(L.edm_bias_update_forces_dev(bias.h, n_atoms, x.data_ptr(), D, f_dev.data_ptr(), D, None, -1, None, stream))
+        ev_k1.record(main)
+        with torch.cuda.stream(side):
             # the round's writers (deposit, tail) follow the force update on the main stream: nothing to join
             edm.check(L.edm_bias_round_commit_on(bias.h, main.cuda_stream))
             edm.check(L.edm_bias_energy_with_round(bias.h, energy_dev.data_ptr()))   # summed by an idle deposit CTA
@@ -869,6 +870,7 @@ def run_coord(args, rank, local_rank, world):
     launches = edm.launch_count() - launches0
     info1 = bias.round_info()
     stamps_fused = bias.round_times_us()       # device-clock stamps of the last overlapped step
+    xstamps_fused = bias.exchange_times_us()   # selection / exchange of that step, same clock
     total_ms = float(sum(e[0].elapsed_time(e[1]) for e in ev))
     # the two halves one after the other, for the breakdown only
     evb = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(5)]
@@ -969,6 +971,10 @@ def run_coord(args, rank, local_rank, world):
                 "legend": "us since the plan began: [0-6] plan phases, [7,8] decision, [9,10] first deposit taken / last "
                           "deposit done, [11,12] in-order kernel begin/end, [13] last deposit CTA left, [14] force update began, [15] in-order kernel resident",
                 "overlapped_step": [round(float(v), 2) for v in stamps_fused],
+                "overlapped_step_exchange": {
+                    "legend": "same clock: selection began / its last CTA left / exchange kernel past its predecessor / "
+                              "own block delivered to every peer / every peer's block in",
+                    "us": [round(float(v), 2) for v in xstamps_fused]},
                 "back_to_back": [round(float(v), 2) for v in bias.round_times_us()]},
             "batched_deposit": dep_hills_per_s,
             "hills": {"rounds_parallel": info1["parallel"] - info0["parallel"],

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) select_kernel(long n, const double* __res
                                                      long cap) {
   pdl_trigger();
   pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->stamp2[0] = global_ns();
   long stride = (long)gridDim.x * blockDim.x;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     if (apply_mask >= 0 && !(apply_mask & mask[i])) continue;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) select_kernel(long n, const double* __res
       }
     }
   }
+  if (threadIdx.x == 0) atomicMax(&st->stamp2[1], global_ns());  // measurement: when the last CTA left
 }
 
 // ------------------------------------------------------------------ K4: the hill round
@@ -1263,24 +1265,57 @@ __global__ void __launch_bounds__(512) pack_push_kernel(BiasDev* st, HillAccepte
                                                         int parity, int epoch, unsigned long long timeout_ns) {
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x == 0) st->stamp2[2] = global_ns();
+  __shared__ unsigned long long s_key[512];
   int n = st->n_accepted;
   if (n > cap) {
     if (threadIdx.x == 0) st->accepted_overflow = 1;
     n = (int)cap;
   }
-  if (!st->accepted_sorted) cta_sort_accepted(acc, tmp, n);
-  if (threadIdx.x == 0) st->accepted_sorted = 1;
   const size_t bw = 1 + (size_t)cap * DIM;  // the block stride the round's unpack uses
   const size_t slot = ((size_t)parity * nranks + rank) * bw;
-  for (int p = 0; p < nranks; p++) {
-    double* dst = reinterpret_cast<double*>(peer[p] + EDM_PEER_FLAG_BYTES) + slot;
-    if (threadIdx.x == 0) dst[0] = (double)n;
-    for (int i = threadIdx.x; i < n * DIM; i += blockDim.x) dst[1 + i] = acc[i / DIM].x[i % DIM];
+  if (n <= (int)blockDim.x && n <= 512) {
+    // the usual few hundred hills: one record per thread, held in registers; its rank among the keys (shared
+    // memory, every thread reads the same word at the same time) is where it goes -- in every peer's window and in
+    // the local list -- without a pass through global memory in between
+    HillAccepted rec;
+    const bool have = (int)threadIdx.x < n;
+    if (have) {
+      rec = acc[threadIdx.x];
+      s_key[threadIdx.x] = rec.key;
+    }
+    __syncthreads();
+    if (have) {
+      int r = threadIdx.x;
+      if (!st->accepted_sorted) {
+        r = 0;
+        for (int j = 0; j < n; j++) r += (s_key[j] < rec.key);
+      }
+      for (int p = 0; p < nranks; p++) {
+        double* dst = reinterpret_cast<double*>(peer[p] + EDM_PEER_FLAG_BYTES) + slot + 1 + (size_t)r * DIM;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) dst[d] = rec.x[d];
+      }
+      acc[r] = rec;  // every record was read before the barrier above
+    }
+    if (threadIdx.x == 0)
+      for (int p = 0; p < nranks; p++) reinterpret_cast<double*>(peer[p] + EDM_PEER_FLAG_BYTES)[slot] = (double)n;
+    __syncthreads();
+    if (threadIdx.x == 0) st->accepted_sorted = 1;
+  } else {
+    if (!st->accepted_sorted) cta_sort_accepted(acc, tmp, n);
+    if (threadIdx.x == 0) st->accepted_sorted = 1;
+    for (int p = 0; p < nranks; p++) {
+      double* dst = reinterpret_cast<double*>(peer[p] + EDM_PEER_FLAG_BYTES) + slot;
+      if (threadIdx.x == 0) dst[0] = (double)n;
+      for (int i = threadIdx.x; i < n * DIM; i += blockDim.x) dst[1 + i] = acc[i / DIM].x[i % DIM];
+    }
   }
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < nranks)
     st_release_sys(reinterpret_cast<int*>(peer[threadIdx.x]) + parity * EDM_PEER_MAX_RANKS + rank, epoch);
+  if (threadIdx.x == 0) st->stamp2[3] = global_ns();
   if ((int)threadIdx.x < nranks) {
     const int* fl = reinterpret_cast<const int*>(peer[rank]) + parity * EDM_PEER_MAX_RANKS + threadIdx.x;
     const unsigned long long t0 = global_ns();
@@ -1292,6 +1327,7 @@ __global__ void __launch_bounds__(512) pack_push_kernel(BiasDev* st, HillAccepte
     }
   }
   __syncthreads();
+  if (threadIdx.x == 0) st->stamp2[4] = global_ns();
 }
 
 template <int DIM>
@@ -1902,6 +1938,13 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
   }
   EDM_CUDA(cudaEventRecord(b->ev_fork, st));
   EDM_CUDA(cudaStreamWaitEvent(b->st_side, b->ev_fork, 0));
+  // The selection goes in FIRST: it is a few microseconds of hashing, but launched behind the force update its CTAs
+  // wait ~20 us for SM slots among the force CTAs and everything behind it (exchange, plan, integrals, decision)
+  // starts that much later -- on several GPUs, where the round is as long as the force update, that is step time.
+  const long long est = edm_job_est(b, n);
+  EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
+  EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
+  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, est, seed, step, 0, b->st_side));
   b->forces_event = b->ev_forces;
   // the energy sum (a one-CTA kernel) goes behind the round's deposit, not between it and the force update
   if (n > 0) EDM_TRY(edm_bias_update_forces_dev(b, n, x, xstride, f, fstride, mask, apply_mask, nullptr, stream));
@@ -1909,10 +1952,6 @@ int edm_bias_step_coords_dev(edm_bias_t* b, long n, const double* x, long xstrid
     EDM_CUDA(cudaEventRecord(b->ev_forces, st));
     b->forces_event = nullptr;
   }
-  const long long est = edm_job_est(b, n);
-  EDM_TRY(edm_bias_size_accepted(b, (double)n, est));
-  EDM_TRY(edm_bias_reset_accepted(b, b->st_side));
-  EDM_TRY(select_launch(b, n, x, xstride, runiform, mask, apply_mask, est, seed, step, 0, b->st_side));
   // the round's writers (deposit, in-order tail) follow the force update on the caller's stream; nothing to join
   b->commit_stream = st;
   b->commit_stream_set = 1;
@@ -2008,6 +2047,18 @@ int edm_bias_round_times_us(edm_bias_t* b, double* out13) {
   BiasDev hdr;
   EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 16; i++) out13[i] = ((double)hdr.stamp[i] - (double)hdr.stamp[0]) * 1e-3;
+  return EDM_OK;
+}
+
+// Selection and exchange of the last round, us relative to the plan's begin (the same origin as
+// edm_bias_round_times_us): [0] selection began, [1] its last CTA left, [2] exchange kernel past its predecessor,
+// [3] own block delivered to every peer, [4] every peer's block in.  out holds 5 doubles.
+int edm_bias_exchange_times_us(edm_bias_t* b, double* out5) {
+  EDM_REQUIRE(b && out5, "NULL argument");
+  EDM_TRY(ensure_device(b->device));
+  BiasDev hdr;
+  EDM_CUDA(cudaMemcpy(&hdr, b->d_state, offsetof(BiasDev, overflow), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; i++) out5[i] = ((double)hdr.stamp2[i] - (double)hdr.stamp[0]) * 1e-3;
   return EDM_OK;
 }
 

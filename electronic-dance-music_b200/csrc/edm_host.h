@@ -124,6 +124,9 @@ struct BiasDev {  // lives in HBM; mirrors the mutable members of EDMBias, lib/e
   unsigned long long stamp[16];
   int round_epoch; // value a finished hill leaves in hill_done[]: one more per parallel round
   int exchange_timeout;  // a peer's hill block did not arrive in time (edm_bias_check reports EDM_ERR_COMM)
+  // more %globaltimer stamps (ns): [0] selection began, [1] selection's last CTA left, [2] exchange kernel past its
+  // predecessor, [3] own block delivered to every peer, [4] every peer's block in (edm_bias_exchange_times_us)
+  unsigned long long stamp2[8];
   unsigned long long n_pairs;
   unsigned long long n_pairs_ghost;  // of those, pairs with one ghost atom (one hill proposal instead of two)
   double overflow[EDM_BUFFER_DBLS + 8];  // T19: slack for the D=3 write one record past the array

@@ -129,6 +129,7 @@ EXPORTS = {
     "edm_bias_profile_pair_ms": (C.c_int, [vp, c_dp, c_dp]),
     "edm_bias_profile_e2e_ms": (C.c_int, [vp, c_dp, c_dp, c_dp, c_dp]),
     "edm_bias_round_times_us": (C.c_int, [vp, c_dp]),
+    "edm_bias_exchange_times_us": (C.c_int, [vp, c_dp]),
     "edm_host_pin": (C.c_int, [vp, C.c_size_t]),
     "edm_host_unpin": (C.c_int, [vp]),
     "edm_pair_list_set": (C.c_int, [vp, C.c_long, c_ip, C.POINTER(C.c_long), c_ip]),
@@ -523,6 +524,11 @@ class Bias:
     def round_times_us(self):
         out = np.zeros(16)
         check(self.L.edm_bias_round_times_us(self.h, _dp(out)))
+        return out
+
+    def exchange_times_us(self):
+        out = np.zeros(5)
+        check(self.L.edm_bias_exchange_times_us(self.h, _dp(out)))
         return out
 
     def round_info(self):

@@ -385,6 +385,10 @@ int edm_bias_profile_e2e_ms(edm_bias_t* b, double* x_up_ms, double* kernels_ms, 
  * [15] the in-order kernel became resident (before it waits for its predecessor).
  * out holds 16 doubles.  Synchronises on a small copy. */
 int edm_bias_round_times_us(edm_bias_t* b, double* out16);
+/* The same clock for the selection and the exchange that fed that round: [0] selection began, [1] its last CTA
+ * left, [2] the exchange kernel got past its predecessor, [3] this rank's block delivered to every peer, [4] every
+ * peer's block in (peer-window transport; the ncclAllGather path leaves [2..4] untouched).  out holds 5 doubles. */
+int edm_bias_exchange_times_us(edm_bias_t* b, double* out5);
 
 /* How the hill rounds so far ran.  `parallel`: planned, integrated and deposited all hills at once.
  * `split`: the hills before the one at which the running sum reaches bias_per_step went in at once,
