@@ -955,6 +955,8 @@ def run_coord(args, rank, local_rank, world):
         grid_bytes = n_pts * (1 + D) * 8
         alg = 24 * D * n_atoms + min(n_atoms * (2 ** D) * (1 + D) * 8, grid_bytes)   # SURVEY 8(d), per launch
         achieved = alg / (k1 * 1e-3) / 1e9
+        # the capture on record depends on how the atoms were ordered: random order under the workload's own name
+        roof_key = args.workload if args.input_order == "random" else "%s@%s" % (args.workload, args.input_order)
         out = {
             "metric": "CV bias+force evals/sec", "value": evals / (total_ms * 1e-3), "unit": "evals/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
@@ -982,9 +984,9 @@ def run_coord(args, rank, local_rank, world):
                       "rounds_in_order": info1["in_order"] - info0["in_order"]},
             "roofline": {"bound": "hbm", "kernel": "forces_kernel<%d>" % D, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[0],
-                         "traffic_source": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[2],
-                         "binding_resource": ncu_roofline(args.workload, "forces_kernel<%d>" % D)[1],
+                         "traffic": ncu_roofline(roof_key, "forces_kernel<%d>" % D)[0],
+                         "traffic_source": ncu_roofline(roof_key, "forces_kernel<%d>" % D)[2],
+                         "binding_resource": ncu_roofline(roof_key, "forces_kernel<%d>" % D)[1],
                          "peak_source": peak_src,
                          "kernel_ms": k1, "algorithmic_bytes_per_launch": alg,
                          "note": "kernel_ms spans forces_kernel + the 1-CTA energy sum (CUDA events on the launch stream)"},

@@ -24,9 +24,9 @@ sum() { # capture-name [workload kernel]...
 sum block_eval c2_pair_rdf block_eval_kernel c5_pair_rdf_backlog block_eval_kernel c2_pair_rdf_local_tempering block_eval_kernel c2_one_box block_eval_kernel
 sum block_find
 sum forces_c3 c3_coord_2d "forces_kernel<2>"
-sum forces_c3_cell
+sum forces_c3_cell "c3_coord_2d@cell" "forces_kernel<2>"
 sum forces_c4 c4_coord_3d "forces_kernel<3>"
-sum forces_c4_cell
+sum forces_c4_cell "c4_coord_3d@cell" "forces_kernel<3>"
 sum plan_c3
 sum integrals_c4
 sum deposit_c4
