@@ -32,6 +32,10 @@ import time
 
 import numpy as np
 
+# Peer-window exchange: how long a rank's exchange kernel waits for a peer's hills before it reports EDM_ERR_COMM
+# (library default 10 s).  Ranks of a benchmark run can sit in set-up code far apart; give them a minute.
+os.environ.setdefault("EDM_B200_PEER_TIMEOUT", "60")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "electronic-dance-music_b200", "python"))
 
@@ -536,6 +540,7 @@ def run_gpu(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()   # the first exchange waits for every rank's hills: ranks that set up at different speeds meet here first
     clocks = ClockSampler(local_rank)
     clocks.start()
     step_no = 0
@@ -848,6 +853,7 @@ def run_coord(args, rank, local_rank, world):
             edm.check(L.edm_bias_energy_with_round(bias.h, energy_dev.data_ptr()))   # summed by an idle deposit CTA
             edm.check(L.edm_bias_exchange_dev(bias.h, comm.h, HILL_CAP, est_total, sst))
 
+    barrier()   # the first exchange waits for every rank's hills: ranks that set up at different speeds meet here first
     clocks = ClockSampler(local_rank)
     clocks.start()
     step_no = 0
