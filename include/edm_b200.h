@@ -317,7 +317,9 @@ int edm_bias_round_after(edm_bias_t* b, void* event);
  *     means (MPI_Bcast in a LAMMPS build, a torch.distributed broadcast in bench.py), every rank then
  *     calls edm_comm_init_rank; or edm_comm_init_file, which passes the id through a file all ranks see;
  *   - one process driving several devices: edm_comm_init_all (ncclCommInitAll);
- *   - an ncclComm_t the application already owns: edm_comm_from_nccl (borrowed, never destroyed here). */
+ *   - an ncclComm_t the application already owns: edm_comm_from_nccl (borrowed, never destroyed here).
+ * Creating a communicator of more than one rank is COLLECTIVE: every rank must make the call (the NVLink peer
+ * windows are set up and agreed on over the communicator itself, see edm_comm_peer_windows). */
 #define EDM_COMM_ID_BYTES 128
 int edm_comm_nccl_version(int* version);
 int edm_comm_unique_id(unsigned char* id /* [EDM_COMM_ID_BYTES] */);
