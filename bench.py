@@ -56,12 +56,28 @@ SEED = 20261018
 NCU_ROOFLINE_JSON = os.path.join(ROOT, "profiles", "ncu_roofline.json")
 
 
-def csrc_hash():
-    """sha1 over the CUDA sources of the build (file names + contents, sorted)."""
-    d = os.path.join(ROOT, "electronic-dance-music_b200", "csrc")
+def _csrc_dir():
+    return os.path.join(ROOT, "electronic-dance-music_b200", "csrc")
+
+
+def kernel_unit(kernel):
+    """The .cu file that defines `kernel` (template arguments ignored), or None."""
+    base = kernel.split("<")[0]
+    d = _csrc_dir()
+    for name in sorted(os.listdir(d)):
+        if name.endswith(".cu") and (" " + base + "(") in open(os.path.join(d, name)).read():
+            return name
+    return None
+
+
+def csrc_hash(kernel=None):
+    """sha1 over CUDA sources (file names + contents, sorted): the whole csrc/ tree, or -- for a kernel -- the
+    translation unit that defines it plus every header, i.e. exactly what that kernel is compiled from."""
+    d = _csrc_dir()
+    unit = kernel_unit(kernel) if kernel else None
     h = hashlib.sha1()
     for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".h")):
+        if name.endswith((".cuh", ".h")) or (name.endswith(".cu") and (unit is None or name == unit)):
             h.update(name.encode())
             h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
@@ -73,9 +89,9 @@ def ncu_roofline(workload, kernel):
         rec = json.load(open(NCU_ROOFLINE_JSON))[workload][kernel]
     except Exception:
         return None, None, "no ncu capture on record for this kernel (profiles/ncu_roofline.json)"
-    if rec.get("csrc_hash") != csrc_hash():
-        return None, None, ("ncu capture on record (%s) was taken on csrc %s, this build is %s: not reported"
-                            % (rec.get("source"), rec.get("csrc_hash"), csrc_hash()))
+    if rec.get("csrc_hash") != csrc_hash(kernel):
+        return None, None, ("ncu capture on record (%s) was taken on sources %s, this build's are %s: not reported"
+                            % (rec.get("source"), rec.get("csrc_hash"), csrc_hash(kernel)))
     return rec.get("dram_bytes_per_launch"), rec.get("binding"), rec.get("source")
 
 
@@ -701,7 +717,7 @@ def run_gpu(args, rank, local_rank, world):
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "search_kernel_ms": float(np.mean(find_ms)), "pair_kernels_ms": float(np.mean(pair_ms)),
                          "bricks": list(info["bricks"]), "fallbacks": info["fallbacks"],
-                         "traffic_source": traffic_src, "binding_resource": binding, "csrc_hash": csrc_hash(),
+                         "traffic_source": traffic_src, "binding_resource": binding, "csrc_hash": csrc_hash("block_eval_kernel"),
                          "note": "not HBM bound by design (SURVEY 8d: 2.9 B/pair of compulsory traffic)"},
             "e2e": {"value": e2e_pairs_all / e2e_s, "unit": "evals/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + 32,
@@ -1018,7 +1034,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--csrc-hash", action="store_true", help="print the hash of the csrc/ tree and exit")
+    ap.add_argument("--csrc-hash", action="store_true", help="print the hash of the csrc/ tree and of every translation unit, and exit")
     ap.add_argument("--input-order", default="random", choices=["random", "cell", "strip"],
                     help="coordinate workloads: order of the caller's atom array (see run_coord.ordered)")
     ap.add_argument("--workload", default="c2_pair_rdf",
@@ -1026,8 +1042,16 @@ def main():
                     sorted(COORD_WORKLOADS),
                     help="c2_pair_rdf is the benchmark (BASELINE.json configs[1]); the others are the remaining configs")
     args = ap.parse_args()
-    if args.csrc_hash:
+    if args.csrc_hash:   # first line: the whole tree; then one line per translation unit (unit + headers)
         print(csrc_hash())
+        for name in sorted(os.listdir(_csrc_dir())):
+            if name.endswith(".cu"):
+                h = hashlib.sha1()
+                for n2 in sorted(os.listdir(_csrc_dir())):
+                    if n2.endswith((".cuh", ".h")) or n2 == name:
+                        h.update(n2.encode())
+                        h.update(open(os.path.join(_csrc_dir(), n2), "rb").read())
+                print(name, h.hexdigest()[:16])
         return
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

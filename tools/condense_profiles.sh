@@ -5,7 +5,7 @@
 TAG=${1:-r02}
 O=gpurun_out
 P=profiles
-H=$(cat $O/${TAG}_csrc_hash.txt)
+H=$O/${TAG}_csrc_hash.txt   # ncu_summary.py picks the line of the kernel's translation unit
 cp $O/${TAG}_bench_*.json $O/${TAG}_launches_*.csv $P/ 2>/dev/null
 sum() { # capture-name [workload kernel]...
   rep=$O/${TAG}_$1.ncu-rep

@@ -42,7 +42,24 @@ def to_bytes(value, unit):
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 
 
+def unit_hash(hash_file_or_value, kernel):
+    """The hash bench.py compares against for `kernel`: the line of its translation unit in the file written by
+    `python bench.py --csrc-hash` on the snapshot that ran (first line = whole tree, kept for old files)."""
+    if not os.path.exists(hash_file_or_value):
+        return hash_file_or_value
+    sys.path.insert(0, ROOT)
+    import bench
+    unit = bench.kernel_unit(kernel)
+    lines = open(hash_file_or_value).read().split("\n")
+    for ln in lines[1:]:
+        parts = ln.split()
+        if len(parts) == 2 and parts[0] == unit:
+            return parts[1]
+    return lines[0].strip()
+
+
 def record_roofline(hdr, units, vals, workload, kernel, csrc, source):
+    csrc = unit_hash(csrc, kernel)
     get = lambda k: (vals[hdr.index(k)], units[hdr.index(k)]) if k in hdr else (None, None)
     rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
     pct = {
@@ -81,7 +98,7 @@ def main():
     roof = sys.argv[sys.argv.index("--roofline") + 1:] if "--roofline" in sys.argv else None
     print("# %s  (ncu --set full --clock-control none, one launch; values as ncu reports them)" % rep)
     if roof:
-        print("# csrc tree %s" % roof[2])
+        print("# sources %s (%s)" % (unit_hash(roof[2], roof[1]), roof[1]))
     for vals in rows[2:]:
         for w in WANT:
             if w in hdr:
