@@ -56,3 +56,21 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_roofline_record_is_keyed_by_the_sources_of_its_kernel():
+    """bench.py reports ncu traffic / binding resource only for a capture taken on the sources the kernel is compiled
+    from (its translation unit + every header): a change elsewhere in csrc/ must not silence it, a change there must."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.kernel_unit("block_eval_kernel") == "edm_pair.cu"
+    assert bench.kernel_unit("forces_kernel<2>") == "edm_bias.cu"
+    assert bench.kernel_unit("no_such_kernel") is None
+    h_pair, h_bias, h_tree = bench.csrc_hash("block_eval_kernel"), bench.csrc_hash("forces_kernel<3>"), bench.csrc_hash()
+    assert len({h_pair, h_bias, h_tree}) == 3
+    rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_roofline.json")))
+    traffic, binding, note = bench.ncu_roofline("c2_pair_rdf", "block_eval_kernel")
+    if rec["c2_pair_rdf"]["block_eval_kernel"]["csrc_hash"] == h_pair:
+        assert traffic and binding["bound"] in ("lsu", "issue", "fp64", "hbm", "l2")
+    else:   # the sources moved on since the capture (tools/capture_roofline.sh refreshes it): nothing may be reported
+        assert traffic is None and binding is None and "not reported" in note
