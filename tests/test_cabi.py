@@ -92,14 +92,39 @@ def test_product_never_touches_the_oracle():
     assert not bad, bad
 
 
-def _build_c_example(tmp_path):
-    exe = tmp_path / "c_abi_minimal"
+def _build_c_example(tmp_path, name="c_abi_minimal"):
+    exe = tmp_path / name
     libdir = os.path.join(ROOT, "electronic-dance-music_b200", "lib")
     cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "c_abi_minimal.c"), "-L" + libdir, "-ledm_b200", "-Wl,-rpath," + libdir, "-lm",
+           os.path.join(ROOT, "examples", name + ".c"), "-L" + libdir, "-ledm_b200", "-Wl,-rpath," + libdir, "-lm",
            "-o", str(exe)]
     subprocess.check_call(cmd)
     return exe
+
+
+def test_multi_gpu_c_example_builds(edm, tmp_path):
+    """The one-process-per-GPU recipe in plain C (communicator through a file, edm_bias_set_comm, the single-rank
+    host-buffer step) compiles against the header alone."""
+    assert os.path.exists(_build_c_example(tmp_path, "c_abi_multi_gpu"))
+
+
+@pytest.mark.gpu
+def test_multi_gpu_c_example_runs_and_replicas_agree(edm, tmp_path):
+    """One rank on one GPU; with two or more devices visible also two processes, whose replicas must print the
+    same cum_bias and the same checksum of the bias to the last digit."""
+    exe = str(_build_c_example(tmp_path, "c_abi_multi_gpu"))
+    r = subprocess.run([exe, "0", "1", str(tmp_path / "rv1")], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "transport none" in r.stdout
+    if edm.device_count() >= 2:
+        rv = str(tmp_path / "rv2")
+        procs = [subprocess.Popen([exe, str(k), "2", rv], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for k in range(2)]
+        outs = [p.communicate(timeout=300) for p in procs]
+        print(outs)
+        assert all(p.returncode == 0 for p in procs)
+        tails = [o[0].strip().split(" steps ")[1] for o in outs]   # steps, hills, cum_bias, checksum
+        assert tails[0] == tails[1], tails
 
 
 def test_c_example_builds_against_the_header_and_library(edm, tmp_path):
